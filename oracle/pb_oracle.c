@@ -1,0 +1,672 @@
+/*
+ * oracle/pb_oracle.c — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+ *
+ * CPU restatement of the reference's instance-grouping path
+ *   PB_lib.binary_cluster  (lib/PB_lib/src/pbnet/cluster.cu:16-119)
+ * step by step, in plain C with exact fp32 arithmetic (explicit fmaf, compiled with
+ * -ffp-contract=off).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this file; the shipped library never links it.
+ *
+ * Two entry points with identical outputs:
+ *   pb_oracle_literal  — O(n^2), no acceleration structure: the plainest possible transcription
+ *                        (materialised neighbour lists, level-synchronous BFS, brute-force 1-NN).
+ *   pb_oracle_grid     — same semantics; a uniform grid only ENUMERATES candidates, the accept
+ *                        test is the exact predicate, so outputs are bit-identical to _literal.
+ *
+ * Pinning status: cross-checked against the compiled reference (oracle/_ref, built from
+ * /root/reference by oracle/build_ref.py) on the GPU box — see tests/test_ref_crosscheck.py and
+ * the committed fixtures under tests/golden/.
+ *
+ * Reference map (file:line under /root/reference/lib/PB_lib/src/pbnet/):
+ *   predicate            binary_cuda_functions.cu:305-308 (+ SASS FMA contraction), :85, :160-161
+ *   degree / den_queue   binary.cu:71-103, binary_cuda_functions.cu:29-89
+ *   HP rule              binary_cuda_functions.cu:175-186
+ *   BFS clustering       binary.cu:154-217, binary_cuda_functions.cu:197-215
+ *   fragment filter      binary.cu:219-268, binary_cuda_functions.cu:249-256
+ *   LP 1-NN assignment   binary.cu:270-358, binary_cuda_functions.cu:258-302
+ *   centres              binary.cu:360-415, binary_cuda_functions.cu:217-246
+ *   segment loop         cluster.cu:57-118
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PB_OK 0
+#define PB_ERR_ARG 1
+#define PB_ERR_NOMEM 2
+
+/* binary.cu:229 */
+static const float k_mean_count[18] = {3917.0f, 12056.0f, 2303.0f, 8331.0f, 3948.0f, 3166.0f,
+                                       5629.0f, 11719.0f, 1003.0f, 3317.0f, 4912.0f, 10221.0f,
+                                       3889.0f, 4136.0f,  2120.0f, 945.0f,  3967.0f, 2589.0f};
+
+/* binary_cuda_functions.cu:305-308 as nvcc compiles it: FADD,FMUL,FADD,FFMA,FADD,FFMA */
+static inline float sqd(float x1, float y1, float z1, float x2, float y2, float z2) {
+    float dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
+    float t = dx * dx;
+    t = fmaf(dy, dy, t);
+    return fmaf(dz, dz, t);
+}
+
+typedef struct {
+    int64_t pair_tests; /* candidate tests in the degree pass */
+    int64_t sum_deg;    /* sum of degrees */
+    int64_t n_hp;       /* number of HPs */
+    int64_t n_noise;    /* points entering LP assignment */
+    int64_t nn_tests;   /* candidate tests in the 1-NN pass */
+} pb_oracle_stats;
+
+/* ---------------------------------------------------------------------------------------------
+ * shared tail: fragment filter (binary.cu:219-268) on one segment.
+ * ids hold raw ids in [start, start+num_cluster) or -1.  Returns number of survivors.
+ * ------------------------------------------------------------------------------------------- */
+static int filter_segment(int n, const int *sem, int *ids, int num_cluster, int start, float para_f,
+                          int *clt_sem_out /* append target */, int *n_clt_sem) {
+    if (num_cluster == 0) return 0;
+    int *clt_semv = (int *)calloc(num_cluster, sizeof(int));
+    int *clt_num = (int *)calloc(num_cluster, sizeof(int));
+    int *remap = (int *)malloc(sizeof(int) * num_cluster);
+    for (int i = 0; i < n; i++) { /* :241-247 — class = class of the highest-index member */
+        int c = ids[i];
+        if (c != -1) {
+            clt_num[c - start]++;
+            clt_semv[c - start] = sem[i];
+        }
+    }
+    int kept = 0;
+    for (int i = 0; i < num_cluster; i++) { /* :252-264 */
+        int cur_sem = clt_semv[i] - 2;
+        float cur_mean_count = k_mean_count[cur_sem] * para_f; /* fp32 multiply */
+        if ((float)clt_num[i] < cur_mean_count) {
+            remap[i] = -1;
+        } else {
+            remap[i] = start + kept;
+            clt_sem_out[(*n_clt_sem)++] = clt_semv[i];
+            kept++;
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (ids[i] != -1) ids[i] = remap[ids[i] - start]; /* net effect of repeated shift_con_clt */
+    free(clt_semv);
+    free(clt_num);
+    free(remap);
+    return kept;
+}
+
+/* centres (binary_cuda_functions.cu:217-246): sequential running mean, IEEE division */
+static void centres_segment(int n, const float *x, const float *y, const float *z, const int *ids,
+                            int num_cluster, int start, float *center_out, int *n_center) {
+    float *mx = (float *)calloc(num_cluster, sizeof(float));
+    float *my = (float *)calloc(num_cluster, sizeof(float));
+    float *mz = (float *)calloc(num_cluster, sizeof(float));
+    int *cnt = (int *)calloc(num_cluster, sizeof(int));
+    for (int i = 0; i < n; i++) {
+        int c = ids[i];
+        if (c < start || c >= start + num_cluster) continue;
+        int k = c - start;
+        cnt[k]++;
+        float N = (float)cnt[k];
+        mx[k] = mx[k] + (x[i] - mx[k]) / N;
+        my[k] = my[k] + (y[i] - my[k]) / N;
+        mz[k] = mz[k] + (z[i] - mz[k]) / N;
+    }
+    for (int k = 0; k < num_cluster; k++) {
+        center_out[(*n_center)++] = mx[k];
+        center_out[(*n_center)++] = my[k];
+        center_out[(*n_center)++] = mz[k];
+    }
+    free(mx);
+    free(my);
+    free(mz);
+    free(cnt);
+}
+
+/* =============================================================================================
+ * LITERAL variant (O(n^2))
+ * =========================================================================================== */
+static int literal_segment(int n, const float *x, const float *y, const float *z, const float *xo,
+                           const float *yo, const float *zo, const int *sem, const float *radius,
+                           const int *min_pts, float para_f, int nv_flag, int *ids, int *den,
+                           int acc, int *clt_sem_out, int *n_clt_sem, pb_oracle_stats *st) {
+    /* degree + neighbour lists (binary.cu:71-128) */
+    int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (n + 1));
+    int *deg = (int *)malloc(sizeof(int) * n);
+    for (int u = 0; u < n; u++) {
+        float r = radius[sem[u] - 2];
+        float r2 = r * r;
+        int ans = 0;
+        for (int v = 0; v < n; v++) ans += (sqd(x[u], y[u], z[u], x[v], y[v], z[v]) <= r2);
+        deg[u] = ans - 1; /* :88 */
+        den[u] = deg[u];
+    }
+    start[0] = 0;
+    for (int u = 0; u < n; u++) start[u + 1] = start[u] + deg[u];
+    int *nbr = (int *)malloc(sizeof(int) * (start[n] > 0 ? start[n] : 1));
+    for (int u = 0; u < n; u++) {
+        float r = radius[sem[u] - 2];
+        float r2 = r * r;
+        int64_t p = start[u];
+        for (int v = 0; v < n; v++)
+            if (v != u && sqd(x[u], y[u], z[u], x[v], y[v], z[v]) <= r2) nbr[p++] = v;
+    }
+    if (st) {
+        st->pair_tests += (int64_t)n * n;
+        st->sum_deg += start[n];
+    }
+    /* HP rule (binary_cuda_functions.cu:175-186) */
+    int *member = (int *)malloc(sizeof(int) * n);
+    for (int u = 0; u < n; u++) {
+        member[u] = (deg[u] >= min_pts[sem[u] - 2]) ? 0 : 2;
+        if (st && member[u] == 0) st->n_hp++;
+    }
+    /* identify_clusters + bfs_sem (binary.cu:154-217): level-synchronous boolean frontier */
+    unsigned char *visited = (unsigned char *)malloc(n);
+    unsigned char *frontier = (unsigned char *)malloc(n);
+    unsigned char *next = (unsigned char *)malloc(n);
+    int cluster = acc;
+    for (int u = 0; u < n; u++) {
+        if (ids[u] == -1 && member[u] == 0) {
+            memset(visited, 0, n);
+            memset(frontier, 0, n);
+            frontier[u] = 1;
+            int nf = 1;
+            while (nf > 0) {
+                memcpy(next, frontier, n);
+                for (int v = 0; v < n; v++) {
+                    if (!frontier[v]) continue;
+                    next[v] = 0;
+                    visited[v] = 1;
+                }
+                for (int v = 0; v < n; v++) {
+                    if (!frontier[v]) continue;
+                    if (member[v] != 0) continue;
+                    for (int64_t i = start[v]; i < start[v + 1]; i++)
+                        if (!visited[nbr[i]]) next[nbr[i]] = 1;
+                }
+                nf = 0;
+                for (int v = 0; v < n; v++) {
+                    frontier[v] = next[v];
+                    nf += next[v];
+                }
+            }
+            int sem_cur = sem[u];
+            for (int v = 0; v < n; v++) {
+                if (visited[v] && sem[v] == sem_cur) {
+                    ids[v] = cluster; /* overwrites earlier labels of border LPs */
+                    if (member[v] != 0) member[v] = 1;
+                }
+            }
+            cluster++;
+        }
+    }
+    free(visited);
+    free(frontier);
+    free(next);
+    free(nbr);
+    free(start);
+    free(deg);
+    free(member);
+    /* filter */
+    int K = filter_segment(n, sem, ids, cluster - acc, acc, para_f, clt_sem_out, n_clt_sem);
+    /* assigned_LPs (binary.cu:270-358, kernel :258-302) */
+    if (nv_flag) {
+        int n_lab = 0;
+        int *lab = (int *)malloc(sizeof(int) * (n > 0 ? n : 1));
+        for (int i = 0; i < n; i++)
+            if (ids[i] != -1) lab[n_lab++] = i;
+        if (n_lab < n) {
+            int *newid = (int *)malloc(sizeof(int) * n);
+            memcpy(newid, ids, sizeof(int) * n);
+            for (int p = 0; p < n; p++) {
+                if (ids[p] != -1) continue;
+                if (st) st->n_noise++;
+                float min_dist = 0.f;
+                int min_index = 0, count_i = 0, real = 0;
+                for (int i = 0; i < n_lab; i++) {
+                    real = lab[i];
+                    if (sem[real] != sem[p]) continue;
+                    float d = sqd(xo[p], yo[p], zo[p], xo[real], yo[real], zo[real]);
+                    if (count_i == 0) min_dist = d;
+                    count_i++;
+                    if (d <= min_dist) {
+                        min_dist = d;
+                        min_index = real;
+                    }
+                }
+                if (count_i == 0 && n_lab > 0) min_index = real; /* :287-300: last labelled point */
+                newid[p] = ids[min_index]; /* min_index==0 when n_lab==0: ids[0] is -1 then */
+            }
+            memcpy(ids, newid, sizeof(int) * n);
+            free(newid);
+        }
+        free(lab);
+    }
+    return K;
+}
+
+/* =============================================================================================
+ * GRID variant
+ * =========================================================================================== */
+typedef struct {
+    double minx, miny, minz, h;
+    int64_t nx, ny, nz;
+    int n;        /* points in the grid */
+    int *ord;     /* point ids sorted by cell key */
+    int C;        /* occupied cells */
+    int64_t *ckey;
+    int *cstart;  /* C+1 */
+    int *cell_of; /* per sorted position: cell ordinal */
+} grid_t;
+
+typedef struct {
+    int64_t key;
+    int id;
+} kv_t;
+
+static int kv_cmp(const void *a, const void *b) {
+    const kv_t *p = (const kv_t *)a, *q = (const kv_t *)b;
+    if (p->key != q->key) return p->key < q->key ? -1 : 1;
+    return p->id < q->id ? -1 : (p->id > q->id);
+}
+
+static inline void grid_cell(const grid_t *g, float x, float y, float z, int64_t *cx, int64_t *cy,
+                             int64_t *cz) {
+    *cx = (int64_t)floor(((double)x - g->minx) / g->h);
+    *cy = (int64_t)floor(((double)y - g->miny) / g->h);
+    *cz = (int64_t)floor(((double)z - g->minz) / g->h);
+}
+
+static int grid_build(grid_t *g, const float *x, const float *y, const float *z, const int *ids,
+                      int n, double h) {
+    memset(g, 0, sizeof(*g));
+    g->h = h;
+    g->n = n;
+    if (n == 0) return PB_OK;
+    double mnx = 1e300, mny = 1e300, mnz = 1e300, mxx = -1e300, mxy = -1e300, mxz = -1e300;
+    for (int i = 0; i < n; i++) {
+        int p = ids ? ids[i] : i;
+        if (x[p] < mnx) mnx = x[p];
+        if (y[p] < mny) mny = y[p];
+        if (z[p] < mnz) mnz = z[p];
+        if (x[p] > mxx) mxx = x[p];
+        if (y[p] > mxy) mxy = y[p];
+        if (z[p] > mxz) mxz = z[p];
+    }
+    g->minx = mnx;
+    g->miny = mny;
+    g->minz = mnz;
+    g->nx = (int64_t)floor((mxx - mnx) / h) + 1;
+    g->ny = (int64_t)floor((mxy - mny) / h) + 1;
+    g->nz = (int64_t)floor((mxz - mnz) / h) + 1;
+    if ((double)g->nx * (double)g->ny * (double)g->nz > 9e18) return PB_ERR_ARG;
+    kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * n);
+    if (!kv) return PB_ERR_NOMEM;
+    for (int i = 0; i < n; i++) {
+        int p = ids ? ids[i] : i;
+        int64_t cx, cy, cz;
+        grid_cell(g, x[p], y[p], z[p], &cx, &cy, &cz);
+        kv[i].key = (cz * g->ny + cy) * g->nx + cx;
+        kv[i].id = p;
+    }
+    qsort(kv, n, sizeof(kv_t), kv_cmp);
+    g->ord = (int *)malloc(sizeof(int) * n);
+    g->cell_of = (int *)malloc(sizeof(int) * n);
+    int C = 0;
+    for (int i = 0; i < n; i++)
+        if (i == 0 || kv[i].key != kv[i - 1].key) C++;
+    g->C = C;
+    g->ckey = (int64_t *)malloc(sizeof(int64_t) * C);
+    g->cstart = (int *)malloc(sizeof(int) * (C + 1));
+    int c = -1;
+    for (int i = 0; i < n; i++) {
+        if (i == 0 || kv[i].key != kv[i - 1].key) {
+            c++;
+            g->ckey[c] = kv[i].key;
+            g->cstart[c] = i;
+        }
+        g->ord[i] = kv[i].id;
+        g->cell_of[i] = c;
+    }
+    g->cstart[C] = n;
+    free(kv);
+    return PB_OK;
+}
+
+static void grid_free(grid_t *g) {
+    free(g->ord);
+    free(g->ckey);
+    free(g->cstart);
+    free(g->cell_of);
+    memset(g, 0, sizeof(*g));
+}
+
+/* first cell ordinal with key >= k */
+static int grid_lower(const grid_t *g, int64_t k) {
+    int lo = 0, hi = g->C;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (g->ckey[mid] < k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+/* sorted-position range [*b,*e) of the x-run cells (cx0..cx1, cy, cz); returns 0 if outside grid */
+static int grid_run(const grid_t *g, int64_t cx0, int64_t cx1, int64_t cy, int64_t cz, int *b, int *e) {
+    if (cy < 0 || cy >= g->ny || cz < 0 || cz >= g->nz) return 0;
+    if (cx0 < 0) cx0 = 0;
+    if (cx1 >= g->nx) cx1 = g->nx - 1;
+    if (cx0 > cx1) return 0;
+    int64_t base = (cz * g->ny + cy) * g->nx;
+    int c0 = grid_lower(g, base + cx0);
+    int c1 = grid_lower(g, base + cx1 + 1);
+    if (c0 >= c1) return 0;
+    *b = g->cstart[c0];
+    *e = g->cstart[c1];
+    return 1;
+}
+
+static int grid_segment(int n, const float *x, const float *y, const float *z, const float *xo,
+                        const float *yo, const float *zo, const int *sem, const float *radius,
+                        const int *min_pts, float para_f, int nv_flag, int *ids, int *den, int acc,
+                        int *clt_sem_out, int *n_clt_sem, pb_oracle_stats *st) {
+    /* the grid needs one cell edge >= every radius in use */
+    float rmax = 0.f;
+    for (int i = 0; i < n; i++) {
+        float r = radius[sem[i] - 2];
+        if (r > rmax) rmax = r;
+    }
+    double h = (double)rmax * 1.001;
+    if (!(h > 0)) h = 1e-3;
+    grid_t g;
+    int rc = grid_build(&g, x, y, z, NULL, n, h);
+    if (rc) return -rc;
+
+    /* per cell: the 9 candidate runs in sorted positions */
+    int *runs = (int *)malloc(sizeof(int) * 18 * (g.C > 0 ? g.C : 1));
+    int *nruns = (int *)malloc(sizeof(int) * (g.C > 0 ? g.C : 1));
+    int maxcand = 0;
+    for (int c = 0; c < g.C; c++) {
+        int64_t k = g.ckey[c];
+        int64_t cx = k % g.nx, cy = (k / g.nx) % g.ny, cz = k / (g.nx * g.ny);
+        int m = 0, tot = 0;
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++) {
+                int b, e;
+                if (grid_run(&g, cx - 1, cx + 1, cy + dy, cz + dz, &b, &e)) {
+                    runs[18 * c + 2 * m] = b;
+                    runs[18 * c + 2 * m + 1] = e;
+                    tot += e - b;
+                    m++;
+                }
+            }
+        nruns[c] = m;
+        if (tot > maxcand) maxcand = tot;
+    }
+    /* coordinates in sorted order for contiguous inner loops */
+    float *sx = (float *)malloc(sizeof(float) * (n + 1));
+    float *sy = (float *)malloc(sizeof(float) * (n + 1));
+    float *sz = (float *)malloc(sizeof(float) * (n + 1));
+    for (int i = 0; i < n; i++) {
+        sx[i] = x[g.ord[i]];
+        sy[i] = y[g.ord[i]];
+        sz[i] = z[g.ord[i]];
+    }
+    /* A1 degree: count of pred-true candidates minus self (binary_cuda_functions.cu:85-88) */
+    int64_t sumdeg = 0, tests = 0;
+    for (int c = 0; c < g.C; c++) {
+        for (int i = g.cstart[c]; i < g.cstart[c + 1]; i++) {
+            int u = g.ord[i];
+            float r = radius[sem[u] - 2];
+            float r2 = r * r;
+            float ux = sx[i], uy = sy[i], uz = sz[i];
+            int ans = 0;
+            for (int m = 0; m < nruns[c]; m++) {
+                int b = runs[18 * c + 2 * m], e = runs[18 * c + 2 * m + 1];
+                for (int j = b; j < e; j++) ans += (sqd(ux, uy, uz, sx[j], sy[j], sz[j]) <= r2);
+                tests += e - b;
+            }
+            den[u] = ans - 1;
+            sumdeg += ans - 1;
+        }
+    }
+    /* A2 HP rule */
+    int *member = (int *)malloc(sizeof(int) * (n + 1));
+    int64_t nhp = 0;
+    for (int u = 0; u < n; u++) {
+        member[u] = (den[u] >= min_pts[sem[u] - 2]) ? 0 : 2;
+        nhp += member[u] == 0;
+    }
+    if (st) {
+        st->pair_tests += tests;
+        st->sum_deg += sumdeg;
+        st->n_hp += nhp;
+    }
+    /* position of each point in sorted order */
+    int *pos = (int *)malloc(sizeof(int) * (n + 1));
+    for (int i = 0; i < n; i++) pos[g.ord[i]] = i;
+    /* A3 clusters: seeds ascending; BFS expands only out of HPs; every visited same-class vertex is
+     * (re)labelled (binary.cu:154-217).  Neighbours are enumerated on the fly with the predicate. */
+    unsigned char *state = (unsigned char *)calloc(n + 1, 1); /* bit0 visited, bit1 queued (per BFS) */
+    int *queue = (int *)malloc(sizeof(int) * (n + 1));
+    int cluster = acc;
+    for (int u = 0; u < n; u++) {
+        if (!(ids[u] == -1 && member[u] == 0)) continue;
+        int qh = 0, qt = 0;
+        queue[qt++] = u;
+        state[u] = 2;
+        while (qh < qt) {
+            int v = queue[qh++];
+            state[v] |= 1;
+            if (member[v] != 0) continue;
+            int i = pos[v];
+            int c = g.cell_of[i];
+            /* the reference looks the radius up with sem indexed by SORTED position
+             * (binary_cuda_functions.cu:35,110) — only well defined when every class present in
+             * the segment has the same radius, which run() enforces */
+            float r = radius[sem[v] - 2];
+            float r2 = r * r;
+            float vx = sx[i], vy = sy[i], vz = sz[i];
+            for (int m = 0; m < nruns[c]; m++) {
+                int b = runs[18 * c + 2 * m], e = runs[18 * c + 2 * m + 1];
+                for (int j = b; j < e; j++) {
+                    if (j == i) continue;
+                    if (sqd(vx, vy, vz, sx[j], sy[j], sz[j]) <= r2) {
+                        int w = g.ord[j];
+                        if (!state[w]) {
+                            state[w] = 2;
+                            queue[qt++] = w;
+                        }
+                    }
+                }
+            }
+        }
+        int sem_cur = sem[u];
+        for (int k = 0; k < qt; k++) {
+            int v = queue[k];
+            if (sem[v] == sem_cur) {
+                ids[v] = cluster;
+                if (member[v] != 0) member[v] = 1;
+            }
+            state[v] = 0;
+        }
+        cluster++;
+    }
+    free(state);
+    free(queue);
+    free(pos);
+    free(member);
+    free(runs);
+    free(nruns);
+    free(sx);
+    free(sy);
+    free(sz);
+    grid_free(&g);
+
+    /* A4 filter */
+    int K = filter_segment(n, sem, ids, cluster - acc, acc, para_f, clt_sem_out, n_clt_sem);
+
+    /* A5 LP assignment: exact 1-NN in ORIGINAL coordinates, ties -> largest index */
+    if (nv_flag) {
+        int n_lab = 0;
+        int *lab = (int *)malloc(sizeof(int) * (n + 1));
+        unsigned lab_classes = 0;
+        for (int i = 0; i < n; i++)
+            if (ids[i] != -1) {
+                lab[n_lab++] = i;
+                lab_classes |= 1u << sem[i];
+            }
+        if (n_lab < n && n_lab > 0) {
+            const double gh = 0.06;
+            const int RING_MAX = 5;
+            grid_t lg;
+            rc = grid_build(&lg, xo, yo, zo, lab, n_lab, gh);
+            if (rc) {
+                free(lab);
+                return -rc;
+            }
+            int *newid = (int *)malloc(sizeof(int) * n);
+            memcpy(newid, ids, sizeof(int) * n);
+            int last_lab = lab[n_lab - 1];
+            int64_t nnt = 0, nnoise = 0;
+            for (int p = 0; p < n; p++) {
+                if (ids[p] != -1) continue;
+                nnoise++;
+                if (!(lab_classes & (1u << sem[p]))) { /* fallback :287-300 */
+                    newid[p] = ids[last_lab];
+                    continue;
+                }
+                float px = xo[p], py = yo[p], pz = zo[p];
+                int64_t cx, cy, cz;
+                grid_cell(&lg, px, py, pz, &cx, &cy, &cz);
+                float best = 0.f;
+                int bestq = -1;
+                int done = 0;
+                for (int k = 0; k <= RING_MAX && !done; k++) {
+                    /* scan the shell of Chebyshev radius k, row by row */
+                    for (int64_t dz = -k; dz <= k; dz++)
+                        for (int64_t dy = -k; dy <= k; dy++) {
+                            int full = (dz == -k || dz == k || dy == -k || dy == k);
+                            for (int part = 0; part < (full ? 1 : (k == 0 ? 1 : 2)); part++) {
+                                int64_t x0, x1;
+                                if (full) {
+                                    x0 = cx - k;
+                                    x1 = cx + k;
+                                } else {
+                                    x0 = x1 = (part == 0) ? cx - k : cx + k;
+                                }
+                                int b, e;
+                                if (!grid_run(&lg, x0, x1, cy + dy, cz + dz, &b, &e)) continue;
+                                for (int j = b; j < e; j++) {
+                                    int q = lg.ord[j];
+                                    if (sem[q] != sem[p]) continue;
+                                    float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
+                                    nnt++;
+                                    if (bestq < 0 || d < best || (d == best && q > bestq)) {
+                                        best = d;
+                                        bestq = q;
+                                    }
+                                }
+                            }
+                        }
+                    /* every unscanned point is farther than k*gh in true distance */
+                    double lim = (double)k * gh;
+                    if (bestq >= 0 && (double)best < lim * lim * (1.0 - 1e-5)) done = 1;
+                }
+                if (!done) { /* brute force over all labelled points (literal scan) */
+                    bestq = -1;
+                    for (int i = 0; i < n_lab; i++) {
+                        int q = lab[i];
+                        if (sem[q] != sem[p]) continue;
+                        float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
+                        nnt++;
+                        if (bestq < 0 || d <= best) {
+                            best = d;
+                            bestq = q;
+                        }
+                    }
+                }
+                newid[p] = ids[bestq];
+            }
+            memcpy(ids, newid, sizeof(int) * n);
+            free(newid);
+            grid_free(&lg);
+            if (st) {
+                st->n_noise += nnoise;
+                st->nn_tests += nnt;
+            }
+        }
+        free(lab);
+    }
+    return K;
+}
+
+/* =============================================================================================
+ * segment loop (cluster.cu:57-118)
+ * =========================================================================================== */
+static int run(int use_grid, const float *x, const float *y, const float *z, const float *xo,
+               const float *yo, const float *zo, const int *sem, const int *seg_counts, int n_seg,
+               const float *radius, const int *min_pts, float para_f, int nv_flag, int *cluster_id,
+               int *cluster_num, int *den_queue, float *center, int *clt_sem, int *n_clusters_out,
+               pb_oracle_stats *st) {
+    int64_t total = 0;
+    for (int b = 0; b < n_seg; b++) {
+        if (seg_counts[b] < 0) return PB_ERR_ARG;
+        total += seg_counts[b];
+    }
+    for (int64_t i = 0; i < total; i++)
+        if (sem[i] < 2 || sem[i] > 19) return PB_ERR_ARG;
+    {
+        int64_t o = 0;
+        for (int b = 0; b < n_seg; b++) { /* radius must be uniform over the classes of a segment */
+            for (int i = 1; i < seg_counts[b]; i++)
+                if (radius[sem[o + i] - 2] != radius[sem[o] - 2]) return PB_ERR_ARG;
+            o += seg_counts[b];
+        }
+    }
+    if (st) memset(st, 0, sizeof(*st));
+    int start = 0, acc = 0, n_center = 0, n_clt_sem = 0;
+    for (int b = 0; b < n_seg; b++) {
+        int n = seg_counts[b];
+        cluster_num[b] = 0;
+        if (n == 0) continue;
+        for (int i = 0; i < n; i++) cluster_id[start + i] = -1;
+        int K;
+        if (use_grid)
+            K = grid_segment(n, x + start, y + start, z + start, xo + start, yo + start, zo + start,
+                             sem + start, radius, min_pts, para_f, nv_flag, cluster_id + start,
+                             den_queue + start, acc, clt_sem, &n_clt_sem, st);
+        else
+            K = literal_segment(n, x + start, y + start, z + start, xo + start, yo + start,
+                                zo + start, sem + start, radius, min_pts, para_f, nv_flag,
+                                cluster_id + start, den_queue + start, acc, clt_sem, &n_clt_sem, st);
+        if (K < 0) return -K;
+        cluster_num[b] = K;
+        if (K > 0)
+            centres_segment(n, x + start, y + start, z + start, cluster_id + start, K, acc, center,
+                            &n_center);
+        acc += K;
+        start += n;
+    }
+    *n_clusters_out = acc;
+    return PB_OK;
+}
+
+int pb_oracle_literal(const float *x, const float *y, const float *z, const float *xo, const float *yo,
+                      const float *zo, const int *sem, const int *seg_counts, int n_seg,
+                      const float *radius, const int *min_pts, float para_f, int nv_flag,
+                      int *cluster_id, int *cluster_num, int *den_queue, float *center, int *clt_sem,
+                      int *n_clusters_out, pb_oracle_stats *st) {
+    return run(0, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, radius, min_pts, para_f, nv_flag,
+               cluster_id, cluster_num, den_queue, center, clt_sem, n_clusters_out, st);
+}
+
+int pb_oracle_grid(const float *x, const float *y, const float *z, const float *xo, const float *yo,
+                   const float *zo, const int *sem, const int *seg_counts, int n_seg,
+                   const float *radius, const int *min_pts, float para_f, int nv_flag, int *cluster_id,
+                   int *cluster_num, int *den_queue, float *center, int *clt_sem, int *n_clusters_out,
+                   pb_oracle_stats *st) {
+    return run(1, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, radius, min_pts, para_f, nv_flag,
+               cluster_id, cluster_num, den_queue, center, clt_sem, n_clusters_out, st);
+}
