@@ -41,11 +41,17 @@ static const float k_mean_count[18] = {3917.0f, 12056.0f, 2303.0f, 8331.0f, 3948
                                        5629.0f, 11719.0f, 1003.0f, 3317.0f, 4912.0f, 10221.0f,
                                        3889.0f, 4136.0f,  2120.0f, 945.0f,  3967.0f, 2589.0f};
 
-/* binary_cuda_functions.cu:305-308 as nvcc compiles it: FADD,FMUL,FADD,FFMA,FADD,FFMA */
+/* binary_cuda_functions.cu:305-308 as nvcc 12.9 compiles it for sm_100a.  SASS of all three call
+ * sites (k_num_nbs, k_append_neighbours, noise_id_cluster; `cuobjdump -sass oracle/_ref/PB_lib*.so`)
+ * reads  FADD dy; FMUL t=dy*dy; FADD dx; FFMA t=dx*dx+t; FADD dz; FFMA D=dz*dz+t  — i.e. the product
+ * that stays a separate rounded multiply is the MIDDLE term:
+ *     D = fma(dz, dz, fma(dx, dx, fl(dy*dy)))
+ * (first GPU cross-check against the compiled reference caught the dx*dx-first guess being wrong on
+ * pairs within 1 ulp of r^2). */
 static inline float sqd(float x1, float y1, float z1, float x2, float y2, float z2) {
     float dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
-    float t = dx * dx;
-    t = fmaf(dy, dy, t);
+    float t = dy * dy;
+    t = fmaf(dx, dx, t);
     return fmaf(dz, dz, t);
 }
 
