@@ -1,0 +1,113 @@
+/*
+ * pbnet_b200.h — C ABI of libpbnet_b200.so: the B200-native (sm_100a) replacement of PBNet's
+ * post-backbone instance-grouping hot path.
+ *
+ * Every entry point below replaces one interface of the reference (paths under /root/reference):
+ *
+ *   pb_binary_cluster          <-  void binary_cluster(at::Tensor x17, int, float, bool)
+ *                                  lib/PB_lib/src/pbnet/cluster.h:13-18, cluster.cu:16-119,
+ *                                  bound to Python at lib/PB_lib/src/PB_lib_api.cpp:7 and called from
+ *                                  lib/PB_lib/torch_io/pbnet_ops.py:73-74
+ *   pb_binary_cluster_batched  <-  the 18-iteration per-class Python loop around that call,
+ *                                  network/PBNet.py:151-179 (one launch for many calls)
+ *   pb_create / pb_destroy     <-  class BINARY::Solver ctor / (missing) dtor,
+ *                                  lib/PB_lib/src/pbnet/binary.cuh:33-95, binary.cu:19-47
+ *   error codes                <-  CUDA_ERR_CHK -> exit(code), lib/PB_lib/src/pbnet/binary.cuh:20-27
+ *
+ * Plain pointers and sizes only; no torch types.  All arrays are 1-D contiguous.  fp32 / int32.
+ * The library never falls back to a CPU path: without a usable CUDA device pb_create fails.
+ */
+#ifndef PBNET_B200_H
+#define PBNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+/* status codes (returned by every int function; text via pb_last_error) */
+enum {
+    PB_OK = 0,
+    PB_ERR_ARG = 1,         /* null pointer, negative size, sum(seg_counts) != n_pts ... */
+    PB_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+    PB_ERR_SEM_RANGE = 3,   /* a class id outside [2,19] (the reference indexes 18-entry tables with sem-2) */
+    PB_ERR_NONFINITE = 4,   /* NaN / Inf coordinate */
+    PB_ERR_RANGE = 5,       /* a segment spans more than 16383 grid cells along one axis */
+    PB_ERR_MIXED_CLASS = 6, /* a segment mixes classes (PBNet never does; not supported yet) */
+    PB_ERR_CAPACITY = 7,    /* center / clt_sem capacity too small for the clusters found */
+    PB_ERR_NOMEM = 8
+};
+
+/* where the data pointers of a call live */
+enum { PB_MEM_HOST = 0, PB_MEM_DEVICE = 1 };
+
+/* Creates a context bound to CUDA device `device`: owns a stream, a growable device workspace
+ * (no per-call cudaMalloc) and pinned scratch.  One context per host thread. */
+int pb_create(int device, pb_ctx **out);
+void pb_destroy(pb_ctx *ctx);
+const char *pb_last_error(const pb_ctx *ctx);
+
+/* number of kernel launches issued by the last pb_binary_cluster* call on this context */
+int64_t pb_last_launch_count(const pb_ctx *ctx);
+
+/*
+ * One reference call.  Segment b covers points [off_b, off_b + seg_counts[b]).
+ *
+ * in   x,y,z        shifted coordinates (clustering space)            f32[n_pts]
+ *      xo,yo,zo     original coordinates (LP assignment space)        f32[n_pts]
+ *      sem          class per point, in [2,19]                        i32[n_pts]
+ *      seg_counts   points per segment — ALWAYS a host pointer        i32[n_seg]
+ *      radius       per-class radius table (index sem-2)              f32[18]   host pointer
+ *      min_pts      per-class HP threshold (index sem-2)              i32[18]   host pointer
+ *      para_f       fragment filter factor (reference passes 0.05)
+ *      assign_lp    the reference's nv_flag
+ * out  cluster_id   -1 or id in [0, n_clusters); ids run across segments  i32[n_pts]
+ *      cluster_num  clusters per segment                              i32[n_seg]
+ *      degree       raw neighbour count (pbnet_ops returns degree+1)  i32[n_pts]
+ *      center       xyz per cluster, shifted space                    f32[3*n_clusters] (capacity center_cap floats)
+ *      clt_sem      class per cluster                                 i32[n_clusters]   (capacity clt_sem_cap)
+ *      n_clusters_out  total clusters — host pointer
+ * mem_kind  PB_MEM_HOST: data pointers are host memory (pinned memory makes the copies asynchronous);
+ *           PB_MEM_DEVICE: device pointers on the context's device, results stay on the device.
+ * stream    cudaStream_t or NULL for the context's own stream.  The call returns after the stream
+ *           has been synchronised (n_clusters_out is valid on return).
+ */
+int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo,
+                      const float *yo, const float *zo, const int32_t *sem, const int32_t *seg_counts,
+                      int32_t n_seg, int64_t n_pts, const float *radius, const int32_t *min_pts,
+                      float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
+                      int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem,
+                      int64_t clt_sem_cap, int64_t *n_clusters_out, int mem_kind, void *stream);
+
+/*
+ * Many reference calls in one launch sequence.  Call c owns call_seg_counts[c] consecutive segments;
+ * cluster ids restart at 0 for every call (exactly what n_calls separate pb_binary_cluster calls
+ * return); center / clt_sem are the per-call results concatenated in call order;
+ * call_clusters[c] (host, may be NULL) receives the cluster count of call c.
+ */
+int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const float *z,
+                              const float *xo, const float *yo, const float *zo, const int32_t *sem,
+                              const int32_t *seg_counts, int32_t n_seg, const int32_t *call_seg_counts,
+                              int32_t n_calls, int64_t n_pts, const float *radius, const int32_t *min_pts,
+                              float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
+                              int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem,
+                              int64_t clt_sem_cap, int64_t *n_clusters_out, int64_t *call_clusters,
+                              int mem_kind, void *stream);
+
+/* Optional per-stage device timings (ms, CUDA events) of the last call when enabled; stage names via
+ * pb_stage_name.  Off by default (events add launch overhead). */
+void pb_set_profiling(pb_ctx *ctx, int on);
+int pb_stage_count(void);
+const char *pb_stage_name(int i);
+float pb_stage_ms(const pb_ctx *ctx, int i);
+/* counters of the last call: [0] pair tests issued by the degree kernel, [1] sum of degrees,
+ * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter */
+int64_t pb_counter(const pb_ctx *ctx, int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBNET_B200_H */

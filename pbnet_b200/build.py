@@ -1,0 +1,35 @@
+"""In-tree build of libpbnet_b200.so (nvcc, sm_100a only).  The .so is git-ignored but travels to the
+GPU box with the gpurun snapshot."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "pb_api.cu")
+DEPS = [SRC, os.path.join(HERE, "csrc", "pb_kernels.cuh"), os.path.join(HERE, "..", "include", "pbnet_b200.h")]
+SO = os.path.join(HERE, "libpbnet_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+        cmd = [nvcc, *NVCC_FLAGS, SRC, "-o", SO]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

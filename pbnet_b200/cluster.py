@@ -1,0 +1,171 @@
+"""Host side of the grouping path: thin Python over the C ABI (include/pbnet_b200.h).
+
+``Context.binary_cluster`` is the array-level call (torch CPU / CUDA tensors or numpy arrays);
+``pbnet_b200.pbnet_ops.cluster`` and ``pbnet_b200.shim.PB_lib.binary_cluster`` mirror the reference's
+operator surface (lib/PB_lib/torch_io/pbnet_ops.py:12-82, lib/PB_lib/src/PB_lib_api.cpp:7) on top of it.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from ._lib import PBError, lib
+
+PB_MEM_HOST, PB_MEM_DEVICE = 0, 1
+
+
+def _addr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _as_host_i32(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _as_host_f32(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """Owns a pb_ctx (stream + device workspace).  Not thread-safe: one Context per thread."""
+
+    def __init__(self, device: int = 0, profiling: bool = False):
+        self._lib = lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.pb_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise PBError(rc, f"pb_create(device={device}) failed — a CUDA device is required (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        if profiling:
+            self.set_profiling(True)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_profiling(self, on: bool):
+        self._lib.pb_set_profiling(self._h, int(bool(on)))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.pb_last_launch_count(self._h))
+
+    def stage_ms(self) -> dict:
+        n = self._lib.pb_stage_count()
+        return {self._lib.pb_stage_name(i).decode(): float(self._lib.pb_stage_ms(self._h, i)) for i in range(n)}
+
+    def counters(self) -> dict:
+        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters"]
+        return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
+
+    # ------------------------------------------------------------------------------------------------
+    def binary_cluster(self, x, y, z, xo, yo, zo, sem, seg_counts, radius18, min_pts18, para_f=0.05,
+                       assign_lp=True, call_seg_counts=None, cluster_id=None, cluster_num=None, degree=None,
+                       center=None, clt_sem=None, stream=None):
+        """Runs the grouping path on SoA fp32 coordinates / int32 classes.
+
+        All of x..sem must live in the same place: host (numpy or torch CPU — pinned torch tensors make
+        the copies asynchronous) or CUDA device ``self.device``.  ``seg_counts`` / ``call_seg_counts`` /
+        ``radius18`` / ``min_pts18`` are host metadata.  Outputs are allocated next to the inputs unless
+        passed in.  Returns dict(cluster_id, cluster_num, degree, center, clt_sem, n_clusters,
+        call_clusters)."""
+        is_torch = isinstance(x, torch.Tensor)
+        on_device = is_torch and x.is_cuda
+        n = int(x.shape[0])
+        seg = _as_host_i32(seg_counts)
+        S = int(seg.shape[0])
+        r18 = _as_host_f32(radius18)
+        m18 = _as_host_i32(min_pts18)
+        if r18.shape != (18,) or m18.shape != (18,):
+            raise ValueError("radius / min_pts tables must have 18 entries")
+        for name, a, dt in (("x", x, "float32"), ("y", y, "float32"), ("z", z, "float32"), ("xo", xo, "float32"),
+                            ("yo", yo, "float32"), ("zo", zo, "float32"), ("sem", sem, "int32")):
+            if isinstance(a, torch.Tensor) != is_torch:
+                raise TypeError("mixing torch and numpy inputs")
+            if is_torch:
+                if a.is_cuda != on_device or not a.is_contiguous() or str(a.dtype) != "torch." + dt or a.dim() != 1:
+                    raise TypeError(f"{name}: need a contiguous 1-D {dt} tensor on the same device as x")
+                if on_device and a.device.index != self.device:
+                    raise TypeError(f"{name}: tensor is on cuda:{a.device.index}, context on cuda:{self.device}")
+            else:
+                if a.dtype != np.dtype(dt) or not a.flags["C_CONTIGUOUS"] or a.ndim != 1:
+                    raise TypeError(f"{name}: need a contiguous 1-D {dt} array")
+            if a.shape[0] != n:
+                raise ValueError(f"{name}: length {a.shape[0]} != {n}")
+
+        def new(shape, dtype_t, dtype_n, like_pinned=False):
+            if is_torch:
+                if on_device:
+                    return torch.empty(shape, dtype=dtype_t, device=x.device)
+                return torch.empty(shape, dtype=dtype_t, pin_memory=like_pinned)
+            return np.empty(shape, dtype=dtype_n)
+
+        pinned = is_torch and not on_device and x.is_pinned()
+        if cluster_id is None:
+            cluster_id = new(n, torch.int32, np.int32, pinned)
+        if cluster_num is None:
+            cluster_num = new(S, torch.int32, np.int32, pinned)
+        if degree is None:
+            degree = new(n, torch.int32, np.int32, pinned)
+        cap = max(n, 1)
+        if center is None:
+            center = new(3 * cap, torch.float32, np.float32, pinned)
+        if clt_sem is None:
+            clt_sem = new(cap, torch.int32, np.int32, pinned)
+        nclt = ctypes.c_int64(0)
+        kind = PB_MEM_DEVICE if on_device else PB_MEM_HOST
+        sptr = None
+        if stream is not None:
+            sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        if call_seg_counts is None:
+            call_clusters = None
+            rc = self._lib.pb_binary_cluster(
+                self._h, _addr(x), _addr(y), _addr(z), _addr(xo), _addr(yo), _addr(zo), _addr(sem), _addr(seg), S, n,
+                _addr(r18), _addr(m18), float(para_f), int(bool(assign_lp)), _addr(cluster_id), _addr(cluster_num),
+                _addr(degree), _addr(center), int(center.shape[0]), _addr(clt_sem), int(clt_sem.shape[0]),
+                ctypes.byref(nclt), kind, sptr)
+        else:
+            calls = _as_host_i32(call_seg_counts)
+            call_clusters = np.zeros(calls.shape[0], dtype=np.int64)
+            rc = self._lib.pb_binary_cluster_batched(
+                self._h, _addr(x), _addr(y), _addr(z), _addr(xo), _addr(yo), _addr(zo), _addr(sem), _addr(seg), S,
+                _addr(calls), int(calls.shape[0]), n, _addr(r18), _addr(m18), float(para_f), int(bool(assign_lp)),
+                _addr(cluster_id), _addr(cluster_num), _addr(degree), _addr(center), int(center.shape[0]),
+                _addr(clt_sem), int(clt_sem.shape[0]), ctypes.byref(nclt), _addr(call_clusters), kind, sptr)
+        if rc != 0:
+            raise PBError(rc, self._lib.pb_last_error(self._h).decode())
+        k = int(nclt.value)
+        return dict(cluster_id=cluster_id, cluster_num=cluster_num, degree=degree, center=center[:3 * k],
+                    clt_sem=clt_sem[:k], n_clusters=k, call_clusters=call_clusters)
+
+
+_tls = threading.local()
+
+
+def default_context(device: int = 0) -> Context:
+    """Per-thread, per-device cached context (workspace is reused across calls)."""
+    d = getattr(_tls, "ctx", None)
+    if d is None:
+        d = _tls.ctx = {}
+    if device not in d:
+        d[device] = Context(device)
+    return d[device]

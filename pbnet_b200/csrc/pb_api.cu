@@ -1,0 +1,499 @@
+// pb_api.cu — context, workspace and launch sequence behind the C ABI of include/pbnet_b200.h.
+//
+// Replaces the host side of the reference: binary_cluster's per-segment loop
+// (lib/PB_lib/src/pbnet/cluster.cu:57-110) and BINARY::Solver's ~90 synchronous
+// cudaMalloc/cudaMemcpy/cudaFree calls per segment plus one host round trip per BFS level
+// (lib/PB_lib/src/pbnet/binary.cu).  Here ALL segments of ALL calls go through one fixed sequence
+// of ~35 launches on one stream with a single host synchronisation at the end.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pbnet_b200.h"
+#include "pb_kernels.cuh"
+
+namespace {
+
+// binary.cu:229 (class mean sizes "from HAIS"); filter threshold = mean_count * para_f in fp32
+const float kMeanCount[18] = {3917.0f, 12056.0f, 2303.0f, 8331.0f, 3948.0f, 3166.0f, 5629.0f, 11719.0f, 1003.0f,
+                              3317.0f, 4912.0f,  10221.0f, 3889.0f, 4136.0f, 2120.0f, 945.0f,  3967.0f, 2589.0f};
+
+enum Stage {
+    ST_H2D = 0, ST_PREP, ST_SORT, ST_GRID, ST_DEGREE, ST_HP, ST_UNION, ST_COMPONENTS, ST_LABEL, ST_FILTER,
+    ST_LP_BUILD, ST_LP_NN, ST_CENTRES, ST_D2H, ST_COUNT
+};
+const char *kStageNames[ST_COUNT] = {"h2d", "prep", "sort", "grid", "degree", "hp_cells", "union", "components",
+                                     "label", "filter", "lp_build", "lp_nn", "centres", "d2h"};
+
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0;
+    bool dry = false;
+    template <class T>
+    T *get(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        char *p = dry ? nullptr : base + off;
+        off += bytes;
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    std::string err;
+    int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    float stage_ms[ST_COUNT] = {};
+    int64_t counters[8] = {};
+    // pinned scratch for scalars read back at the end of a call
+    int *h_scalars = nullptr;  // [0] err bits [1] C [2] R [3] K [4] Q [5] L
+    unsigned long long *h_counters = nullptr;
+};
+
+namespace {
+
+int fail(pb_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define PB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
+
+struct Scan {  // exclusive scan of int32, n known on host or (upper bound on host, exact on device)
+    int *block_sums = nullptr;
+    int nb = 0;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int pb_create(int device, pb_ctx **out) {
+    if (!out) return PB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return PB_ERR_CUDA;  // no CPU fallback exists
+    pb_ctx *ctx = new pb_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_scalars, 16 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return PB_ERR_CUDA;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return PB_OK;
+}
+
+extern "C" void pb_destroy(pb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *pb_last_error(const pb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t pb_last_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void pb_set_profiling(pb_ctx *ctx, int on) {
+    if (ctx) ctx->profiling = on != 0;
+}
+extern "C" int pb_stage_count(void) { return ST_COUNT; }
+extern "C" const char *pb_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+extern "C" float pb_stage_ms(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < ST_COUNT) ? ctx->stage_ms[i] : 0.f; }
+extern "C" int64_t pb_counter(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < 8) ? ctx->counters[i] : 0; }
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Work {  // all device buffers of one call; laid out by plan() on the arena
+    // inputs (device copies when the caller's data is on the host)
+    float *x, *y, *z, *xo, *yo, *zo;
+    int *sem;
+    // outputs
+    int *cluster_id, *cluster_num, *degree, *clt_sem;
+    float *center;
+    // tables
+    float *radius, *thresh;
+    int *min_pts;
+    int *seg_start, *seg_call_first;
+    pb::SegArrays sg;
+    // per point
+    int *seg_of, *cell_of, *deg_sorted, *head, *tmp_scan, *raw_label, *flag, *gid_at, *qflag, *qpos, *labflag, *lpos, *qlist;
+    uint64_t *key1, *key1_alt, *key2, *key2_alt;
+    uint32_t *val, *order1, *order2;
+    float4 *pts4, *lab4, *box_lo, *box_hi;
+    // per cell (upper bound N)
+    int *cell_start, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid;
+    uint64_t *cell_key;
+    int2 *runs;
+    // per raw cluster (upper bound N)
+    int *rep, *raw_count, *keep, *kscan, *clt_seg;
+    // scalars
+    int *d_scalars;  // [0] err [1] C [2] R [3] K [4] Q [5] L
+    unsigned long long *d_counters;
+    int *scan_blocks;
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_cap, long long clt_cap) {
+    size_t N = (size_t)n;
+    if (host_io) {
+        w.x = a.get<float>(N); w.y = a.get<float>(N); w.z = a.get<float>(N);
+        w.xo = a.get<float>(N); w.yo = a.get<float>(N); w.zo = a.get<float>(N);
+        w.sem = a.get<int>(N);
+        w.cluster_id = a.get<int>(N);
+        w.cluster_num = a.get<int>(S);
+        w.degree = a.get<int>(N);
+    }
+    // cluster metadata is always produced in workspace first (its size is only known at the end)
+    w.center = a.get<float>(3 * N);
+    w.clt_sem = a.get<int>(N);
+    w.clt_seg = a.get<int>(N);
+    w.radius = a.get<float>(18); w.thresh = a.get<float>(18); w.min_pts = a.get<int>(18);
+    w.seg_start = a.get<int>(S + 1); w.seg_call_first = a.get<int>(S);
+    w.sg.enc_min_s = a.get<unsigned>(3 * S); w.sg.enc_min_o = a.get<unsigned>(3 * S); w.sg.enc_max_o = a.get<unsigned>(3 * S);
+    w.sg.cls = a.get<int>(S); w.sg.min_pts = a.get<int>(S); w.sg.r2 = a.get<float>(S); w.sg.inv_h = a.get<float>(S);
+    w.sg.min_s = a.get<float>(3 * S); w.sg.min_o = a.get<float>(3 * S); w.sg.inv_g = a.get<float>(S);
+    w.sg.cell_start = a.get<int>(S + 1); w.sg.lab_start = a.get<int>(S + 1); w.sg.id_base = a.get<int>(S);
+    w.sg.k_base = a.get<int>(S); w.sg.cluster_num = a.get<int>(S);
+    w.seg_of = a.get<int>(N); w.cell_of = a.get<int>(N); w.deg_sorted = a.get<int>(N); w.head = a.get<int>(N);
+    w.tmp_scan = a.get<int>(N); w.raw_label = a.get<int>(N); w.flag = a.get<int>(N); w.gid_at = a.get<int>(N);
+    w.qflag = a.get<int>(N); w.qpos = a.get<int>(N); w.labflag = a.get<int>(N); w.lpos = a.get<int>(N); w.qlist = a.get<int>(N);
+    w.key1 = a.get<uint64_t>(N); w.key1_alt = a.get<uint64_t>(N); w.key2 = a.get<uint64_t>(N); w.key2_alt = a.get<uint64_t>(N);
+    w.val = a.get<uint32_t>(N); w.order1 = a.get<uint32_t>(N); w.order2 = a.get<uint32_t>(N);
+    w.pts4 = a.get<float4>(N); w.lab4 = a.get<float4>(N);
+    w.box_lo = a.get<float4>(N / 32 + 2); w.box_hi = a.get<float4>(N / 32 + 2);
+    w.cell_start = a.get<int>(N + 1); w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N);
+    w.comp_min = a.get<int>(N); w.cell_gid = a.get<int>(N); w.cell_key = a.get<uint64_t>(N);
+    w.runs = a.get<int2>(N * pb::kRuns);
+    w.rep = a.get<int>(N); w.raw_count = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
+    w.d_scalars = a.get<int>(16);
+    w.d_counters = a.get<unsigned long long>(8);
+    w.scan_blocks = a.get<int>(N / pb::kScanTile + 2);
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
+    w.cub_bytes = bytes;
+    w.cub_tmp = a.get<char>(bytes);
+    (void)center_cap;
+    (void)clt_cap;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
+                    const float *zo, const int32_t *sem, const int32_t *seg_counts, int32_t n_seg,
+                    const int32_t *call_seg_counts, int32_t n_calls, int64_t n_pts, const float *radius,
+                    const int32_t *min_pts, float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
+                    int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap,
+                    int64_t *n_clusters_out, int64_t *call_clusters, int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_seg < 0 || n_pts < 0 || n_calls < 0 || (n_seg > 0 && !seg_counts) || !radius || !min_pts || !n_clusters_out)
+        return fail(ctx, PB_ERR_ARG, "null / negative argument");
+    if (n_pts >= (int64_t)1 << 31) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^31");
+    if (n_seg >= (1 << 22)) return fail(ctx, PB_ERR_ARG, "n_seg must be below 2^22");
+    if (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE) return fail(ctx, PB_ERR_ARG, "bad mem_kind");
+    const int S = n_seg;
+    const int n = (int)n_pts;
+    std::vector<int> start(S + 1, 0), call_first(std::max(S, 1), 0);
+    for (int s = 0; s < S; s++) {
+        if (seg_counts[s] < 0) return fail(ctx, PB_ERR_ARG, "negative segment size");
+        long long t = (long long)start[s] + seg_counts[s];
+        if (t > n_pts) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+        start[s + 1] = (int)t;
+    }
+    if ((S == 0 ? 0 : start[S]) != n) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+    {
+        int s = 0;
+        for (int c = 0; c < n_calls; c++) {
+            if (!call_seg_counts || call_seg_counts[c] < 0 || s + call_seg_counts[c] > S)
+                return fail(ctx, PB_ERR_ARG, "bad call_seg_counts");
+            for (int k = 0; k < call_seg_counts[c]; k++) call_first[s + k] = s;
+            s += call_seg_counts[c];
+        }
+        if (s != S) return fail(ctx, PB_ERR_ARG, "sum(call_seg_counts) != n_seg");
+    }
+    *n_clusters_out = 0;
+    if (call_clusters)
+        for (int c = 0; c < n_calls; c++) call_clusters[c] = 0;
+    if (n > 0 && (!x || !y || !z || !xo || !yo || !zo || !sem || !cluster_id || !degree))
+        return fail(ctx, PB_ERR_ARG, "null data pointer");
+    if (S > 0 && !cluster_num) return fail(ctx, PB_ERR_ARG, "null cluster_num");
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (n == 0) {
+        if (S > 0) {
+            if (host_io) std::memset(cluster_num, 0, sizeof(int) * S);
+            else PB_CUDA(cudaMemsetAsync(cluster_num, 0, sizeof(int) * S, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+        return PB_OK;
+    }
+
+    // ---- workspace --------------------------------------------------------------------------------
+    Work w;
+    std::memset(&w, 0, sizeof(w));
+    Arena dry;
+    dry.dry = true;
+    plan(dry, w, n, S, host_io, center_cap, clt_sem_cap);
+    if (dry.off > ctx->arena.cap) {
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
+        ctx->arena.base = nullptr;
+        ctx->arena.cap = 0;
+        size_t want = dry.off + dry.off / 4;
+        cudaError_t e = cudaMalloc(&ctx->arena.base, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, PB_ERR_NOMEM, "workspace allocation of " + std::to_string(want) + " bytes failed");
+        }
+        ctx->arena.cap = want;
+    }
+    ctx->arena.off = 0;
+    ctx->arena.dry = false;
+    plan(ctx->arena, w, n, S, host_io, center_cap, clt_sem_cap);
+    w.sg.start = w.seg_start;
+
+    const bool prof = ctx->profiling;
+    int stage_ev = 0;
+    auto mark = [&]() {
+        if (prof) cudaEventRecord(ctx->ev[stage_ev], st);
+        stage_ev++;
+    };
+    int64_t &L = ctx->launches;
+    const int T = 256;
+    const int gN = div_up(n, T);
+    const int gS = div_up(S + 1, T);
+    const int gPersist = 148 * 8;
+
+    mark();  // start of H2D
+    // ---- inputs -----------------------------------------------------------------------------------
+    const float *dx = x, *dy = y, *dz = z, *dxo = xo, *dyo = yo, *dzo = zo;
+    const int *dsem = sem;
+    int *d_cluster_id = cluster_id, *d_cluster_num = cluster_num, *d_degree = degree;
+    if (host_io) {
+        size_t fb = sizeof(float) * (size_t)n;
+        PB_CUDA(cudaMemcpyAsync(w.x, x, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.y, y, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.z, z, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.xo, xo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.yo, yo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.zo, zo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.sem, sem, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+        dx = w.x, dy = w.y, dz = w.z, dxo = w.xo, dyo = w.yo, dzo = w.zo, dsem = w.sem;
+        d_cluster_id = w.cluster_id, d_cluster_num = w.cluster_num, d_degree = w.degree;
+    }
+    float thresh[18];
+    for (int i = 0; i < 18; i++) thresh[i] = kMeanCount[i] * para_f;  // fp32 multiply, binary.cu:256
+    // small tables: pageable host memory -> the async copies are staged synchronously by the driver
+    PB_CUDA(cudaMemcpyAsync(w.radius, radius, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(w.min_pts, min_pts, sizeof(int) * 18, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(w.thresh, thresh, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(w.seg_start, start.data(), sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(w.seg_call_first, call_first.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(w.sg.enc_min_s, 0xff, sizeof(unsigned) * 3 * S, st));
+    PB_CUDA(cudaMemsetAsync(w.sg.enc_min_o, 0xff, sizeof(unsigned) * 3 * S, st));
+    PB_CUDA(cudaMemsetAsync(w.sg.enc_max_o, 0x00, sizeof(unsigned) * 3 * S, st));
+    PB_CUDA(cudaMemsetAsync(w.d_scalars, 0, sizeof(int) * 16, st));
+    PB_CUDA(cudaMemsetAsync(w.d_counters, 0, sizeof(unsigned long long) * 8, st));
+    PB_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int) * (size_t)n, st));
+    PB_CUDA(cudaMemsetAsync(w.raw_count, 0, sizeof(int) * (size_t)n, st));
+    int *d_err = w.d_scalars, *d_C = w.d_scalars + 1, *d_R = w.d_scalars + 2, *d_K = w.d_scalars + 3,
+        *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5;
+    unsigned long long *cnt = prof ? w.d_counters : nullptr;
+
+    auto scan = [&](const int *in, int n_host, const int *n_dev, int *out, int *total) {
+        int nb = div_up(n_host, pb::kScanTile);
+        pb::k_scan_reduce<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, w.scan_blocks);
+        pb::k_scan_spine<<<1, pb::kScanThreads, 0, st>>>(w.scan_blocks, nb, total);
+        pb::k_scan_down<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, w.scan_blocks, out);
+        L += 3;
+    };
+
+    mark();  // PREP
+    pb::k_prep_points<<<gN, T, 0, st>>>(n, S, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, d_err);
+    pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, w.radius, w.min_pts);
+    pb::k_keys<<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err);
+    L += 3;
+
+    mark();  // SORT
+    int seg_bits = 1;
+    while ((1 << seg_bits) < S) seg_bits++;
+    int end_bit = pb::kSegShift + seg_bits;
+    {
+        size_t bytes = w.cub_bytes;
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key1, w.key1_alt, w.val, w.order1, n, 0, end_bit, st));
+        if (assign_lp) {
+            bytes = w.cub_bytes;
+            PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit, st));
+        }
+        L += assign_lp ? 2 * (2 + (end_bit + 7) / 8) : (2 + (end_bit + 7) / 8);  // histogram + onesweep passes
+    }
+    const uint64_t *skey = w.key1_alt;
+
+    mark();  // GRID
+    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.head);
+    L++;
+    scan(w.head, n, nullptr, w.tmp_scan, d_C);  // d_C is overwritten by k_cells with the same value
+    pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head, w.tmp_scan, w.cell_of, w.cell_start, w.cell_key, w.parent, w.cell_hp,
+                                  w.cell_minhp, w.comp_min, d_C);
+    pb::k_seg_cells<<<gS, T, 0, st>>>(n, S, w.sg, w.cell_of, d_C);
+    pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cell_key, d_C, w.runs);
+    L += 3;
+
+    mark();  // DEGREE
+    pb::k_degree<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_start, w.cell_key, w.runs,
+                                                 w.deg_sorted, cnt);
+    L++;
+    mark();  // HP
+    pb::k_hp_cells<<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_key, w.deg_sorted, d_degree, w.cell_hp,
+                                     w.cell_minhp, cnt);
+    L++;
+    mark();  // UNION
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, w.pts4, w.cell_start, w.cell_key, w.runs, w.cell_hp, w.parent, d_C);
+    L++;
+    mark();  // COMPONENTS
+    pb::k_comp_min<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.cell_minhp, w.comp_min);
+    pb::k_flag_roots<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.comp_min, w.flag);
+    L += 2;
+    scan(w.flag, n, nullptr, w.gid_at, d_R);
+    pb::k_cell_gid<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep);
+    L++;
+    mark();  // LABEL
+    pb::k_label<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_start, w.cell_key, w.runs, w.cell_hp,
+                                                w.cell_gid, w.raw_label, w.raw_count);
+    L++;
+    mark();  // FILTER
+    pb::k_filter<<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, w.thresh, w.keep);
+    L++;
+    scan(w.keep, n, d_R, w.kscan, d_K);
+    pb::k_seg_clusters<<<gS, T, 0, st>>>(n, S, w.sg, w.seg_call_first, w.gid_at, d_R, w.kscan, d_K, d_cluster_num);
+    pb::k_relabel<<<gN, T, 0, st>>>(n, w.sg, w.seg_of, w.raw_label, w.keep, w.kscan, assign_lp, d_cluster_id, w.qflag,
+                                    w.clt_sem, w.clt_seg, w.rep);
+    L += 2;
+    mark();  // LP_BUILD
+    if (assign_lp) {
+        pb::k_lab_flags<<<gN, T, 0, st>>>(n, w.order2, d_cluster_id, w.labflag);
+        L++;
+        scan(w.qflag, n, nullptr, w.qpos, d_Q);
+        scan(w.labflag, n, nullptr, w.lpos, d_L);
+        pb::k_compact<<<gN, T, 0, st>>>(n, w.qflag, w.qpos, w.qlist, w.order2, w.labflag, w.lpos, dxo, dyo, dzo, w.lab4);
+        pb::k_seg_lab<<<gS, T, 0, st>>>(n, S, w.sg, w.lpos, d_L);
+        pb::k_lab_boxes<<<gPersist, T, 0, st>>>(d_L, w.lab4, w.box_lo, w.box_hi);
+        L += 3;
+    }
+    mark();  // LP_NN
+    if (assign_lp) {
+        pb::k_nn<<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, dxo, dyo, dzo, w.lab4, w.box_lo, w.box_hi,
+                                         d_cluster_id, cnt);
+        L++;
+    }
+    mark();  // CENTRES
+    pb::k_centres<<<gPersist, 128, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, w.center);
+    L++;
+    mark();  // D2H
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+    if (prof) PB_CUDA(cudaMemcpyAsync(ctx->h_counters, w.d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    if (host_io) {
+        PB_CUDA(cudaMemcpyAsync(cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(cluster_num, w.cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    const int errbits = ctx->h_scalars[0];
+    if (errbits & pb::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "class id outside [2,19]");
+    if (errbits & pb::kErrNonFinite) return fail(ctx, PB_ERR_NONFINITE, "non-finite coordinate");
+    if (errbits & pb::kErrRange) return fail(ctx, PB_ERR_RANGE, "segment spans more than 16383 grid cells along an axis");
+    if (errbits & pb::kErrMixed) return fail(ctx, PB_ERR_MIXED_CLASS, "segment mixes classes (unsupported)");
+    const int K = ctx->h_scalars[3];
+    *n_clusters_out = K;
+    if (K > 0) {
+        if (!center || !clt_sem || 3LL * K > center_cap || K > clt_sem_cap)
+            return fail(ctx, PB_ERR_CAPACITY, "center / clt_sem capacity too small for " + std::to_string(K) + " clusters");
+        cudaMemcpyKind kind = host_io ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        PB_CUDA(cudaMemcpyAsync(center, w.center, sizeof(float) * 3 * (size_t)K, kind, st));
+        PB_CUDA(cudaMemcpyAsync(clt_sem, w.clt_sem, sizeof(int) * (size_t)K, kind, st));
+    }
+    mark();  // end
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (call_clusters) {
+        // cluster counts per call: needs cluster_num on the host
+        std::vector<int> cn(S);
+        const int *src = cluster_num;
+        if (!host_io) {
+            PB_CUDA(cudaMemcpy(cn.data(), cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost));
+            src = cn.data();
+        }
+        int s = 0;
+        for (int c = 0; c < n_calls; c++) {
+            long long t = 0;
+            for (int k = 0; k < call_seg_counts[c]; k++) t += src[s + k];
+            call_clusters[c] = t;
+            s += call_seg_counts[c];
+        }
+    }
+    if (prof) {
+        for (int i = 0; i < ST_COUNT; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+        ctx->counters[0] = (int64_t)ctx->h_counters[0];
+        ctx->counters[1] = (int64_t)ctx->h_counters[1];
+        ctx->counters[2] = (int64_t)ctx->h_counters[2];
+        ctx->counters[3] = (int64_t)ctx->h_scalars[4];
+        ctx->counters[4] = (int64_t)ctx->h_scalars[1];
+        ctx->counters[5] = (int64_t)ctx->h_scalars[2];
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo,
+                                         const float *yo, const float *zo, const int32_t *sem, const int32_t *seg_counts,
+                                         int32_t n_seg, const int32_t *call_seg_counts, int32_t n_calls, int64_t n_pts,
+                                         const float *radius, const int32_t *min_pts, float para_f, int assign_lp,
+                                         int32_t *cluster_id, int32_t *cluster_num, int32_t *degree, float *center,
+                                         int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap,
+                                         int64_t *n_clusters_out, int64_t *call_clusters, int mem_kind, void *stream) {
+    return run_impl(ctx, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, call_seg_counts, n_calls, n_pts, radius, min_pts,
+                    para_f, assign_lp, cluster_id, cluster_num, degree, center, center_cap, clt_sem, clt_sem_cap,
+                    n_clusters_out, call_clusters, mem_kind, stream);
+}
+
+extern "C" int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo,
+                                 const float *yo, const float *zo, const int32_t *sem, const int32_t *seg_counts,
+                                 int32_t n_seg, int64_t n_pts, const float *radius, const int32_t *min_pts, float para_f,
+                                 int assign_lp, int32_t *cluster_id, int32_t *cluster_num, int32_t *degree, float *center,
+                                 int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap, int64_t *n_clusters_out,
+                                 int mem_kind, void *stream) {
+    int32_t one = n_seg;
+    return run_impl(ctx, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, &one, 1, n_pts, radius, min_pts, para_f, assign_lp,
+                    cluster_id, cluster_num, degree, center, center_cap, clt_sem, clt_sem_cap, n_clusters_out, nullptr,
+                    mem_kind, stream);
+}

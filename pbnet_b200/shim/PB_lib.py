@@ -1,0 +1,53 @@
+"""Drop-in module named ``PB_lib``: put ``pbnet_b200/shim`` on ``sys.path`` (or call
+``pbnet_b200.install_shim()``) and the reference's unmodified wrapper
+``lib/PB_lib/torch_io/pbnet_ops.py`` imports this instead of the reference's pybind11 extension.
+
+Surface = the four ``m.def`` of lib/PB_lib/src/PB_lib_api.cpp:7-10.  ``binary_cluster`` keeps the
+20-argument positional signature of lib/PB_lib/src/pbnet/cluster.h:13-18 and the reference's in-place
+output convention (cluster.cu:112-118: ``center`` / ``clt_sem`` are resized to 3*K / K).
+"""
+from __future__ import annotations
+
+import torch
+
+from pbnet_b200.cluster import default_context
+
+
+def binary_cluster(x, y, z, l1_norm, index_mapper, xo, yo, zo, sem, ins_bp, radius, min_pts, cluster_id,
+                   cluster_num, den_queue, center, clt_sem, batch_size, para_f, nv_flag):
+    """``l1_norm`` / ``index_mapper`` only steer the reference's slab pruning
+    (binary.cu:49-69) and are accepted but unused.  Tensors may be CPU (as the reference requires) or
+    all-CUDA (zero-copy fast path)."""
+    dev = x.device.index if x.is_cuda else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    ctx = default_context(dev)
+    n = x.shape[0]
+    cap_c = center if center.shape[0] >= 3 * max(n, 1) else torch.empty(3 * max(n, 1), dtype=torch.float32,
+                                                                       device=center.device)
+    cap_s = clt_sem if clt_sem.shape[0] >= max(n, 1) else torch.empty(max(n, 1), dtype=torch.int32,
+                                                                     device=clt_sem.device)
+    segs = ins_bp[:int(batch_size)]
+    out = ctx.binary_cluster(x, y, z, xo, yo, zo, sem, segs, radius, min_pts, float(para_f), bool(nv_flag),
+                             cluster_id=cluster_id, cluster_num=cluster_num, degree=den_queue, center=cap_c,
+                             clt_sem=cap_s)
+    k = out["n_clusters"]
+    if cap_c is center:
+        center.resize_(3 * k)
+    else:
+        center.resize_(3 * k).copy_(cap_c[:3 * k])
+    if cap_s is clt_sem:
+        clt_sem.resize_(k)
+    else:
+        clt_sem.resize_(k).copy_(cap_s[:k])
+    return None
+
+
+def _not_on_path(name, where):
+    def f(*a, **k):
+        raise NotImplementedError(f"PB_lib.{name} ({where}) is outside the grouping hot path; see DESIGN.md 'next'")
+    f.__name__ = name
+    return f
+
+
+get_iou = _not_on_path("get_iou", "lib/PB_lib/src/iou/get_iou.cu")
+cal_iou_and_masklabel = _not_on_path("cal_iou_and_masklabel", "lib/PB_lib/src/cal_iou_and_masklabel")
+cal_normal_line = _not_on_path("cal_normal_line", "lib/PB_lib/src/normal/cal_normal.cu")

@@ -1,0 +1,140 @@
+"""-m gpu parity tests: the sm_100a path (through the C ABI) against the committed golden vectors of the
+compiled reference and against the CPU oracle on seeded synthetic scenes."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pbnet_b200.cluster import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("path", H.golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_reference_vectors(ctx, path):
+    """Outputs of the UNMODIFIED compiled reference (tests/golden/make_golden.py) on a B200."""
+    d, ref = H.load_golden(path)
+    seg = d["seg_counts"]
+    if not H.is_single_class(d["sem"], seg):
+        from pbnet_b200._lib import PBError
+        with pytest.raises(PBError) as e:
+            H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]))
+        assert e.value.code == 6  # PB_ERR_MIXED_CLASS: documented gap, fails loudly
+        return
+    got = H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]))
+    assert H.diff_report(got, ref) == []
+
+
+@pytest.mark.parametrize("device", [False, True], ids=["host", "device"])
+@pytest.mark.parametrize("seed,npts,copies", [(31, 40000, 1), (32, 40000, 3), (33, 150000, 1)])
+def test_scene_per_class_calls_vs_oracle(ctx, seed, npts, copies, device):
+    from oracle import pb_oracle as po
+    from pbnet_b200 import scenes
+    sc = scenes.make_scene(seed, npts)
+    for c in scenes.class_calls(sc, copies):
+        want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], H.R18, H.M18)
+        got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=device)
+        assert H.diff_report(got, want) == [], f"class {c['sem_id']}"
+
+
+@pytest.mark.parametrize("radius", [0.02, 0.03, 0.06])
+def test_radius_sweep_vs_oracle(ctx, radius):
+    from oracle import pb_oracle as po
+    from pbnet_b200 import scenes
+    sc = scenes.make_scene(41, 60000)
+    r18 = np.full(18, np.float32(radius), np.float32)
+    for c in scenes.class_calls(sc, 1):
+        want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], r18, H.M18)
+        got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], radius=r18)
+        assert H.diff_report(got, want) == [], f"class {c['sem_id']} r={radius}"
+
+
+def test_batched_equals_separate_calls(ctx):
+    """pb_binary_cluster_batched over all per-class calls of several scenes == the calls one by one."""
+    from oracle import pb_oracle as po
+    from pbnet_b200 import scenes
+    calls = []
+    for seed in (51, 52, 53):
+        calls += scenes.class_calls(scenes.make_scene(seed, 50000), 3 if seed == 52 else 1)
+    xs = np.concatenate([c["xyz_shift"] for c in calls])
+    xo = np.concatenate([c["xyz_orig"] for c in calls])
+    sem = np.concatenate([c["sem"] for c in calls])
+    seg = np.concatenate([c["seg_counts"] for c in calls])
+    csc = np.array([len(c["seg_counts"]) for c in calls], np.int32)
+    got = H.run_cuda(ctx, xs, xo, sem, seg, call_seg_counts=csc, device=True)
+    o = 0
+    so = 0
+    ko = 0
+    for i, c in enumerate(calls):
+        want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], H.R18, H.M18)
+        n = len(c["sem"])
+        k = int(want["cluster_num"].sum())
+        part = dict(cluster_id=got["cluster_id"][o:o + n], den_queue=got["den_queue"][o:o + n],
+                    cluster_num=got["cluster_num"][so:so + len(c["seg_counts"])],
+                    center=got["center"][3 * ko:3 * (ko + k)], clt_sem=got["clt_sem"][ko:ko + k])
+        assert H.diff_report(part, want) == [], f"call {i}"
+        assert int(got["call_clusters"][i]) == k
+        o += n
+        so += len(c["seg_counts"])
+        ko += k
+    assert got["n_clusters"] == ko
+
+
+def test_edge_cases(ctx):
+    from oracle import pb_oracle as po
+    from pbnet_b200._lib import PBError
+    rng = np.random.Generator(np.random.PCG64(5))
+    # empty call / empty segments
+    e = np.zeros((0, 3), np.float32)
+    got = H.run_cuda(ctx, e, e, np.zeros(0, np.int32), [0, 0])
+    assert got["n_clusters"] == 0 and got["cluster_num"].tolist() == [0, 0]
+    # ragged segments incl. empty ones, tiny blobs below / above the fragment threshold (class 17: 48)
+    p = rng.normal(0, 0.012, size=(1000, 3)).astype(np.float32)
+    seg = [0, 47, 0, 48, 200, 1, 704, 0]
+    sem = np.full(1000, 17, np.int32)
+    want = po.oracle_binary_cluster(p, p * 2, sem, seg, H.R18, H.M18)
+    got = H.run_cuda(ctx, p, p * 2, sem, seg)
+    assert H.diff_report(got, want) == []
+    # exact duplicates and ties in the 1-NN (all labelled points equidistant -> largest index wins)
+    q = np.repeat(rng.normal(0, 0.01, size=(60, 3)).astype(np.float32), 4, axis=0)
+    far = np.tile(np.array([[5, 5, 5]], np.float32), (10, 1))
+    xs = np.concatenate([q, far + rng.normal(0, 1, size=(10, 3)).astype(np.float32)])
+    xo = np.concatenate([np.zeros_like(q), far])
+    sem = np.full(len(xs), 17, np.int32)
+    want = po.oracle_binary_cluster(xs, xo, sem, [len(xs)], H.R18, H.M18)
+    got = H.run_cuda(ctx, xs, xo, sem, [len(xs)])
+    assert H.diff_report(got, want) == []
+    # error behaviour: class out of range, NaN, mixed classes -> error codes, never exit()
+    bad = np.full(10, 1, np.int32)
+    with pytest.raises(PBError) as ei:
+        H.run_cuda(ctx, p[:10], p[:10], bad, [10])
+    assert ei.value.code == 3
+    pn = p[:10].copy()
+    pn[3, 1] = np.nan
+    with pytest.raises(PBError) as ei:
+        H.run_cuda(ctx, pn, p[:10], np.full(10, 5, np.int32), [10])
+    assert ei.value.code == 4
+    with pytest.raises(PBError) as ei:
+        H.run_cuda(ctx, p[:10], p[:10], np.full(10, 5, np.int32), [4, 5])
+    assert ei.value.code == 1
+
+
+def test_dropin_pbnet_ops_surface(ctx):
+    """pbnet_b200.pbnet_ops.cluster mirrors the reference wrapper: CPU tensors and CUDA tensors."""
+    import torch
+    from oracle import pb_oracle as po
+    from pbnet_b200 import pbnet_ops, scenes
+    sc = scenes.make_scene(61, 40000)
+    c = scenes.class_calls(sc, 3)[0]
+    want = po.oracle_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], 0.04, 31)
+    for dev in ("cpu", "cuda"):
+        a = pbnet_ops.cluster(torch.from_numpy(c["xyz_shift"]).to(dev), torch.from_numpy(c["xyz_orig"]).to(dev),
+                              torch.from_numpy(c["sem"]).to(dev), torch.from_numpy(c["seg_counts"]), 0.04, 31, 3)
+        for g, w in zip(a, want):
+            assert np.array_equal(g.cpu().numpy().view(np.uint32), np.asarray(w).view(np.uint32))
