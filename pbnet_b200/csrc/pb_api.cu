@@ -142,14 +142,15 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     int *seg_start, *seg_call_first;
     pb::SegArrays sg;
     // per point
-    int *seg_of, *cell_of, *deg_sorted, *head, *tmp_scan, *raw_label, *flag, *gid_at, *qflag, *qpos, *labflag, *lpos, *qlist;
+    int *seg_of, *fcell_of, *row_of, *deg_sorted, *head_f, *head_c, *head_r, *ex_f, *ex_c, *ex_r, *raw_label, *flag, *gid_at,
+        *qflag, *qpos, *labflag, *lpos, *qlist, *inv2;
     uint64_t *key1, *key1_alt, *key2, *key2_alt;
     uint32_t *val, *order1, *order2;
-    float4 *pts4, *lab4, *box_lo, *box_hi;
-    // per cell (upper bound N)
-    int *cell_start, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid;
-    uint64_t *cell_key;
-    int2 *runs;
+    float4 *pts4, *lab4, *box_lo, *box_hi, *box2_lo, *box2_hi;
+    // per fine cell / coarse cell (upper bound N)
+    int *fcell_start, *fcell_cc, *cc_pstart, *cc_fstart, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid;
+    uint64_t *fcell_key, *cc_key;
+    int2 *runs9;
     // per raw cluster (upper bound N)
     int *rep, *raw_count, *keep, *kscan, *clt_seg;
     // scalars
@@ -179,18 +180,23 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_
     w.sg.enc_min_s = a.get<unsigned>(3 * S); w.sg.enc_min_o = a.get<unsigned>(3 * S); w.sg.enc_max_o = a.get<unsigned>(3 * S);
     w.sg.cls = a.get<int>(S); w.sg.min_pts = a.get<int>(S); w.sg.r2 = a.get<float>(S); w.sg.inv_h = a.get<float>(S);
     w.sg.min_s = a.get<float>(3 * S); w.sg.min_o = a.get<float>(3 * S); w.sg.inv_g = a.get<float>(S);
-    w.sg.cell_start = a.get<int>(S + 1); w.sg.lab_start = a.get<int>(S + 1); w.sg.id_base = a.get<int>(S);
+    w.sg.cc_start = a.get<int>(S + 1); w.sg.lab_start = a.get<int>(S + 1); w.sg.id_base = a.get<int>(S);
     w.sg.k_base = a.get<int>(S); w.sg.cluster_num = a.get<int>(S);
-    w.seg_of = a.get<int>(N); w.cell_of = a.get<int>(N); w.deg_sorted = a.get<int>(N); w.head = a.get<int>(N);
-    w.tmp_scan = a.get<int>(N); w.raw_label = a.get<int>(N); w.flag = a.get<int>(N); w.gid_at = a.get<int>(N);
+    w.seg_of = a.get<int>(N); w.fcell_of = a.get<int>(N); w.row_of = a.get<int>(N); w.deg_sorted = a.get<int>(N);
+    w.head_f = a.get<int>(N); w.head_c = a.get<int>(N); w.head_r = a.get<int>(N);
+    w.ex_f = a.get<int>(N); w.ex_c = a.get<int>(N); w.ex_r = a.get<int>(N);
+    w.raw_label = a.get<int>(N); w.flag = a.get<int>(N); w.gid_at = a.get<int>(N);
     w.qflag = a.get<int>(N); w.qpos = a.get<int>(N); w.labflag = a.get<int>(N); w.lpos = a.get<int>(N); w.qlist = a.get<int>(N);
+    w.inv2 = a.get<int>(N);
     w.key1 = a.get<uint64_t>(N); w.key1_alt = a.get<uint64_t>(N); w.key2 = a.get<uint64_t>(N); w.key2_alt = a.get<uint64_t>(N);
     w.val = a.get<uint32_t>(N); w.order1 = a.get<uint32_t>(N); w.order2 = a.get<uint32_t>(N);
     w.pts4 = a.get<float4>(N); w.lab4 = a.get<float4>(N);
     w.box_lo = a.get<float4>(N / 32 + 2); w.box_hi = a.get<float4>(N / 32 + 2);
-    w.cell_start = a.get<int>(N + 1); w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N);
-    w.comp_min = a.get<int>(N); w.cell_gid = a.get<int>(N); w.cell_key = a.get<uint64_t>(N);
-    w.runs = a.get<int2>(N * pb::kRuns);
+    w.box2_lo = a.get<float4>(N / 1024 + 2); w.box2_hi = a.get<float4>(N / 1024 + 2);
+    w.fcell_start = a.get<int>(N + 1); w.fcell_cc = a.get<int>(N); w.cc_pstart = a.get<int>(N + 1); w.cc_fstart = a.get<int>(N + 1);
+    w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N);
+    w.comp_min = a.get<int>(N); w.cell_gid = a.get<int>(N); w.fcell_key = a.get<uint64_t>(N); w.cc_key = a.get<uint64_t>(N);
+    w.runs9 = a.get<int2>(N * pb::kRuns);
     w.rep = a.get<int>(N); w.raw_count = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
     w.d_scalars = a.get<int>(16);
     w.d_counters = a.get<unsigned long long>(8);
@@ -327,8 +333,8 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     PB_CUDA(cudaMemsetAsync(w.d_counters, 0, sizeof(unsigned long long) * 8, st));
     PB_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int) * (size_t)n, st));
     PB_CUDA(cudaMemsetAsync(w.raw_count, 0, sizeof(int) * (size_t)n, st));
-    int *d_err = w.d_scalars, *d_C = w.d_scalars + 1, *d_R = w.d_scalars + 2, *d_K = w.d_scalars + 3,
-        *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5;
+    int *d_err = w.d_scalars, *d_F = w.d_scalars + 1, *d_R = w.d_scalars + 2, *d_K = w.d_scalars + 3,
+        *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5, *d_Cc = w.d_scalars + 6, *d_rows = w.d_scalars + 7;
     unsigned long long *cnt = prof ? w.d_counters : nullptr;
 
     auto scan = [&](const int *in, int n_host, const int *n_dev, int *out, int *total) {
@@ -361,36 +367,41 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     const uint64_t *skey = w.key1_alt;
 
     mark();  // GRID
-    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.head);
+    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.head_f, w.head_c, w.head_r);
     L++;
-    scan(w.head, n, nullptr, w.tmp_scan, d_C);  // d_C is overwritten by k_cells with the same value
-    pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head, w.tmp_scan, w.cell_of, w.cell_start, w.cell_key, w.parent, w.cell_hp,
-                                  w.cell_minhp, w.comp_min, d_C);
-    pb::k_seg_cells<<<gS, T, 0, st>>>(n, S, w.sg, w.cell_of, d_C);
-    pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cell_key, d_C, w.runs);
+    scan(w.head_f, n, nullptr, w.ex_f, d_F);  // d_F / d_Cc are rewritten by k_cells with the same values
+    scan(w.head_c, n, nullptr, w.ex_c, d_Cc);
+    scan(w.head_r, n, nullptr, w.ex_r, d_rows);
+    pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head_f, w.ex_f, w.head_c, w.ex_c, w.head_r, w.ex_r, w.fcell_of, w.row_of,
+                                  w.fcell_start, w.fcell_key, w.fcell_cc, w.cc_pstart, w.cc_fstart, w.cc_key, w.parent,
+                                  w.cell_hp, w.cell_minhp, w.comp_min, d_F, d_Cc);
+    pb::k_seg_cells<<<gS, T, 0, st>>>(n, S, w.sg, w.fcell_of, w.fcell_cc, d_Cc);
+    pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
     L += 3;
+    pb::Grid grid;
+    grid.pts4 = w.pts4; grid.fcell_of = w.fcell_of; grid.row_of = w.row_of; grid.fcell_start = w.fcell_start;
+    grid.fcell_key = w.fcell_key; grid.fcell_cc = w.fcell_cc; grid.cc_pstart = w.cc_pstart; grid.cc_fstart = w.cc_fstart;
+    grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
 
     mark();  // DEGREE
-    pb::k_degree<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_start, w.cell_key, w.runs,
-                                                 w.deg_sorted, cnt);
+    pb::k_degree<<<div_up(n, pb::kWindow * 4), 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
     L++;
     mark();  // HP
-    pb::k_hp_cells<<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_key, w.deg_sorted, d_degree, w.cell_hp,
+    pb::k_hp_cells<<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
                                      w.cell_minhp, cnt);
     L++;
     mark();  // UNION
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, w.pts4, w.cell_start, w.cell_key, w.runs, w.cell_hp, w.parent, d_C);
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent);
     L++;
     mark();  // COMPONENTS
-    pb::k_comp_min<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.cell_minhp, w.comp_min);
-    pb::k_flag_roots<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.comp_min, w.flag);
+    pb::k_comp_min<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min);
+    pb::k_flag_roots<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag);
     L += 2;
     scan(w.flag, n, nullptr, w.gid_at, d_R);
-    pb::k_cell_gid<<<gPersist, T, 0, st>>>(d_C, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep);
+    pb::k_cell_gid<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep);
     L++;
     mark();  // LABEL
-    pb::k_label<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, w.pts4, w.cell_of, w.cell_start, w.cell_key, w.runs, w.cell_hp,
-                                                w.cell_gid, w.raw_label, w.raw_count);
+    pb::k_label<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label, w.raw_count);
     L++;
     mark();  // FILTER
     pb::k_filter<<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, w.thresh, w.keep);
@@ -402,23 +413,24 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     L += 2;
     mark();  // LP_BUILD
     if (assign_lp) {
-        pb::k_lab_flags<<<gN, T, 0, st>>>(n, w.order2, d_cluster_id, w.labflag);
+        pb::k_lab_flags<<<gN, T, 0, st>>>(n, w.order2, d_cluster_id, w.labflag, w.inv2);
         L++;
         scan(w.qflag, n, nullptr, w.qpos, d_Q);
         scan(w.labflag, n, nullptr, w.lpos, d_L);
         pb::k_compact<<<gN, T, 0, st>>>(n, w.qflag, w.qpos, w.qlist, w.order2, w.labflag, w.lpos, dxo, dyo, dzo, w.lab4);
         pb::k_seg_lab<<<gS, T, 0, st>>>(n, S, w.sg, w.lpos, d_L);
         pb::k_lab_boxes<<<gPersist, T, 0, st>>>(d_L, w.lab4, w.box_lo, w.box_hi);
-        L += 3;
+        pb::k_lab_boxes2<<<gPersist, T, 0, st>>>(d_L, w.box_lo, w.box_hi, w.box2_lo, w.box2_hi);
+        L += 4;
     }
     mark();  // LP_NN
     if (assign_lp) {
-        pb::k_nn<<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, dxo, dyo, dzo, w.lab4, w.box_lo, w.box_hi,
-                                         d_cluster_id, cnt);
+        pb::k_nn<<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, w.inv2, w.lpos, dxo, dyo, dzo, w.lab4, w.box_lo,
+                                         w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id);
         L++;
     }
     mark();  // CENTRES
-    pb::k_centres<<<gPersist, 128, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, w.center);
+    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, w.center);
     L++;
     mark();  // D2H
     PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));

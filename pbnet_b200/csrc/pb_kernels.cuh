@@ -3,29 +3,33 @@
 // Reference semantics: SURVEY.md Appendix A (normative restatement of
 // lib/PB_lib/src/pbnet/{cluster.cu,binary.cu,binary_cuda_functions.cu}).  Nothing here is a
 // translation of those kernels: the reference materialises neighbour lists and drives a BFS from the
-// host; this file works on a sorted cell grid with a cell-level union-find.
+// host; this file works on a two-level sorted cell grid with a cell-level union-find.
 //
 // Data layout in HBM (N points of all segments concatenated, S segments):
-//   pts4[N]      float4 {x,y,z, bits(orig_index | HP<<31)} in (segment, cell) order  — one 16-B
-//                broadcast load per candidate in the pair-test loops
-//   cell_*[C]    one entry per occupied grid cell (edge h = r/2*(1+2^-7)); cells of a segment are
-//                contiguous and sorted (z,y,x)-major so a stencil row is ONE contiguous point range
-//   runs[C*25]   the 25 stencil rows of every cell as cell-ordinal ranges
-// Grid-cell edge h < r/sqrt(3): any two points of one cell are neighbours, so HP connectivity is a
-// union-find over CELLS, not points (k_union), and border LPs only probe cells whose cluster id could
-// still raise their maximum (k_label).
+//   pts4[N]       float4 {x,y,z, bits(orig_index | HP<<31)} sorted by
+//                 key = seg | coarse(z,y,x) | fine(z,y,x bit)  — one 16-B broadcast load per candidate
+//   fine cells    edge h = r/2*(1+2^-7) < r/sqrt(3): any two points of one fine cell are neighbours,
+//                 so HP connectivity is a union-find over FINE CELLS (k_union) and border LPs only
+//                 probe cells whose cluster id could still raise their maximum (k_label)
+//   coarse cells  2x2x2 fine cells, edge >= r: the 27-cell stencil (9 contiguous x-rows, runs9[])
+//                 is a superset of the r-ball; candidates are enumerated per coarse ROW so that a
+//                 warp's 128 query points share one candidate stream (k_degree)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pb {
 
-constexpr int kCellBits = 14;
+constexpr int kCellBits = 14;                  // fine cell coordinate bits per axis
 constexpr int kCellMax = (1 << kCellBits) - 1;
-constexpr int kSegShift = 3 * kCellBits;  // 42
-constexpr int kRuns = 25;                 // 5 x 5 stencil rows, each up to 5 cells long
+constexpr int kCoarseBits = kCellBits - 1;     // 13
+constexpr int kCoarseMax = (1 << kCoarseBits) - 1;
+constexpr int kSegShift = 3 * kCellBits;       // 42: key = seg<<42 | cz'<<29 | cy'<<16 | cx'<<3 | fine bits
+constexpr int kRowShift = 3 + kCoarseBits;     // 16: key >> 16 identifies (seg, cz', cy') = one coarse row
+constexpr int kRuns = 9;                       // 3 x 3 coarse stencil rows, each up to 3 coarse cells long
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHpBit = 0x80000000;
+constexpr int kWindow = 128;                   // query points per warp in k_degree (4 per lane)
 
 enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8 };
 
@@ -59,22 +63,32 @@ struct SegArrays {
     float *min_s;         // [3S]
     float *min_o;         // [3S]
     float *inv_g;         // [S]
-    int *cell_start;      // [S+1] first cell ordinal of each segment
+    int *cc_start;        // [S+1] first coarse-cell ordinal of each segment
     int *lab_start;       // [S+1] first labelled-list position of each segment
     int *id_base;         // [S] global kept-cluster index at which this segment's CALL starts
     int *k_base;          // [S] global kept-cluster index of this segment's first cluster
     int *cluster_num;     // [S]
 };
 
+struct Grid {             // two-level cell table (device pointers)
+    const float4 *pts4;
+    const int *fcell_of;      // [N] fine-cell ordinal of every sorted point
+    const int *row_of;        // [N] coarse-row ordinal of every sorted point
+    const int *fcell_start;   // [F+1] first sorted point of every fine cell
+    const uint64_t *fcell_key;// [F] full sort key of the fine cell
+    const int *fcell_cc;      // [F] coarse-cell ordinal of the fine cell
+    const int *cc_pstart;     // [Cc+1] first sorted point of every coarse cell
+    const int *cc_fstart;     // [Cc+1] first fine cell of every coarse cell
+    const uint64_t *cc_key;   // [Cc] key >> 3
+    const int2 *runs9;        // [Cc*9] coarse-cell ordinal ranges of the 9 stencil rows
+    const int *d_F;           // number of fine cells
+    const int *d_Cc;          // number of coarse cells
+};
+
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
 
 __device__ __forceinline__ uint64_t spread3(uint32_t v) {
     uint64_t x = v & 0x1fffffu;
@@ -84,6 +98,13 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v) {
     x = (x | (x << 4)) & 0x10c30c30c30c30c3ULL;
     x = (x | (x << 2)) & 0x1249249249249249ULL;
     return x;
+}
+
+// fine cell coordinates from a full key
+__device__ __forceinline__ void key_fine(uint64_t key, int &cx, int &cy, int &cz) {
+    cx = (int)(((key >> 3) & kCoarseMax) << 1) | (int)(key & 1);
+    cy = (int)(((key >> (3 + kCoarseBits)) & kCoarseMax) << 1) | (int)((key >> 1) & 1);
+    cz = (int)(((key >> (3 + 2 * kCoarseBits)) & kCoarseMax) << 1) | (int)((key >> 2) & 1);
 }
 
 __device__ __forceinline__ int uf_find(int *parent, int x) {
@@ -187,8 +208,9 @@ __global__ void k_seg_params(int n, int S, SegArrays sg, const int *__restrict__
     sg.min_pts[s] = min_pts_tab[c - 2];
     float r = radius_tab[c - 2];
     sg.r2[s] = __fmul_rn(r, r);  // binary_cuda_functions.cu:85  cur_radius * cur_radius
-    // cell edge h = r/2 * (1 + 2^-7): h*sqrt(3) < r (one cell = clique) and 2 cells >= r (5^3 stencil
-    // is a superset of the r-ball) with margins far above fp32 rounding of the cell coordinate
+    // fine cell edge h = r/2 * (1 + 2^-7): h*sqrt(3) < r (one fine cell = clique) and the coarse cell
+    // (2h >= r) makes the 3^3 coarse stencil a superset of the r-ball, with margins far above the
+    // fp32 rounding of the cell coordinate
     float h = r * 0.5f * (1.0f + 1.0f / 128.0f);
     if (!(h > 0.f)) h = 1e-6f;
     sg.inv_h[s] = 1.0f / h;
@@ -207,7 +229,7 @@ __global__ void k_seg_params(int n, int S, SegArrays sg, const int *__restrict__
     sg.inv_g[s] = 1.0f / g;
 }
 
-// K3  per point: 64-bit sort keys.  key1 = seg | cz | cy | cx (shifted space, cell edge h);
+// K3  per point: 64-bit sort keys.  key1 = seg | coarse z,y,x | fine z,y,x bit (shifted space);
 //     key2 = seg | morton(original space, cell edge g) for the LP-assignment ordering
 __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const float *__restrict__ y,
                        const float *__restrict__ z, const float *__restrict__ xo,
@@ -220,185 +242,243 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
     int s = seg_of[i];
     if (sem[i] != sg.cls[s]) atomicOr(err, kErrMixed);
     float ih = sg.inv_h[s];
-    int c[3];
-    float v[3] = {x[i], y[i], z[i]};
-    int e = 0;
-    for (int k = 0; k < 3; k++) {
-        float f = __fmul_rn(__fsub_rn(v[k], sg.min_s[3 * s + k]), ih);
-        int q = (f >= 0.f && f < 1e9f) ? (int)f : 0;
-        if (q > kCellMax) {
-            q = kCellMax;
-            e = kErrRange;
-        }
-        c[k] = q;
+    float fx = __fmul_rn(__fsub_rn(x[i], sg.min_s[3 * s]), ih);
+    float fy = __fmul_rn(__fsub_rn(y[i], sg.min_s[3 * s + 1]), ih);
+    float fz = __fmul_rn(__fsub_rn(z[i], sg.min_s[3 * s + 2]), ih);
+    int cx = (fx >= 0.f && fx < 1e9f) ? (int)fx : 0;
+    int cy = (fy >= 0.f && fy < 1e9f) ? (int)fy : 0;
+    int cz = (fz >= 0.f && fz < 1e9f) ? (int)fz : 0;
+    if (cx > kCellMax || cy > kCellMax || cz > kCellMax) {
+        atomicOr(err, kErrRange);
+        cx = min(cx, kCellMax), cy = min(cy, kCellMax), cz = min(cz, kCellMax);
     }
-    if (e) atomicOr(err, e);
-    key1[i] = ((uint64_t)s << kSegShift) | ((uint64_t)c[2] << (2 * kCellBits)) | ((uint64_t)c[1] << kCellBits) |
-              (uint64_t)c[0];
+    key1[i] = ((uint64_t)s << kSegShift) | ((uint64_t)(cz >> 1) << (3 + 2 * kCoarseBits)) |
+              ((uint64_t)(cy >> 1) << (3 + kCoarseBits)) | ((uint64_t)(cx >> 1) << 3) |
+              (uint64_t)(((cz & 1) << 2) | ((cy & 1) << 1) | (cx & 1));
     float ig = sg.inv_g[s];
-    float o[3] = {xo[i], yo[i], zo[i]};
-    uint32_t m[3];
-    for (int k = 0; k < 3; k++) {
-        float f = (o[k] - sg.min_o[3 * s + k]) * ig;
-        int q = (f >= 0.f && f < 1e9f) ? (int)f : 0;
-        m[k] = (uint32_t)min(q, kCellMax);
-    }
-    key2[i] = ((uint64_t)s << kSegShift) | spread3(m[0]) | (spread3(m[1]) << 1) | (spread3(m[2]) << 2);
+    float gx = (xo[i] - sg.min_o[3 * s]) * ig, gy = (yo[i] - sg.min_o[3 * s + 1]) * ig,
+          gz = (zo[i] - sg.min_o[3 * s + 2]) * ig;
+    uint32_t mx = (uint32_t)min((gx >= 0.f && gx < 1e9f) ? (int)gx : 0, kCellMax);
+    uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kCellMax);
+    uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kCellMax);
+    key2[i] = ((uint64_t)s << kSegShift) | spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
     val[i] = (uint32_t)i;
 }
 
-// K4  after sort 1: gather coordinates into cell order, flag cell heads
+// K4  after sort 1: gather coordinates into cell order, flag fine-cell / coarse-cell / row heads
 __global__ void k_gather_heads(int n, const uint64_t *__restrict__ skey, const uint32_t *__restrict__ order,
                                const float *__restrict__ x, const float *__restrict__ y,
-                               const float *__restrict__ z, float4 *__restrict__ pts4, int *__restrict__ head) {
+                               const float *__restrict__ z, float4 *__restrict__ pts4, int *__restrict__ head_f,
+                               int *__restrict__ head_c, int *__restrict__ head_r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t o = order[i];
     pts4[i] = make_float4(x[o], y[o], z[o], __int_as_float((int)o));
-    head[i] = (i == 0 || skey[i] != skey[i - 1]) ? 1 : 0;
+    uint64_t k = skey[i], p = i ? skey[i - 1] : ~k;
+    head_f[i] = (k != p) ? 1 : 0;
+    head_c[i] = ((k >> 3) != (p >> 3)) ? 1 : 0;
+    head_r[i] = ((k >> kRowShift) != (p >> kRowShift)) ? 1 : 0;
 }
 
-// K5  cell table from the scanned head flags
-__global__ void k_cells(int n, const uint64_t *__restrict__ skey, const int *__restrict__ head,
-                        const int *__restrict__ head_excl, int *__restrict__ cell_of,
-                        int *__restrict__ cell_start, uint64_t *__restrict__ cell_key,
-                        int *__restrict__ parent, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
-                        int *__restrict__ comp_min, int *__restrict__ d_C) {
+// K5  cell tables from the scanned head flags
+__global__ void k_cells(int n, const uint64_t *__restrict__ skey, const int *__restrict__ head_f,
+                        const int *__restrict__ ex_f, const int *__restrict__ head_c, const int *__restrict__ ex_c,
+                        const int *__restrict__ head_r, const int *__restrict__ ex_r, int *__restrict__ fcell_of,
+                        int *__restrict__ row_of, int *__restrict__ fcell_start, uint64_t *__restrict__ fcell_key,
+                        int *__restrict__ fcell_cc, int *__restrict__ cc_pstart, int *__restrict__ cc_fstart,
+                        uint64_t *__restrict__ cc_key, int *__restrict__ parent, int *__restrict__ cell_hp,
+                        int *__restrict__ cell_minhp, int *__restrict__ comp_min, int *__restrict__ d_F,
+                        int *__restrict__ d_Cc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int h = head[i];
-    int c = head_excl[i] + h - 1;
-    cell_of[i] = c;
-    if (h) {
-        cell_start[c] = i;
-        cell_key[c] = skey[i];
-        parent[c] = c;
-        cell_hp[c] = 0;
-        cell_minhp[c] = 0x7fffffff;
-        comp_min[c] = 0x7fffffff;
+    int hf = head_f[i], hc = head_c[i];
+    int f = ex_f[i] + hf - 1, c = ex_c[i] + hc - 1;
+    fcell_of[i] = f;
+    row_of[i] = ex_r[i] + head_r[i] - 1;
+    uint64_t key = skey[i];
+    if (hf) {
+        fcell_start[f] = i;
+        fcell_key[f] = key;
+        fcell_cc[f] = c;
+        parent[f] = f;
+        cell_hp[f] = 0;
+        cell_minhp[f] = 0x7fffffff;
+        comp_min[f] = 0x7fffffff;
+    }
+    if (hc) {
+        cc_pstart[c] = i;
+        cc_fstart[c] = f;
+        cc_key[c] = key >> 3;
     }
     if (i == n - 1) {
-        cell_start[c + 1] = n;
-        *d_C = c + 1;
+        fcell_start[f + 1] = n;
+        cc_pstart[c + 1] = n;
+        cc_fstart[c + 1] = f + 1;
+        *d_F = f + 1;
+        *d_Cc = c + 1;
     }
 }
 
-// K6  first cell ordinal of every segment
-__global__ void k_seg_cells(int n, int S, SegArrays sg, const int *__restrict__ cell_of,
-                            const int *__restrict__ d_C) {
+// K6  first coarse-cell ordinal of every segment
+__global__ void k_seg_cells(int n, int S, SegArrays sg, const int *__restrict__ fcell_of,
+                            const int *__restrict__ fcell_cc, const int *__restrict__ d_Cc) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > S) return;
     int b = sg.start[s];
-    sg.cell_start[s] = (b < n) ? cell_of[b] : *d_C;
+    sg.cc_start[s] = (b < n) ? fcell_cc[fcell_of[b]] : *d_Cc;
 }
 
-// K7  stencil rows of every cell: runs[c*25 + (dz+2)*5 + (dy+2)] = [first cell, last cell+1) with
-//     cx-2 <= x <= cx+2 in row (cy+dy, cz+dz) — a contiguous range because cells are sorted x-fastest
-__global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cell_key, const int *__restrict__ d_C,
-                       int2 *__restrict__ runs) {
-    long long total = (long long)(*d_C) * kRuns;
+// K7  coarse stencil rows: runs9[c*9 + (dz+1)*3 + (dy+1)] = [first coarse cell, last+1) with
+//     cx'-1 <= x' <= cx'+1 in coarse row (cy'+dy, cz'+dz) — contiguous because cells sort x-fastest
+__global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const int *__restrict__ d_Cc,
+                       int2 *__restrict__ runs9) {
+    long long total = (long long)(*d_Cc) * kRuns;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         int c = (int)(t / kRuns), k = (int)(t % kRuns);
-        uint64_t key = cell_key[c];
-        int s = (int)(key >> kSegShift);
-        int cx = (int)(key & kCellMax), cy = (int)((key >> kCellBits) & kCellMax),
-            cz = (int)((key >> (2 * kCellBits)) & kCellMax);
-        int ny = cy + (k % 5) - 2, nz = cz + (k / 5) - 2;
+        uint64_t key = cc_key[c];  // seg<<39 | z'<<26 | y'<<13 | x'
+        int s = (int)(key >> (3 * kCoarseBits));
+        int cx = (int)(key & kCoarseMax), cy = (int)((key >> kCoarseBits) & kCoarseMax),
+            cz = (int)((key >> (2 * kCoarseBits)) & kCoarseMax);
+        int ny = cy + (k % 3) - 1, nz = cz + (k / 3) - 1;
         int2 out = make_int2(0, 0);
-        if (ny >= 0 && ny <= kCellMax && nz >= 0 && nz <= kCellMax) {
-            uint64_t base = ((uint64_t)s << kSegShift) | ((uint64_t)nz << (2 * kCellBits)) | ((uint64_t)ny << kCellBits);
-            uint64_t klo = base | (uint64_t)max(cx - 2, 0);
-            uint64_t khi = base | (uint64_t)min(cx + 2, kCellMax);  // inclusive
-            int b = sg.cell_start[s], e = sg.cell_start[s + 1];
+        if (ny >= 0 && ny <= kCoarseMax && nz >= 0 && nz <= kCoarseMax) {
+            uint64_t base = ((uint64_t)s << (3 * kCoarseBits)) | ((uint64_t)nz << (2 * kCoarseBits)) |
+                            ((uint64_t)ny << kCoarseBits);
+            uint64_t klo = base | (uint64_t)max(cx - 1, 0);
+            uint64_t khi = base | (uint64_t)min(cx + 1, kCoarseMax);  // inclusive
+            int b = sg.cc_start[s], e = sg.cc_start[s + 1];
             int lo = b, hi = e;
             while (lo < hi) {  // first cell with key >= klo
                 int mid = (lo + hi) >> 1;
-                if (__ldg(cell_key + mid) < klo) lo = mid + 1;
+                if (__ldg(cc_key + mid) < klo) lo = mid + 1;
                 else hi = mid;
             }
             int first = lo;
             hi = e;
             while (lo < hi) {  // first cell with key > khi
                 int mid = (lo + hi) >> 1;
-                if (__ldg(cell_key + mid) <= khi) lo = mid + 1;
+                if (__ldg(cc_key + mid) <= khi) lo = mid + 1;
                 else hi = mid;
             }
             out = make_int2(first, lo);
         }
-        runs[t] = out;
+        runs9[t] = out;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K8  degree (pass A) — the dominant kernel.  One warp per 32 consecutive sorted points; the lanes
-//     that share a cell walk that cell's 25 stencil rows together, every candidate is one broadcast
-//     16-B load tested by all lanes with the exact predicate.
+// K8  degree (pass A) — the dominant kernel.
+//     One warp owns a window of 128 consecutive sorted points and splits it into groups of points of
+//     the same coarse ROW.  A group shares one candidate stream: the 9 stencil rows widened to
+//     [cx'min-1, cx'max+1] (any superset of the r-ball is valid, the accept test is the exact
+//     predicate).  Every candidate is ONE broadcast 16-B load tested against up to 4 query points per
+//     lane (register tiling: the LSU write-back of a uniform LDG.128 costs 4 cycles/warp, so one load
+//     per 32 tests made the first version LSU-bound at 94 % — profiles/ncu_r01_degree_v1.txt).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_degree(int n, SegArrays sg, const float4 *__restrict__ pts4, const int *__restrict__ cell_of,
-         const int *__restrict__ cell_start, const uint64_t *__restrict__ cell_key,
-         const int2 *__restrict__ runs, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
-    int i = (blockIdx.x * blockDim.x + threadIdx.x);
-    int lane = lane_id();
-    bool valid = i < n;
-    float4 p = valid ? pts4[i] : make_float4(0, 0, 0, 0);
-    int c = valid ? cell_of[i] : -1;
-    int deg = 0;
-    unsigned long long tests = 0;  // candidate tests issued for this warp's query points (profiling)
-    unsigned todo = __ballot_sync(kFull, valid);
-    while (todo) {
-        int leader = __ffs(todo) - 1;
-        int cL = __shfl_sync(kFull, c, leader);
-        bool mine = (c == cL);
-        unsigned mask = __ballot_sync(kFull, mine);
-        todo &= ~mask;
-        float r2 = sg.r2[(int)(cell_key[cL] >> kSegShift)];
-        int jb = 0, je = 0;
-        if (lane < kRuns) {
-            int2 rr = runs[(long long)cL * kRuns + lane];
-            if (rr.y > rr.x) {
-                jb = cell_start[rr.x];
-                je = cell_start[rr.y];
-            }
-        }
-        int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
-        unsigned cand = 0;
+template <int Q>
+__device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, int g0, int total, int lane, float r2,
+                                             int jb, int je, int *__restrict__ deg_sorted) {
+    float px[Q], py[Q], pz[Q];
+    int cnt[Q];
+#pragma unroll
+    for (int s = 0; s < Q; s++) {
+        int o = 32 * s + lane;
+        float4 p = pts4[g0 + (o < total ? o : 0)];
+        px[s] = p.x, py[s] = p.y, pz[s] = p.z;
+        cnt[s] = 0;
+    }
 #pragma unroll 1
-        for (int k = 0; k < kRuns; k++) {
-            int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
-            cand += (unsigned)(e - b);
-            int j = b;
+    for (int k = 0; k < kRuns; k++) {
+        int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
+        int j = b;
+        if (Q == 1) {
             for (; j + 4 <= e; j += 4) {
                 float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-                cnt0 += sqd(p.x, p.y, p.z, q0.x, q0.y, q0.z) <= r2;
-                cnt1 += sqd(p.x, p.y, p.z, q1.x, q1.y, q1.z) <= r2;
-                cnt2 += sqd(p.x, p.y, p.z, q2.x, q2.y, q2.z) <= r2;
-                cnt3 += sqd(p.x, p.y, p.z, q3.x, q3.y, q3.z) <= r2;
+                cnt[0] += (sqd(px[0], py[0], pz[0], q0.x, q0.y, q0.z) <= r2) + (sqd(px[0], py[0], pz[0], q1.x, q1.y, q1.z) <= r2) +
+                          (sqd(px[0], py[0], pz[0], q2.x, q2.y, q2.z) <= r2) + (sqd(px[0], py[0], pz[0], q3.x, q3.y, q3.z) <= r2);
             }
-            for (; j < e; j++) {
-                float4 q0 = __ldg(pts4 + j);
-                cnt0 += sqd(p.x, p.y, p.z, q0.x, q0.y, q0.z) <= r2;
+        } else {
+            for (; j + 2 <= e; j += 2) {
+                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1);
+#pragma unroll
+                for (int s = 0; s < Q; s++)
+                    cnt[s] += (sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z) <= r2) + (sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z) <= r2);
             }
         }
-        if (mine) deg = cnt0 + cnt1 + cnt2 + cnt3 - 1;  // binary_cuda_functions.cu:88  ans - 1
-        tests += (unsigned long long)cand * (unsigned)__popc(mask);
+        for (; j < e; j++) {
+            float4 q0 = __ldg(pts4 + j);
+#pragma unroll
+            for (int s = 0; s < Q; s++) cnt[s] += sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z) <= r2;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < Q; s++) {
+        int o = 32 * s + lane;
+        if (o < total) deg_sorted[g0 + o] = cnt[s] - 1;  // binary_cuda_functions.cu:88  ans - 1 (self)
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = lane_id();
+    long long base = (long long)warp * kWindow;
+    if (base >= n) return;
+    int end = (int)min((long long)n, base + kWindow);
+    int pos = (int)base;
+    unsigned long long tests = 0;
+    while (pos < end) {  // uniform
+        int row = g.row_of[pos];
+        // group end: first position after pos whose row differs
+        int gend = end;
+#pragma unroll 1
+        for (int k = 0; k < kWindow / 32; k++) {
+            int i = pos + 1 + 32 * k + lane;
+            bool differs = (i < end) && (g.row_of[i] != row);
+            unsigned b = __ballot_sync(kFull, differs);
+            if (b) {
+                gend = pos + 1 + 32 * k + __ffs(b) - 1;
+                break;
+            }
+            if (pos + 1 + 32 * (k + 1) >= end) break;
+        }
+        int total = gend - pos;
+        int fmin = g.fcell_of[pos], fmax = g.fcell_of[gend - 1];
+        int cmin = g.fcell_cc[fmin], cmax = g.fcell_cc[fmax];
+        float r2 = sg.r2[(int)(g.fcell_key[fmin] >> kSegShift)];
+        int jb = 0, je = 0;
+        if (lane < kRuns) {
+            int c0 = g.runs9[(long long)cmin * kRuns + lane].x, c1 = g.runs9[(long long)cmax * kRuns + lane].y;
+            if (c1 > c0) {
+                jb = g.cc_pstart[c0];
+                je = g.cc_pstart[c1];
+            }
+        }
+        if (n_tests) {
+            unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
+            tests += (unsigned long long)cand * (unsigned)total;
+        }
+        if (total <= 32) degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
+        else if (total <= 64) degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
+        else if (total <= 96) degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
+        else degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
+        pos = gend;
     }
     if (n_tests && lane == 0) atomicAdd(n_tests, tests);
-    if (valid) deg_sorted[i] = deg;
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order
-__global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const int *__restrict__ cell_of,
-                           const uint64_t *__restrict__ cell_key, const int *__restrict__ deg_sorted,
+__global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const int *__restrict__ fcell_of,
+                           const uint64_t *__restrict__ fcell_key, const int *__restrict__ deg_sorted,
                            int *__restrict__ degree_out, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
                            unsigned long long *__restrict__ counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     unsigned act = __ballot_sync(kFull, valid);
     if (!valid) return;
-    int c = cell_of[i];
-    int s = (int)(cell_key[c] >> kSegShift);
+    int c = fcell_of[i];
+    int s = (int)(fcell_key[c] >> kSegShift);
     int d = deg_sorted[i];
     int *w = reinterpret_cast<int *>(pts4 + i) + 3;
     int orig = *w;
@@ -414,7 +494,6 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     }
     if (counters) {  // profiling only: [1] sum of degrees, [2] HP count
         unsigned long long dsum = 0, hsum = 0;
-        // lanes outside `act` have exited; use a full-mask-free reduction over act via atomics per warp leader
         for (unsigned m = act; m; m &= m - 1) {
             int l = __ffs(m) - 1;
             dsum += (unsigned)__shfl_sync(act, d, l);
@@ -427,59 +506,87 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     }
 }
 
+// true iff fine cells with keys ka, kb are within the 5x5x5 fine stencil of each other
+__device__ __forceinline__ bool fine_near(uint64_t ka, uint64_t kb) {
+    int ax, ay, az, bx, by, bz;
+    key_fine(ka, ax, ay, az);
+    key_fine(kb, bx, by, bz);
+    return abs(ax - bx) <= 2 && abs(ay - by) <= 2 && abs(az - bz) <= 2;
+}
+
+// cooperative search for ONE HP pair (a in A, b in B) within r; warp-uniform result
+__device__ __forceinline__ bool hp_pair_exists(const float4 *__restrict__ pts4, int a0, int a1, int b0, int b1,
+                                               float r2, int lane) {
+    for (int ia = a0; ia < a1; ia += 32) {
+        int i = ia + lane;
+        float4 p = pts4[i < a1 ? i : a0];
+        bool php = (i < a1) && (__float_as_int(p.w) & kHpBit);
+        if (!__any_sync(kFull, php)) continue;
+        for (int j = b0; j < b1; j++) {
+            float4 q = __ldg(pts4 + j);
+            if (!(__float_as_int(q.w) & kHpBit)) continue;
+            bool hit = php && (sqd(p.x, p.y, p.z, q.x, q.y, q.z) <= r2);
+            if (__any_sync(kFull, hit)) return true;
+        }
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------------------------------------
-// K10  HP connectivity (pass B): union-find over cells.  One warp per HP-cell A; for every stencil
-//      cell B > A that holds HPs and is not yet in A's set, look for ONE HP pair within r.
+// K10  HP connectivity (pass B): union-find over FINE cells.  One warp per HP-cell A; the lanes check
+//      32 stencil cells at a time (HP-bearing, inside the 5^3 fine stencil, ordinal > A, different
+//      root) and only the survivors pay a pair search that stops at the first HP pair within r.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_union(SegArrays sg, const float4 *__restrict__ pts4, const int *__restrict__ cell_start,
-        const uint64_t *__restrict__ cell_key, const int2 *__restrict__ runs,
-        const int *__restrict__ cell_hp, int *parent, const int *__restrict__ d_C) {
-    int C = *d_C;
+k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp, int *parent) {
+    int F = *g.d_F;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int A = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; A < C; A += warps) {
+    for (int A = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; A < F; A += warps) {
         if (cell_hp[A] == 0) continue;
-        float r2 = sg.r2[(int)(cell_key[A] >> kSegShift)];
-        int a0 = cell_start[A], a1 = cell_start[A + 1];
-        int2 rr = make_int2(0, 0);
-        if (lane < kRuns) rr = runs[(long long)A * kRuns + lane];
+        uint64_t kA = g.fcell_key[A];
+        float r2 = sg.r2[(int)(kA >> kSegShift)];
+        int a0 = g.fcell_start[A], a1 = g.fcell_start[A + 1];
+        int cA = g.fcell_cc[A];
+        int f0 = 0, f1 = 0;
+        if (lane < kRuns) {
+            int2 rr = g.runs9[(long long)cA * kRuns + lane];
+            if (rr.y > rr.x) {
+                f0 = g.cc_fstart[rr.x];
+                f1 = g.cc_fstart[rr.y];
+            }
+        }
+        int rootA = uf_find(parent, A);
         for (int k = 0; k < kRuns; k++) {
-            int c0 = __shfl_sync(kFull, rr.x, k), c1 = __shfl_sync(kFull, rr.y, k);
-            for (int B = max(c0, A + 1); B < c1; B++) {
-                if (cell_hp[B] == 0) continue;
-                int same = 0;
-                if (lane == 0) same = (uf_find(parent, A) == uf_find(parent, B));
-                if (__shfl_sync(kFull, same, 0)) continue;
-                int b0 = cell_start[B], b1 = cell_start[B + 1];
-                bool found = false;
-                for (int ia = a0; ia < a1 && !found; ia += 32) {
-                    int i = ia + lane;
-                    float4 p = (i < a1) ? pts4[i] : make_float4(0, 0, 0, 0);
-                    bool php = (i < a1) && (__float_as_int(p.w) & kHpBit);
-                    if (!__any_sync(kFull, php)) continue;
-                    for (int j = b0; j < b1; j++) {
-                        float4 q = __ldg(pts4 + j);
-                        if (!(__float_as_int(q.w) & kHpBit)) continue;
-                        bool hit = php && (sqd(p.x, p.y, p.z, q.x, q.y, q.z) <= r2);
-                        if (__any_sync(kFull, hit)) {
-                            found = true;
-                            break;
-                        }
+            int b = __shfl_sync(kFull, f0, k), e = __shfl_sync(kFull, f1, k);
+            for (int fb = max(b, A + 1); fb < e; fb += 32) {
+                int B = fb + lane;
+                bool cand = false;
+                if (B < e && cell_hp[B] > 0 && fine_near(kA, g.fcell_key[B])) cand = uf_find(parent, B) != rootA;
+                unsigned m = __ballot_sync(kFull, cand);
+                while (m) {
+                    int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    int Bc = fb + l;
+                    int same = 0;
+                    if (lane == 0) same = (uf_find(parent, A) == uf_find(parent, Bc));
+                    if (__shfl_sync(kFull, same, 0)) continue;
+                    if (hp_pair_exists(pts4, a0, a1, g.fcell_start[Bc], g.fcell_start[Bc + 1], r2, lane)) {
+                        if (lane == 0) uf_union(parent, A, Bc);
+                        __syncwarp();
+                        rootA = uf_find(parent, A);
                     }
                 }
-                if (found && lane == 0) uf_union(parent, A, B);
-                __syncwarp();
             }
         }
     }
 }
 
 // K11  flatten + minimum HP index of every component
-__global__ void k_comp_min(const int *__restrict__ d_C, const int *__restrict__ cell_hp, int *parent,
+__global__ void k_comp_min(const int *__restrict__ d_F, const int *__restrict__ cell_hp, int *parent,
                            const int *__restrict__ cell_minhp, int *comp_min) {
-    int C = *d_C;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    int F = *d_F;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x) {
         if (cell_hp[c] == 0) continue;
         int r = uf_find(parent, c);
         if (r != c) __stcg(parent + c, r);
@@ -489,28 +596,28 @@ __global__ void k_comp_min(const int *__restrict__ d_C, const int *__restrict__ 
 
 // K12  flag the minimum-index HP of every component (cluster numbering = rank of that index,
 //      binary.cu:161-166: seeds are taken in ascending point order)
-__global__ void k_flag_roots(const int *__restrict__ d_C, const int *__restrict__ cell_hp,
+__global__ void k_flag_roots(const int *__restrict__ d_F, const int *__restrict__ cell_hp,
                              const int *__restrict__ parent, const int *__restrict__ comp_min,
                              int *__restrict__ flag) {
-    int C = *d_C;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x)
+    int F = *d_F;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x)
         if (cell_hp[c] > 0 && parent[c] == c) flag[comp_min[c]] = 1;
 }
 
 // K13  raw cluster id of every HP-cell; representative point of every raw cluster
-__global__ void k_cell_gid(const int *__restrict__ d_C, const int *__restrict__ cell_hp,
+__global__ void k_cell_gid(const int *__restrict__ d_F, const int *__restrict__ cell_hp,
                            const int *__restrict__ parent, const int *__restrict__ comp_min,
                            const int *__restrict__ gid_at, int *__restrict__ cell_gid, int *__restrict__ rep) {
-    int C = *d_C;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-        int g = -1;
+    int F = *d_F;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x) {
+        int gi = -1;
         if (cell_hp[c] > 0) {
             int r = parent[c];
             int u = comp_min[r];
-            g = gid_at[u];
-            if (r == c) rep[g] = u;
+            gi = gid_at[u];
+            if (r == c) rep[gi] = u;
         }
-        cell_gid[c] = g;
+        cell_gid[c] = gi;
     }
 }
 
@@ -520,15 +627,13 @@ __global__ void k_cell_gid(const int *__restrict__ d_C, const int *__restrict__ 
 //      LPs with no HP neighbour stay -1.  Cluster sizes (incl. border LPs) are counted here.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_label(int n, SegArrays sg, const float4 *__restrict__ pts4, const int *__restrict__ cell_of,
-        const int *__restrict__ cell_start, const uint64_t *__restrict__ cell_key,
-        const int2 *__restrict__ runs, const int *__restrict__ cell_hp, const int *__restrict__ cell_gid,
-        int *__restrict__ raw_label, int *__restrict__ raw_count) {
+k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp,
+        const int *__restrict__ cell_gid, int *__restrict__ raw_label, int *__restrict__ raw_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int lane = lane_id();
     bool valid = i < n;
-    float4 p = valid ? pts4[i] : make_float4(0, 0, 0, 0);
-    int c = valid ? cell_of[i] : -1;
+    float4 p = pts4[valid ? i : 0];
+    int c = valid ? g.fcell_of[i] : -1;
     bool hp = valid && (__float_as_int(p.w) & kHpBit);
     int label = -1;
     if (hp) label = cell_gid[c];
@@ -539,26 +644,43 @@ k_label(int n, SegArrays sg, const float4 *__restrict__ pts4, const int *__restr
         bool mine = (c == cL) && valid && !hp;
         unsigned mask = __ballot_sync(kFull, mine);
         todo &= ~mask;
-        float r2 = sg.r2[(int)(cell_key[cL] >> kSegShift)];
-        int2 rr = make_int2(0, 0);
-        if (lane < kRuns) rr = runs[(long long)cL * kRuns + lane];
+        uint64_t kL = g.fcell_key[cL];
+        float r2 = sg.r2[(int)(kL >> kSegShift)];
+        int cc = g.fcell_cc[cL];
+        int f0 = 0, f1 = 0;
+        if (lane < kRuns) {
+            int2 rr = g.runs9[(long long)cc * kRuns + lane];
+            if (rr.y > rr.x) {
+                f0 = g.cc_fstart[rr.x];
+                f1 = g.cc_fstart[rr.y];
+            }
+        }
         int best = -1;
         for (int k = 0; k < kRuns; k++) {
-            int c0 = __shfl_sync(kFull, rr.x, k), c1 = __shfl_sync(kFull, rr.y, k);
-            for (int B = c0; B < c1; B++) {
-                if (cell_hp[B] == 0) continue;
-                int gB = cell_gid[B];
-                bool pend = mine && best < gB;
-                if (!__any_sync(kFull, pend)) continue;
-                int b0 = cell_start[B], b1 = cell_start[B + 1];
-                for (int j = b0; j < b1; j++) {
-                    float4 q = __ldg(pts4 + j);
-                    if (!(__float_as_int(q.w) & kHpBit)) continue;
-                    if (pend && sqd(p.x, p.y, p.z, q.x, q.y, q.z) <= r2) {
-                        best = gB;
-                        pend = false;
+            int b = __shfl_sync(kFull, f0, k), e = __shfl_sync(kFull, f1, k);
+            for (int fb = b; fb < e; fb += 32) {
+                int B = fb + lane;
+                int gB = -1;
+                if (B < e && cell_hp[B] > 0 && fine_near(kL, g.fcell_key[B])) gB = cell_gid[B];
+                int bestmin = __reduce_min_sync(kFull, mine ? best : 0x7fffffff);  // smallest best among my LPs
+                unsigned m = __ballot_sync(kFull, gB > bestmin);
+                while (m) {
+                    int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    int gc = __shfl_sync(kFull, gB, l);
+                    bool pend = mine && best < gc;
+                    if (!__any_sync(kFull, pend)) continue;
+                    int Bc = fb + l;
+                    int b0 = g.fcell_start[Bc], b1 = g.fcell_start[Bc + 1];
+                    for (int j = b0; j < b1; j++) {
+                        float4 q = __ldg(pts4 + j);
+                        if (!(__float_as_int(q.w) & kHpBit)) continue;
+                        if (pend && sqd(p.x, p.y, p.z, q.x, q.y, q.z) <= r2) {
+                            best = gc;
+                            pend = false;
+                        }
+                        if (!__any_sync(kFull, pend)) break;
                     }
-                    if (!__any_sync(kFull, pend)) break;
                 }
             }
         }
@@ -578,15 +700,15 @@ __global__ void k_filter(const int *__restrict__ d_R, SegArrays sg, const int *_
                          const int *__restrict__ seg_of, const int *__restrict__ raw_count,
                          const float *__restrict__ thresh18, int *__restrict__ keep) {
     int R = *d_R;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < R; g += gridDim.x * blockDim.x) {
-        int s = seg_of[rep[g]];
+    for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < R; gi += gridDim.x * blockDim.x) {
+        int s = seg_of[rep[gi]];
         float t = thresh18[sg.cls[s] - 2];
-        keep[g] = ((float)raw_count[g] < t) ? 0 : 1;
+        keep[gi] = ((float)raw_count[gi] < t) ? 0 : 1;
     }
 }
 
-__device__ __forceinline__ int kept_before(const int *kscan, const int *d_K, int g, int R) {
-    return g < R ? kscan[g] : *d_K;
+__device__ __forceinline__ int kept_before(const int *kscan, const int *d_K, int gi, int R) {
+    return gi < R ? kscan[gi] : *d_K;
 }
 
 // K16  per segment: cluster count, first kept-cluster index, id base of the segment's call
@@ -615,13 +737,13 @@ __global__ void k_relabel(int n, SegArrays sg, const int *__restrict__ seg_of, c
                           int *__restrict__ clt_seg, const int *__restrict__ rep) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n) return;
-    int g = raw_label[u];
+    int gi = raw_label[u];
     int s = seg_of[u];
     int id = -1;
-    if (g >= 0 && keep[g]) {
-        int kk = kscan[g];
+    if (gi >= 0 && keep[gi]) {
+        int kk = kscan[gi];
         id = kk - sg.id_base[s];
-        if (rep[g] == u) {
+        if (rep[gi] == u) {
             clt_sem[kk] = sg.cls[s];
             clt_seg[kk] = s;
         }
@@ -630,12 +752,15 @@ __global__ void k_relabel(int n, SegArrays sg, const int *__restrict__ seg_of, c
     qflag[u] = (id < 0 && assign_lp && sg.cluster_num[s] > 0) ? 1 : 0;
 }
 
-// K18a  labelled flags in LP-assignment order (order2 = points sorted by segment | morton(original))
+// K18a  labelled flags in LP-assignment order (order2 = points sorted by segment | morton(original));
+//       inv2 = rank of every point in that order
 __global__ void k_lab_flags(int n, const uint32_t *__restrict__ order2, const int *__restrict__ cluster_id,
-                            int *__restrict__ labflag) {
+                            int *__restrict__ labflag, int *__restrict__ inv2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    labflag[i] = cluster_id[order2[i]] >= 0 ? 1 : 0;
+    uint32_t o = order2[i];
+    labflag[i] = cluster_id[o] >= 0 ? 1 : 0;
+    inv2[o] = i;
 }
 
 // K18b  compaction: query list (input order) and labelled list (order2) as float4 {xo,yo,zo,index}
@@ -660,15 +785,15 @@ __global__ void k_seg_lab(int n, int S, SegArrays sg, const int *__restrict__ lp
     sg.lab_start[s] = b < n ? lpos[b] : *d_L;
 }
 
-// K19  bounding boxes of 32-point groups of the labelled list
+// K19  bounding boxes of the labelled list: level 1 = 32 points, level 2 = 32 level-1 boxes
 __global__ void k_lab_boxes(const int *__restrict__ d_L, const float4 *__restrict__ lab4,
                             float4 *__restrict__ box_lo, float4 *__restrict__ box_hi) {
     int L = *d_L;
     int G = (L + 31) >> 5;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
-        int j = g * 32 + lane;
+    for (int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gi < G; gi += warps) {
+        int j = gi * 32 + lane;
         float4 q = lab4[min(j, L - 1)];
         float lx = q.x, ly = q.y, lz = q.z, hx = q.x, hy = q.y, hz = q.z;
         for (int o = 16; o; o >>= 1) {
@@ -680,8 +805,32 @@ __global__ void k_lab_boxes(const int *__restrict__ d_L, const float4 *__restric
             hz = fmaxf(hz, __shfl_xor_sync(kFull, hz, o));
         }
         if (lane == 0) {
-            box_lo[g] = make_float4(lx, ly, lz, 0.f);
-            box_hi[g] = make_float4(hx, hy, hz, 0.f);
+            box_lo[gi] = make_float4(lx, ly, lz, 0.f);
+            box_hi[gi] = make_float4(hx, hy, hz, 0.f);
+        }
+    }
+}
+__global__ void k_lab_boxes2(const int *__restrict__ d_L, const float4 *__restrict__ box_lo,
+                             const float4 *__restrict__ box_hi, float4 *__restrict__ box2_lo,
+                             float4 *__restrict__ box2_hi) {
+    int L = *d_L;
+    int G = (L + 31) >> 5, G2 = (G + 31) >> 5;
+    int lane = lane_id();
+    int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g2 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g2 < G2; g2 += warps) {
+        int gi = min(g2 * 32 + lane, G - 1);
+        float4 lo = box_lo[gi], hi = box_hi[gi];
+        for (int o = 16; o; o >>= 1) {
+            lo.x = fminf(lo.x, __shfl_xor_sync(kFull, lo.x, o));
+            lo.y = fminf(lo.y, __shfl_xor_sync(kFull, lo.y, o));
+            lo.z = fminf(lo.z, __shfl_xor_sync(kFull, lo.z, o));
+            hi.x = fmaxf(hi.x, __shfl_xor_sync(kFull, hi.x, o));
+            hi.y = fmaxf(hi.y, __shfl_xor_sync(kFull, hi.y, o));
+            hi.z = fmaxf(hi.z, __shfl_xor_sync(kFull, hi.z, o));
+        }
+        if (lane == 0) {
+            box2_lo[g2] = lo;
+            box2_hi[g2] = hi;
         }
     }
 }
@@ -689,9 +838,9 @@ __global__ void k_lab_boxes(const int *__restrict__ d_L, const float4 *__restric
 // ------------------------------------------------------------------------------------------------
 // K20  LP assignment (binary.cu:270-358, binary_cuda_functions.cu:258-302): exact 1-NN over the
 //      labelled points of the same segment in ORIGINAL coordinates, ties -> largest index.
-//      One warp per query; branch-and-bound over the 32-point group boxes: sweep 1 finds the group
-//      with the smallest lower bound, sweep 2 visits every group whose bound does not exceed the best
-//      distance so far.  A group is pruned only if its (conservatively shrunk) bound is STRICTLY
+//      One warp per query, branch-and-bound over a two-level box hierarchy of the spatially sorted
+//      labelled list.  The first guess is the 32-point group at the query's own rank in that order;
+//      afterwards a box is skipped only if its (conservatively shrunk) lower bound is STRICTLY
 //      greater than the best distance, so equal-distance ties are never lost.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float box_lb(float px, float py, float pz, float4 lo, float4 hi) {
@@ -701,9 +850,9 @@ __device__ __forceinline__ float box_lb(float px, float py, float pz, float4 lo,
     return (dx * dx + dy * dy + dz * dz) * (1.0f - 1e-5f);
 }
 
-__device__ __forceinline__ void nn_scan_group(int g, int l0, int l1, int lane, float px, float py, float pz,
+__device__ __forceinline__ void nn_scan_group(int gi, int l0, int l1, int lane, float px, float py, float pz,
                                               const float4 *__restrict__ lab4, float &bestD, int &bestI) {
-    int j = g * 32 + lane;
+    int j = gi * 32 + lane;
     bool ok = j >= l0 && j < l1;
     float D = __int_as_float(0x7f800000);
     int idx = -1;
@@ -724,9 +873,10 @@ __device__ __forceinline__ void nn_scan_group(int g, int l0, int l1, int lane, f
 
 __global__ void __launch_bounds__(256)
 k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, const int *__restrict__ seg_of,
-     const float *__restrict__ xo, const float *__restrict__ yo, const float *__restrict__ zo,
-     const float4 *__restrict__ lab4, const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi,
-     int *cluster_id, unsigned long long *__restrict__ counters) {
+     const int *__restrict__ inv2, const int *__restrict__ lpos, const float *__restrict__ xo,
+     const float *__restrict__ yo, const float *__restrict__ zo, const float4 *__restrict__ lab4,
+     const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, const float4 *__restrict__ box2_lo,
+     const float4 *__restrict__ box2_hi, int *cluster_id) {
     int Q = *d_Q;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
@@ -737,82 +887,92 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
         if (l1 <= l0) continue;
         float px = xo[p], py = yo[p], pz = zo[p];
         int g0 = l0 >> 5, g1 = (l1 - 1) >> 5;
-        // sweep 1
-        float lbmin = __int_as_float(0x7f800000);
-        int gmin = g0;
-        for (int gb = g0; gb <= g1; gb += 32) {
-            int g = gb + lane;
-            float lb = __int_as_float(0x7f800000);
-            if (g <= g1) lb = box_lb(px, py, pz, __ldg(box_lo + g), __ldg(box_hi + g));
-            unsigned m = __reduce_min_sync(kFull, __float_as_uint(lb));
-            if (__uint_as_float(m) < lbmin) {
-                lbmin = __uint_as_float(m);
-                unsigned who = __ballot_sync(kFull, __float_as_uint(lb) == m);
-                gmin = gb + __ffs(who) - 1;
-            }
-        }
+        // first guess: the group where the query itself would sit in the sorted labelled list
+        int gq = min(max(lpos[inv2[p]], l0), l1 - 1) >> 5;
         float bestD = __int_as_float(0x7f800000);
         int bestI = -1;
-        nn_scan_group(gmin, l0, l1, lane, px, py, pz, lab4, bestD, bestI);
-        // sweep 2
-        for (int gb = g0; gb <= g1; gb += 32) {
-            int g = gb + lane;
-            float lb = __int_as_float(0x7f800000);
-            if (g <= g1 && g != gmin) lb = box_lb(px, py, pz, __ldg(box_lo + g), __ldg(box_hi + g));
-            unsigned m = __ballot_sync(kFull, lb <= bestD);
-            while (m) {
-                int gl = __ffs(m) - 1;
-                m &= m - 1;
-                float lbg = __shfl_sync(kFull, lb, gl);
-                if (lbg > bestD) continue;
-                nn_scan_group(gb + gl, l0, l1, lane, px, py, pz, lab4, bestD, bestI);
+        nn_scan_group(gq, l0, l1, lane, px, py, pz, lab4, bestD, bestI);
+        // level 2 sweep (1024 points per box), descending into level 1 only where the bound allows
+        for (int hb = g0 >> 5; hb <= (g1 >> 5); hb += 32) {
+            int h = hb + lane;
+            float lb2 = __int_as_float(0x7f800000);
+            if (h <= (g1 >> 5)) lb2 = box_lb(px, py, pz, __ldg(box2_lo + h), __ldg(box2_hi + h));
+            unsigned m2 = __ballot_sync(kFull, lb2 <= bestD);
+            while (m2) {
+                int hl = __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                if (__shfl_sync(kFull, lb2, hl) > bestD) continue;
+                int gi = (hb + hl) * 32 + lane;
+                float lb = __int_as_float(0x7f800000);
+                if (gi >= g0 && gi <= g1 && gi != gq) lb = box_lb(px, py, pz, __ldg(box_lo + gi), __ldg(box_hi + gi));
+                unsigned m = __ballot_sync(kFull, lb <= bestD);
+                while (m) {
+                    // visit the most promising group first: it tightens the bound for the others
+                    unsigned lbmin = __reduce_min_sync(kFull, (m >> lane) & 1 ? __float_as_uint(lb) : 0xffffffffu);
+                    if (__uint_as_float(lbmin) > bestD) break;
+                    unsigned who = __ballot_sync(kFull, ((m >> lane) & 1) && __float_as_uint(lb) == lbmin);
+                    int gl = __ffs(who) - 1;
+                    m &= ~(1u << gl);
+                    nn_scan_group((hb + hl) * 32 + gl, l0, l1, lane, px, py, pz, lab4, bestD, bestI);
+                }
             }
         }
         if (lane == 0 && bestI >= 0) cluster_id[p] = cluster_id[bestI];
     }
-    if (counters && blockIdx.x == 0 && threadIdx.x == 0) counters[3] = (unsigned long long)Q;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K21  cluster centres (binary_cuda_functions.cu:217-246): sequential running mean in ascending
-//      point order, M += (x - M) / n with IEEE division — replayed exactly, one warp per cluster.
+//      point order, M += (x - M) / n with IEEE division — replayed exactly.  One warp per cluster:
+//      the warp streams its segment, compacts the member coordinates into a shared-memory buffer and
+//      lanes 0,1,2 then run the x, y, z recurrences side by side (one instruction stream for all
+//      three chains).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kCtrWarps = 4;
+constexpr int kCtrBuf = 256;  // buffered members per warp (3 floats each)
+
+__global__ void __launch_bounds__(kCtrWarps * 32)
 k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
           const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
           const float *__restrict__ z, float *__restrict__ center) {
+    __shared__ float buf[kCtrWarps][3][kCtrBuf + 32];
     int K = *d_K;
-    int lane = lane_id();
+    int lane = lane_id(), wid = threadIdx.x >> 5;
     int warps = (gridDim.x * blockDim.x) >> 5;
+    float(*mybuf)[kCtrBuf + 32] = buf[wid];
+    int coord = lane < 3 ? lane : 0;
     for (int kk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; kk < K; kk += warps) {
         int s = clt_seg[kk];
         int local = kk - sg.id_base[s];
         int b = sg.start[s], e = sg.start[s + 1];
-        float mx = 0.f, my = 0.f, mz = 0.f;
+        float M = 0.f;  // lane c < 3 carries coordinate c
         int cnt = 0;
+        int fill = 0;
         for (int ub = b; ub < e; ub += 32) {
             int u = ub + lane;
             bool hit = (u < e) && (cluster_id[u] == local);
             unsigned m = __ballot_sync(kFull, hit);
-            if (!m) continue;
-            float vx = 0.f, vy = 0.f, vz = 0.f;
-            if (hit) vx = x[u], vy = y[u], vz = z[u];
-            while (m) {
-                int l = __ffs(m) - 1;
-                m &= m - 1;
-                float ax = __shfl_sync(kFull, vx, l), ay = __shfl_sync(kFull, vy, l), az = __shfl_sync(kFull, vz, l);
-                cnt++;
-                float fn = (float)cnt;
-                mx = __fadd_rn(mx, __fdiv_rn(__fsub_rn(ax, mx), fn));
-                my = __fadd_rn(my, __fdiv_rn(__fsub_rn(ay, my), fn));
-                mz = __fadd_rn(mz, __fdiv_rn(__fsub_rn(az, mz), fn));
+            if (hit) {
+                int o = fill + __popc(m & ((1u << lane) - 1));
+                mybuf[0][o] = x[u];
+                mybuf[1][o] = y[u];
+                mybuf[2][o] = z[u];
+            }
+            fill += __popc(m);
+            if (fill >= kCtrBuf || ub + 32 >= e) {  // flush: lanes 0..2 replay the recurrence in order
+                __syncwarp();
+                const float *src = mybuf[coord];
+#pragma unroll 4
+                for (int t = 0; t < fill; t++) {
+                    float v = src[t];
+                    cnt++;
+                    M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
+                }
+                fill = 0;
+                __syncwarp();
             }
         }
-        if (lane == 0) {
-            center[3 * kk] = mx;
-            center[3 * kk + 1] = my;
-            center[3 * kk + 2] = mz;
-        }
+        if (lane < 3) center[3 * kk + lane] = M;
     }
 }
 
@@ -894,6 +1054,7 @@ k_scan_down(const int *__restrict__ in, int n_host, const int *__restrict__ n_de
     int v[kScanItems];
     int sum = 0;
     int i0 = base + threadIdx.x * kScanItems;
+#pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         int i = i0 + k;
         v[k] = i < n ? in[i] : 0;
@@ -901,6 +1062,7 @@ k_scan_down(const int *__restrict__ in, int n_host, const int *__restrict__ n_de
     }
     int total;
     int ex = block_excl_scan(sum, smem, total) + block_offs[blockIdx.x];
+#pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         int i = i0 + k;
         if (i < n) out[i] = ex;
