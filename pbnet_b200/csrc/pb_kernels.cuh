@@ -376,6 +376,11 @@ __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const 
 //     lane (register tiling: the LSU write-back of a uniform LDG.128 costs 4 cycles/warp, so one load
 //     per 32 tests made the first version LSU-bound at 94 % — profiles/ncu_r01_degree_v1.txt).
 // ------------------------------------------------------------------------------------------------
+// cnt += (d <= r2) as FSETP.LE + predicated IADD3 (nvcc emits FSETP.GTU + 2 IADD3 for the C expression)
+__device__ __forceinline__ void count_le(int &cnt, float d, float r2) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(d), "f"(r2));
+}
+
 template <int Q>
 __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, int g0, int total, int lane, float r2,
                                              int jb, int je, int *__restrict__ deg_sorted) {
@@ -392,24 +397,21 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
     for (int k = 0; k < kRuns; k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
         int j = b;
-        if (Q == 1) {
-            for (; j + 4 <= e; j += 4) {
-                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-                cnt[0] += (sqd(px[0], py[0], pz[0], q0.x, q0.y, q0.z) <= r2) + (sqd(px[0], py[0], pz[0], q1.x, q1.y, q1.z) <= r2) +
-                          (sqd(px[0], py[0], pz[0], q2.x, q2.y, q2.z) <= r2) + (sqd(px[0], py[0], pz[0], q3.x, q3.y, q3.z) <= r2);
-            }
-        } else {
-            for (; j + 2 <= e; j += 2) {
-                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1);
+#pragma unroll 1
+        for (; j + 4 <= e; j += 4) {
+            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
 #pragma unroll
-                for (int s = 0; s < Q; s++)
-                    cnt[s] += (sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z) <= r2) + (sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z) <= r2);
+            for (int s = 0; s < Q; s++) {
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q2.x, q2.y, q2.z), r2);
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
             }
         }
         for (; j < e; j++) {
             float4 q0 = __ldg(pts4 + j);
 #pragma unroll
-            for (int s = 0; s < Q; s++) cnt[s] += sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z) <= r2;
+            for (int s = 0; s < Q; s++) count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
         }
     }
 #pragma unroll
