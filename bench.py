@@ -263,22 +263,13 @@ def main():
                  clt_sem=torch.empty(max(n // 32, 1024), dtype=torch.int32, device=dev))
     stream = torch.cuda.current_stream()
 
-    # gather of proposals to rank 0 (the only collective; NCCL over NVLink)
-    n_all = [n]
-    if world > 1:
-        t = torch.tensor([n], device=dev, dtype=torch.int64)
-        g = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(g, t)
-        n_all = [int(x.item()) for x in g]
-        pad = max(n_all)
-        send = torch.full((pad,), -1, dtype=torch.int32, device=dev)
-        recv = [torch.empty(pad, dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None
+    # gather of proposals to rank 0 (the only collective; NCCL over NVLink) — pbnet_b200/sharding.py
+    from pbnet_b200 import sharding
 
     def step_device():
         out = ctx.binary_cluster(*d_in, seg, r18, m18, 0.05, True, call_seg_counts=csc, stream=stream, **d_out)
         if world > 1:
-            send[:n].copy_(d_out["cluster_id"])
-            dist.gather(send, recv, dst=0)
+            sharding.gather_to_rank0(d_out["cluster_id"])
         return out
 
     def barrier():
