@@ -107,6 +107,34 @@ float pb_stage_ms(const pb_ctx *ctx, int i);
  * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter */
 int64_t pb_counter(const pb_ctx *ctx, int i);
 
+/* ------------------------------------------------------------------------------------------------
+ * voxelize / devoxelize (scatter-gather around the sparse-conv backbone).  The reference calls
+ * MinkowskiEngine for these (un-vendored): ME.utils.sparse_quantize at
+ * datasets/scannetv2/dataset_preprocess.py:269-274,348-353; ME.SparseTensor(...).inverse_mapping at
+ * network/PBNet.py:236-247,261-271; the devoxelize gathers X_v[v2p] at network/PBNet.py:130-134,250.
+ *
+ * pb_voxelize   <-  ME.utils.sparse_quantize(coords, quantization_size, return_index, return_inverse)
+ *   coords      [n, stride] fp32 (coord_f64 = 0) or fp64 (= 1), stride 3 (x,y,z) or 4 (batch,x,y,z when
+ *               has_batch_col); optional int32 batch[n] overrides the batch column
+ *   voxel_size  voxel = floor(coord / voxel_size); <= 0 means coords are already in voxel units (floor only)
+ *   vcoords     [V,4] int32 (batch,x,y,z), lexicographic order       index   [V] representative point (smallest index)
+ *   inverse     [n] point -> voxel                                    order / vox_start  CSR voxel -> points
+ *   cap         capacity (in voxels) of vcoords / index / vox_start-1; device outputs need cap >= n
+ * pb_voxel_rows <-  feats[index] (mode 0), SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE (mode 1,
+ *               commented-out option at network/PBNet.py:243,268), or the autograd scatter-add of the
+ *               devoxelize gather (mode 2): out[v,:] = reduce over the points of voxel v, ascending order
+ * pb_devoxelize <-  out[p,:] = vfeat[inverse[p],:]
+ * Parity note: MinkowskiEngine is not available here; voxel ORDER is implementation-defined in ME, so
+ * results are compared with ME's documented contract modulo a permutation of voxels.
+ */
+int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int stride, int has_batch_col, const int32_t *batch,
+                int64_t n, double voxel_size, int32_t *vcoords, int64_t *index, int64_t *inverse, int32_t *order,
+                int32_t *vox_start, int64_t cap, int64_t *n_voxels_out, int mem_kind, void *stream);
+int pb_voxel_rows(pb_ctx *ctx, const float *rows, int64_t n_rows, int C, const int32_t *order, const int32_t *vox_start,
+                  int64_t V, int mode, float *out, int mem_kind, void *stream);
+int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, const int64_t *inverse, int64_t n, float *out,
+                  int mem_kind, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

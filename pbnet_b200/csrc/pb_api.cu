@@ -509,3 +509,211 @@ extern "C" int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, co
                     cluster_id, cluster_num, degree, center, center_cap, clt_sem, clt_sem_cap, n_clusters_out, nullptr,
                     mem_kind, stream);
 }
+
+// =================================================================================================
+// voxelize / devoxelize — see pb_voxel.cuh
+// =================================================================================================
+#include "pb_voxel.cuh"
+
+namespace {
+int ensure_arena(pb_ctx *ctx, size_t need, cudaStream_t st) {
+    if (need > ctx->arena.cap) {
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
+        ctx->arena.base = nullptr;
+        ctx->arena.cap = 0;
+        size_t want = need + need / 4;
+        if (cudaMalloc(&ctx->arena.base, want) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, PB_ERR_NOMEM, "workspace allocation of " + std::to_string(want) + " bytes failed");
+        }
+        ctx->arena.cap = want;
+    }
+    ctx->arena.off = 0;
+    ctx->arena.dry = false;
+    return PB_OK;
+}
+
+void launch_scan(cudaStream_t st, const int *in, int n_host, const int *n_dev, int *out, int *total, int *blocks, int64_t &L) {
+    int nb = div_up(n_host, pb::kScanTile);
+    pb::k_scan_reduce<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks);
+    pb::k_scan_spine<<<1, pb::kScanThreads, 0, st>>>(blocks, nb, total);
+    pb::k_scan_down<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks, out);
+    L += 3;
+}
+}  // namespace
+
+extern "C" int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int stride, int has_batch_col,
+                           const int32_t *batch, int64_t n, double voxel_size, int32_t *vcoords, int64_t *index,
+                           int64_t *inverse, int32_t *order, int32_t *vox_start, int64_t cap, int64_t *n_voxels_out,
+                           int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n < 0 || !n_voxels_out || (stride != 3 && stride != 4) || (has_batch_col && stride != 4) ||
+        (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE))
+        return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (n >= ((int64_t)1 << 31)) return fail(ctx, PB_ERR_ARG, "n must be below 2^31");
+    *n_voxels_out = 0;
+    if (n == 0) return PB_OK;
+    if (!coords || !vcoords || !index || !inverse || !order || !vox_start || cap < 1) return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    const size_t N = (size_t)n, esz = coord_f64 ? 8 : 4;
+    int64_t &L = ctx->launches;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        void *d_coords = host_io ? (void *)a.get<char>(N * stride * esz) : nullptr;
+        int *d_batch = (host_io && batch) ? a.get<int>(N) : nullptr;
+        int4 *d_vcoords = host_io ? a.get<int4>(N) : nullptr;
+        long long *d_index = host_io ? a.get<long long>(N) : nullptr;
+        long long *d_inverse = host_io ? a.get<long long>(N) : nullptr;
+        int *d_order = host_io ? a.get<int>(N) : nullptr;
+        int *d_vstart = host_io ? a.get<int>(N + 1) : nullptr;
+        int4 *q = a.get<int4>(N);
+        uint64_t *key = a.get<uint64_t>(N), *key_alt = a.get<uint64_t>(N);
+        uint32_t *val = a.get<uint32_t>(N), *ord = a.get<uint32_t>(N);
+        int *head = a.get<int>(N), *ex = a.get<int>(N);
+        int *mnmx = a.get<int>(16);
+        int *blocks = a.get<int>(N / pb::kScanTile + 2);
+        size_t cub_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
+        void *cub_tmp = a.get<char>(cub_bytes);
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+            continue;
+        }
+        const void *c_in = coords;
+        const int *b_in = batch;
+        if (host_io) {
+            PB_CUDA(cudaMemcpyAsync(d_coords, coords, N * stride * esz, cudaMemcpyHostToDevice, st));
+            c_in = d_coords;
+            if (batch) {
+                PB_CUDA(cudaMemcpyAsync(d_batch, batch, N * 4, cudaMemcpyHostToDevice, st));
+                b_in = d_batch;
+            }
+        } else {
+            d_vcoords = reinterpret_cast<int4 *>(vcoords);
+            d_index = reinterpret_cast<long long *>(index);
+            d_inverse = reinterpret_cast<long long *>(inverse);
+            d_order = order;
+            d_vstart = vox_start;
+        }
+        if (!host_io && cap < n) return fail(ctx, PB_ERR_CAPACITY, "device outputs need capacity n (the voxel count is not known in advance)");
+        const int h_init[16] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000,
+                                (int)0x80000000, (int)0x80000000, 0, 0, 0, 0, 0, 0, 0, 0};
+        PB_CUDA(cudaMemcpyAsync(mnmx, h_init, sizeof(h_init), cudaMemcpyHostToDevice, st));
+        int *d_err = mnmx + 8, *d_V = mnmx + 9;
+        const int T = 256, g = div_up(n, T);
+        if (coord_f64)
+            pbv::k_quantize<double><<<g, T, 0, st>>>((const double *)c_in, stride, has_batch_col, b_in, n, voxel_size, q, mnmx, mnmx + 4);
+        else
+            pbv::k_quantize<float><<<g, T, 0, st>>>((const float *)c_in, stride, has_batch_col, b_in, n, (float)voxel_size, q, mnmx, mnmx + 4);
+        pbv::k_vox_keys<<<g, T, 0, st>>>(q, n, mnmx, mnmx + 4, key, val, d_err);
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, key, key_alt, val, ord, (int)n, 0, 64, st));
+        pbv::k_vox_heads<<<g, T, 0, st>>>(key_alt, n, head);
+        L += 3 + 10;
+        launch_scan(st, head, (int)n, nullptr, ex, d_V, blocks, L);
+        pbv::k_vox_table<<<g, T, 0, st>>>(q, ord, head, ex, n, d_vcoords, d_index, d_inverse, d_order, d_vstart, d_V);
+        L++;
+        PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, mnmx + 8, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->h_scalars[0] & 4) return fail(ctx, PB_ERR_RANGE, "voxel grid spans more than 65535 cells along an axis");
+        int64_t V = ctx->h_scalars[1];
+        *n_voxels_out = V;
+        if (host_io) {
+            if (V > cap) return fail(ctx, PB_ERR_CAPACITY, "output capacity too small for " + std::to_string(V) + " voxels");
+            PB_CUDA(cudaMemcpyAsync(vcoords, d_vcoords, sizeof(int4) * V, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(index, d_index, 8 * V, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(inverse, d_inverse, 8 * N, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(order, d_order, 4 * N, cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaMemcpyAsync(vox_start, d_vstart, 4 * (V + 1), cudaMemcpyDeviceToHost, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_voxel_rows(pb_ctx *ctx, const float *rows, int64_t n_rows, int C, const int32_t *order,
+                             const int32_t *vox_start, int64_t V, int mode, float *out, int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_rows < 0 || V < 0 || C < 1 || mode < 0 || mode > 2 || (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE))
+        return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (V == 0) return PB_OK;
+    if (!rows || !order || !vox_start || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    const float *d_rows = rows;
+    const int *d_order = order, *d_vs = vox_start;
+    float *d_out = out;
+    if (host_io) {
+        size_t need = ((size_t)n_rows * C + (size_t)V * C) * 4 + (size_t)n_rows * 4 + (size_t)(V + 1) * 4 + 4096;
+        int rc = ensure_arena(ctx, need, st);
+        if (rc) return rc;
+        float *r = ctx->arena.get<float>((size_t)n_rows * C);
+        float *o = ctx->arena.get<float>((size_t)V * C);
+        int *od = ctx->arena.get<int>((size_t)n_rows), *vs = ctx->arena.get<int>((size_t)V + 1);
+        PB_CUDA(cudaMemcpyAsync(r, rows, (size_t)n_rows * C * 4, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(od, order, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(vs, vox_start, (size_t)(V + 1) * 4, cudaMemcpyHostToDevice, st));
+        d_rows = r, d_out = o, d_order = od, d_vs = vs;
+    }
+    const int T = 256;
+    const int g = div_up(V * C, T);
+    if (mode == 0) pbv::k_vox_rows<0><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
+    else if (mode == 1) pbv::k_vox_rows<1><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
+    else pbv::k_vox_rows<2><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
+    ctx->launches = 1;
+    if (host_io) PB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)V * C * 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    if (host_io) PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, const int64_t *inverse, int64_t n,
+                             float *out, int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n < 0 || V < 0 || C < 1 || (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE)) return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (n == 0) return PB_OK;
+    if (!vfeat || !inverse || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    const float *d_v = vfeat;
+    const long long *d_inv = reinterpret_cast<const long long *>(inverse);
+    float *d_out = out;
+    if (host_io) {
+        size_t need = ((size_t)V * C + (size_t)n * C) * 4 + (size_t)n * 8 + 4096;
+        int rc = ensure_arena(ctx, need, st);
+        if (rc) return rc;
+        float *v = ctx->arena.get<float>((size_t)V * C), *o = ctx->arena.get<float>((size_t)n * C);
+        long long *iv = ctx->arena.get<long long>((size_t)n);
+        PB_CUDA(cudaMemcpyAsync(v, vfeat, (size_t)V * C * 4, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(iv, inverse, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        d_v = v, d_out = o, d_inv = iv;
+    }
+    const int T = 256;
+    bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_v) | reinterpret_cast<uintptr_t>(d_out)) % 16 == 0);
+    if (vec4) {
+        int C4 = C / 4;
+        pbv::k_devox<float4><<<div_up(n * C4, T), T, 0, st>>>((const float4 *)d_v, C4, d_inv, n, (float4 *)d_out);
+    } else {
+        pbv::k_devox<float><<<div_up(n * C, T), T, 0, st>>>(d_v, C, d_inv, n, d_out);
+    }
+    ctx->launches = 1;
+    if (host_io) PB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * C * 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    if (host_io) PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
