@@ -292,12 +292,12 @@ def main():
         return float(t.item())
 
     total_points = int(sum_over_ranks(float(n)))
-    for _ in range(args.warmup):
-        out = step_device()
-    launches_per_step = ctx.last_launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        out = step_device()
+    launches_per_step = ctx.last_launch_count
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {}
@@ -309,7 +309,6 @@ def main():
     e1.record(stream)
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     counters = ctx.counters()
     n_clusters = out["n_clusters"]
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
@@ -330,6 +329,7 @@ def main():
         oh = step_host()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None  # sampled from the first warm-up step to the end of the e2e loop
     h2d = 28 * n
     d2h = 8 * n + 4 * S + 16 * int(oh["n_clusters"])
     e2e_stage = ctx.stage_ms()
@@ -356,6 +356,36 @@ def main():
         dropin = {"value": pts / dt, "unit": UNIT, "calls": len(calls), "points": pts,
                   "api": "pbnet_b200.pbnet_ops.cluster per (scene, class), CPU tensors in/out (reference call pattern)",
                   "us_per_call": 1e6 * dt / max(1, len(calls))}
+
+    # ---- voxelize / devoxelize (rows a12-a14): HBM-bound scatter-gather, rank 0 only
+    vox = None
+    if rank == 0:
+        from pbnet_b200 import voxel
+        nv = min(n, 8_000_000)
+        coords = torch.stack([d_in[3][:nv], d_in[4][:nv], d_in[5][:nv]], 1).contiguous()  # original xyz
+        bcol = torch.zeros(nv, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        vm = voxel.voxel_map(coords, scenes.VOXEL_SIZE, batch=bcol)
+        ev[0].record()
+        vm = voxel.voxel_map(coords, scenes.VOXEL_SIZE, batch=bcol)
+        ev[1].record()
+        C = 76  # 32 + 20 + 20 + 3 + 1 channels gathered at network/PBNet.py:130-134
+        vfeat = torch.randn((vm.n_voxels, C), device=dev)
+        o = voxel.devoxelize_raw(vfeat, vm.inverse)
+        ev[2].record()
+        for _ in range(5):
+            o = voxel.devoxelize_raw(vfeat, vm.inverse)
+        ev[3].record()
+        torch.cuda.synchronize()
+        t_vox = ev[0].elapsed_time(ev[1]) * 1e-3
+        t_dev = ev[2].elapsed_time(ev[3]) * 1e-3 / 5
+        gbytes = (nv * C * 4 + vm.n_voxels * C * 4 + nv * 8) / 1e9
+        peak_v, _ = measured_peaks()
+        vox = {"points": nv, "voxels": vm.n_voxels, "voxelize_points_per_s": nv / t_vox,
+               "devoxelize": {"channels": C, "ms": t_dev * 1e3, "algorithmic_gb": gbytes, "achieved_gbs": gbytes / t_dev,
+                              "frac_of_hbm_peak": gbytes / t_dev / peak_v}}
+        del vfeat, o, coords
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
     cpu = None
@@ -406,6 +436,7 @@ def main():
                              "peak_def": "148 SM x 128 fp32 lanes x measured SM clock / 8 issue slots per test"},
             "io_roofline": {"bytes_per_point": 36, "achieved_gbs": value * 36 / 1e9, "frac_of_hbm": value * 36 / 1e9 / peak},
             "counters": counters,
+            "voxel": vox,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -97,6 +97,12 @@ int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const
                               int64_t clt_sem_cap, int64_t *n_clusters_out, int64_t *call_clusters,
                               int mem_kind, void *stream);
 
+/* Large batched calls are split into chunks of about `points` points (runs of whole calls) that alternate
+ * over two internal streams, so the latency-bound tail kernels and the host copies of one chunk overlap the
+ * neighbour-count kernel of the next.  0 = automatic (3 M points once a call has >= 6 M), < 0 or huge = off.
+ * Results do not depend on the chunking. */
+void pb_set_chunk_points(pb_ctx *ctx, int64_t points);
+
 /* Optional per-stage device timings (ms, CUDA events) of the last call when enabled; stage names via
  * pb_stage_name.  Off by default (events add launch overhead). */
 void pb_set_profiling(pb_ctx *ctx, int on);

@@ -7,6 +7,7 @@ operator surface (lib/PB_lib/torch_io/pbnet_ops.py:12-82, lib/PB_lib/src/PB_lib_
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -50,6 +51,8 @@ class Context:
         self.device = int(device)
         if profiling:
             self.set_profiling(True)
+        if os.environ.get("PB_CHUNK_POINTS"):  # experiments: chunk size of the two-stream pipelining
+            self.set_chunk_points(int(os.environ["PB_CHUNK_POINTS"]))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -65,6 +68,10 @@ class Context:
     def set_profiling(self, on: bool):
         self._lib.pb_set_profiling(self._h, int(bool(on)))
 
+    def set_chunk_points(self, points: int):
+        """Chunk size (points) of the two-stream pipelining of large batched calls; 0 = automatic."""
+        self._lib.pb_set_chunk_points(self._h, int(points))
+
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.pb_last_launch_count(self._h))
@@ -74,7 +81,7 @@ class Context:
         return {self._lib.pb_stage_name(i).decode(): float(self._lib.pb_stage_ms(self._h, i)) for i in range(n)}
 
     def counters(self) -> dict:
-        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters"]
+        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks"]
         return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------------------------------------

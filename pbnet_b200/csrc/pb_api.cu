@@ -58,6 +58,14 @@ struct pb_ctx {
     // pinned scratch for scalars read back at the end of a call
     int *h_scalars = nullptr;  // [0] err bits [1] C [2] R [3] K [4] Q [5] L
     unsigned long long *h_counters = nullptr;
+    // chunked two-stream pipelining of large batched calls
+    long long chunk_points = 0;  // 0 = automatic
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int *h_chunk_scalars = nullptr;
+    unsigned long long *h_chunk_counters = nullptr;
+    size_t h_chunk_cap = 0;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 namespace {
@@ -99,6 +107,11 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         return PB_ERR_CUDA;
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming);
     *out = ctx;
     return PB_OK;
 }
@@ -112,6 +125,14 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+    if (ctx->h_chunk_scalars) cudaFreeHost(ctx->h_chunk_scalars);
+    if (ctx->h_chunk_counters) cudaFreeHost(ctx->h_chunk_counters);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+        if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -120,6 +141,9 @@ extern "C" const char *pb_last_error(const pb_ctx *ctx) { return ctx ? ctx->err.
 extern "C" int64_t pb_last_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void pb_set_profiling(pb_ctx *ctx, int on) {
     if (ctx) ctx->profiling = on != 0;
+}
+extern "C" void pb_set_chunk_points(pb_ctx *ctx, int64_t points) {
+    if (ctx) ctx->chunk_points = points;
 }
 extern "C" int pb_stage_count(void) { return ST_COUNT; }
 extern "C" const char *pb_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
@@ -171,11 +195,7 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_
         w.cluster_num = a.get<int>(S);
         w.degree = a.get<int>(N);
     }
-    // cluster metadata is always produced in workspace first (its size is only known at the end)
-    w.center = a.get<float>(3 * N);
-    w.clt_sem = a.get<int>(N);
     w.clt_seg = a.get<int>(N);
-    w.radius = a.get<float>(18); w.thresh = a.get<float>(18); w.min_pts = a.get<int>(18);
     w.seg_start = a.get<int>(S + 1); w.seg_call_first = a.get<int>(S);
     w.sg.enc_min_s = a.get<unsigned>(3 * S); w.sg.enc_min_o = a.get<unsigned>(3 * S); w.sg.enc_max_o = a.get<unsigned>(3 * S);
     w.sg.cls = a.get<int>(S); w.sg.min_pts = a.get<int>(S); w.sg.r2 = a.get<float>(S); w.sg.inv_h = a.get<float>(S);
@@ -213,72 +233,15 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
-                    const float *zo, const int32_t *sem, const int32_t *seg_counts, int32_t n_seg,
-                    const int32_t *call_seg_counts, int32_t n_calls, int64_t n_pts, const float *radius,
-                    const int32_t *min_pts, float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
-                    int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap,
-                    int64_t *n_clusters_out, int64_t *call_clusters, int mem_kind, void *stream_v) {
-    if (!ctx) return PB_ERR_ARG;
-    ctx->err.clear();
-    ctx->launches = 0;
-    if (n_seg < 0 || n_pts < 0 || n_calls < 0 || (n_seg > 0 && !seg_counts) || !radius || !min_pts || !n_clusters_out)
-        return fail(ctx, PB_ERR_ARG, "null / negative argument");
-    if (n_pts >= (int64_t)1 << 31) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^31");
-    if (n_seg >= (1 << 22)) return fail(ctx, PB_ERR_ARG, "n_seg must be below 2^22");
-    if (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE) return fail(ctx, PB_ERR_ARG, "bad mem_kind");
-    const int S = n_seg;
-    const int n = (int)n_pts;
-    std::vector<int> start(S + 1, 0), call_first(std::max(S, 1), 0);
-    for (int s = 0; s < S; s++) {
-        if (seg_counts[s] < 0) return fail(ctx, PB_ERR_ARG, "negative segment size");
-        long long t = (long long)start[s] + seg_counts[s];
-        if (t > n_pts) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
-        start[s + 1] = (int)t;
-    }
-    if ((S == 0 ? 0 : start[S]) != n) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
-    {
-        int s = 0;
-        for (int c = 0; c < n_calls; c++) {
-            if (!call_seg_counts || call_seg_counts[c] < 0 || s + call_seg_counts[c] > S)
-                return fail(ctx, PB_ERR_ARG, "bad call_seg_counts");
-            for (int k = 0; k < call_seg_counts[c]; k++) call_first[s + k] = s;
-            s += call_seg_counts[c];
-        }
-        if (s != S) return fail(ctx, PB_ERR_ARG, "sum(call_seg_counts) != n_seg");
-    }
-    *n_clusters_out = 0;
-    if (call_clusters)
-        for (int c = 0; c < n_calls; c++) call_clusters[c] = 0;
-    if (n > 0 && (!x || !y || !z || !xo || !yo || !zo || !sem || !cluster_id || !degree))
-        return fail(ctx, PB_ERR_ARG, "null data pointer");
-    if (S > 0 && !cluster_num) return fail(ctx, PB_ERR_ARG, "null cluster_num");
-    const bool host_io = mem_kind == PB_MEM_HOST;
-    PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
-    if (n == 0) {
-        if (S > 0) {
-            if (host_io) std::memset(cluster_num, 0, sizeof(int) * S);
-            else PB_CUDA(cudaMemsetAsync(cluster_num, 0, sizeof(int) * S, st));
-            PB_CUDA(cudaStreamSynchronize(st));
-        }
-        return PB_OK;
-    }
-
-    // ---- workspace --------------------------------------------------------------------------------
-    Work w;
-    std::memset(&w, 0, sizeof(w));
-    Arena dry;
-    dry.dry = true;
-    plan(dry, w, n, S, host_io, center_cap, clt_sem_cap);
-    if (dry.off > ctx->arena.cap) {
+namespace {
+int ensure_arena(pb_ctx *ctx, size_t need, cudaStream_t st) {
+    if (need > ctx->arena.cap) {
         PB_CUDA(cudaStreamSynchronize(st));
         if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
         ctx->arena.base = nullptr;
         ctx->arena.cap = 0;
-        size_t want = dry.off + dry.off / 4;
-        cudaError_t e = cudaMalloc(&ctx->arena.base, want);
-        if (e != cudaSuccess) {
+        size_t want = need + need / 4;
+        if (cudaMalloc(&ctx->arena.base, want) != cudaSuccess) {
             cudaGetLastError();
             return fail(ctx, PB_ERR_NOMEM, "workspace allocation of " + std::to_string(want) + " bytes failed");
         }
@@ -286,46 +249,69 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     ctx->arena.off = 0;
     ctx->arena.dry = false;
-    plan(ctx->arena, w, n, S, host_io, center_cap, clt_sem_cap);
-    w.sg.start = w.seg_start;
+    return PB_OK;
+}
 
-    const bool prof = ctx->profiling;
+void launch_scan(cudaStream_t st, const int *in, int n_host, const int *n_dev, int *out, int *total, int *blocks, int64_t &L) {
+    int nb = div_up(n_host, pb::kScanTile);
+    pb::k_scan_reduce<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks);
+    pb::k_scan_spine<<<1, pb::kScanThreads, 0, st>>>(blocks, nb, total);
+    pb::k_scan_down<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks, out);
+    L += 3;
+}
+}  // namespace
+
+namespace {
+
+struct ChunkIO {          // one chunk = a run of consecutive calls; all pointers already offset to the chunk
+    const float *x, *y, *z, *xo, *yo, *zo;
+    const int *sem;
+    int *cluster_id, *cluster_num, *degree;
+    int n, S;
+    const int *start;       // host [S+1], local to the chunk
+    const int *call_first;  // host [S], local to the chunk
+    float *center_out;      // device, capacity 3*n floats (chunk-private region)
+    int *clt_sem_out;       // device, capacity n
+    int *h_scalars;         // pinned [16]
+    unsigned long long *h_counters;  // pinned [8]
+    cudaEvent_t *ev;        // ST_COUNT+1 events or nullptr
+};
+
+// Enqueues the whole launch sequence of one chunk on `st`.  No host synchronisation.
+int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assign_lp, const float *d_radius,
+                  const int *d_min_pts, const float *d_thresh, cudaStream_t st, int64_t &L) {
+    const int n = io.n, S = io.S;
+    const bool prof = io.ev != nullptr;
     int stage_ev = 0;
     auto mark = [&]() {
-        if (prof) cudaEventRecord(ctx->ev[stage_ev], st);
+        if (prof) cudaEventRecord(io.ev[stage_ev], st);
         stage_ev++;
     };
-    int64_t &L = ctx->launches;
     const int T = 256;
     const int gN = div_up(n, T);
     const int gS = div_up(S + 1, T);
     const int gPersist = 148 * 8;
+    w.sg.start = w.seg_start;
 
     mark();  // start of H2D
-    // ---- inputs -----------------------------------------------------------------------------------
-    const float *dx = x, *dy = y, *dz = z, *dxo = xo, *dyo = yo, *dzo = zo;
-    const int *dsem = sem;
-    int *d_cluster_id = cluster_id, *d_cluster_num = cluster_num, *d_degree = degree;
+    const float *dx = io.x, *dy = io.y, *dz = io.z, *dxo = io.xo, *dyo = io.yo, *dzo = io.zo;
+    const int *dsem = io.sem;
+    int *d_cluster_id = io.cluster_id, *d_cluster_num = io.cluster_num, *d_degree = io.degree;
     if (host_io) {
         size_t fb = sizeof(float) * (size_t)n;
-        PB_CUDA(cudaMemcpyAsync(w.x, x, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.y, y, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.z, z, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.xo, xo, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.yo, yo, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.zo, zo, fb, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(w.sem, sem, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.x, io.x, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.y, io.y, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.z, io.z, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.xo, io.xo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.yo, io.yo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.zo, io.zo, fb, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(w.sem, io.sem, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
         dx = w.x, dy = w.y, dz = w.z, dxo = w.xo, dyo = w.yo, dzo = w.zo, dsem = w.sem;
         d_cluster_id = w.cluster_id, d_cluster_num = w.cluster_num, d_degree = w.degree;
     }
-    float thresh[18];
-    for (int i = 0; i < 18; i++) thresh[i] = kMeanCount[i] * para_f;  // fp32 multiply, binary.cu:256
-    // small tables: pageable host memory -> the async copies are staged synchronously by the driver
-    PB_CUDA(cudaMemcpyAsync(w.radius, radius, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(w.min_pts, min_pts, sizeof(int) * 18, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(w.thresh, thresh, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(w.seg_start, start.data(), sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(w.seg_call_first, call_first.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    // segment tables: pageable host memory -> staged synchronously by the driver, safe to reuse after return
+    PB_CUDA(cudaMemcpyAsync(w.seg_start, io.start, sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(w.seg_call_first, io.call_first, sizeof(int) * S, cudaMemcpyHostToDevice, st));
     PB_CUDA(cudaMemsetAsync(w.sg.enc_min_s, 0xff, sizeof(unsigned) * 3 * S, st));
     PB_CUDA(cudaMemsetAsync(w.sg.enc_min_o, 0xff, sizeof(unsigned) * 3 * S, st));
     PB_CUDA(cudaMemsetAsync(w.sg.enc_max_o, 0x00, sizeof(unsigned) * 3 * S, st));
@@ -338,16 +324,12 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     unsigned long long *cnt = prof ? w.d_counters : nullptr;
 
     auto scan = [&](const int *in, int n_host, const int *n_dev, int *out, int *total) {
-        int nb = div_up(n_host, pb::kScanTile);
-        pb::k_scan_reduce<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, w.scan_blocks);
-        pb::k_scan_spine<<<1, pb::kScanThreads, 0, st>>>(w.scan_blocks, nb, total);
-        pb::k_scan_down<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, w.scan_blocks, out);
-        L += 3;
+        launch_scan(st, in, n_host, n_dev, out, total, w.scan_blocks, L);
     };
 
     mark();  // PREP
     pb::k_prep_points<<<gN, T, 0, st>>>(n, S, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, d_err);
-    pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, w.radius, w.min_pts);
+    pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, d_radius, d_min_pts);
     pb::k_keys<<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err);
     L += 3;
 
@@ -391,8 +373,9 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
                                      w.cell_minhp, cnt);
     L++;
     mark();  // UNION
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent);
-    L++;
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0);
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1);
+    L += 2;
     mark();  // COMPONENTS
     pb::k_comp_min<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min);
     pb::k_flag_roots<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag);
@@ -404,12 +387,12 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     pb::k_label<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label, w.raw_count);
     L++;
     mark();  // FILTER
-    pb::k_filter<<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, w.thresh, w.keep);
+    pb::k_filter<<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, d_thresh, w.keep);
     L++;
     scan(w.keep, n, d_R, w.kscan, d_K);
     pb::k_seg_clusters<<<gS, T, 0, st>>>(n, S, w.sg, w.seg_call_first, w.gid_at, d_R, w.kscan, d_K, d_cluster_num);
     pb::k_relabel<<<gN, T, 0, st>>>(n, w.sg, w.seg_of, w.raw_label, w.keep, w.kscan, assign_lp, d_cluster_id, w.qflag,
-                                    w.clt_sem, w.clt_seg, w.rep);
+                                    io.clt_sem_out, w.clt_seg, w.rep);
     L += 2;
     mark();  // LP_BUILD
     if (assign_lp) {
@@ -430,58 +413,246 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         L++;
     }
     mark();  // CENTRES
-    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, w.center);
+    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out);
     L++;
     mark();  // D2H
-    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
-    if (prof) PB_CUDA(cudaMemcpyAsync(ctx->h_counters, w.d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+    if (prof) PB_CUDA(cudaMemcpyAsync(io.h_counters, w.d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     if (host_io) {
-        PB_CUDA(cudaMemcpyAsync(cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(cluster_num, w.cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(io.cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(io.degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(io.cluster_num, w.cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
     }
+    mark();  // end
     PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace
+
+static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
+                    const float *zo, const int32_t *sem, const int32_t *seg_counts, int32_t n_seg,
+                    const int32_t *call_seg_counts, int32_t n_calls, int64_t n_pts, const float *radius,
+                    const int32_t *min_pts, float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
+                    int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap,
+                    int64_t *n_clusters_out, int64_t *call_clusters, int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_seg < 0 || n_pts < 0 || n_calls < 0 || (n_seg > 0 && !seg_counts) || !radius || !min_pts || !n_clusters_out)
+        return fail(ctx, PB_ERR_ARG, "null / negative argument");
+    if (n_pts >= (int64_t)1 << 31) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^31");
+    if (n_seg >= (1 << 22)) return fail(ctx, PB_ERR_ARG, "n_seg must be below 2^22");
+    if (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE) return fail(ctx, PB_ERR_ARG, "bad mem_kind");
+    const int S = n_seg;
+    const int n = (int)n_pts;
+    std::vector<int> start(S + 1, 0);
+    for (int s = 0; s < S; s++) {
+        if (seg_counts[s] < 0) return fail(ctx, PB_ERR_ARG, "negative segment size");
+        long long t = (long long)start[s] + seg_counts[s];
+        if (t > n_pts) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+        start[s + 1] = (int)t;
+    }
+    if ((S == 0 ? 0 : start[S]) != n) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+    std::vector<int> call_seg0(n_calls + 1, 0);
+    for (int c = 0; c < n_calls; c++) {
+        if (!call_seg_counts || call_seg_counts[c] < 0 || call_seg0[c] + call_seg_counts[c] > S)
+            return fail(ctx, PB_ERR_ARG, "bad call_seg_counts");
+        call_seg0[c + 1] = call_seg0[c] + call_seg_counts[c];
+    }
+    if (call_seg0[n_calls] != S) return fail(ctx, PB_ERR_ARG, "sum(call_seg_counts) != n_seg");
+    *n_clusters_out = 0;
+    if (call_clusters)
+        for (int c = 0; c < n_calls; c++) call_clusters[c] = 0;
+    if (n > 0 && (!x || !y || !z || !xo || !yo || !zo || !sem || !cluster_id || !degree))
+        return fail(ctx, PB_ERR_ARG, "null data pointer");
+    if (S > 0 && !cluster_num) return fail(ctx, PB_ERR_ARG, "null cluster_num");
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (n == 0) {
+        if (S > 0) {
+            if (host_io) std::memset(cluster_num, 0, sizeof(int) * S);
+            else PB_CUDA(cudaMemsetAsync(cluster_num, 0, sizeof(int) * S, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+        return PB_OK;
+    }
+
+    // ---- chunking: runs of consecutive calls of ~chunk_points points, alternating over two streams so
+    //      the latency-bound tail kernels and the host copies of one chunk overlap k_degree of the next
+    struct Chunk { int c0, c1, s0, s1, p0, p1; };
+    std::vector<Chunk> chunks;
+    {
+        // automatic: two chunks once a call has >= 6 M points (smaller chunks lose more to launch gaps and
+        // kernel tails than the overlap wins: 48 ms at 2 chunks, 51 at 4, 59 at 10 for 28.8 M points)
+        long long target = ctx->chunk_points > 0 ? ctx->chunk_points
+                           : (ctx->chunk_points == 0 && n >= 6000000 ? ((long long)n + 1) / 2 : (long long)n + 1);
+        int c = 0;
+        while (c < n_calls) {
+            Chunk ch;
+            ch.c0 = c;
+            ch.s0 = call_seg0[c];
+            ch.p0 = start[ch.s0];
+            long long pts = 0;
+            while (c < n_calls && pts < target) {  // whole calls until the chunk reaches the target size
+                pts += start[call_seg0[c + 1]] - start[call_seg0[c]];
+                c++;
+            }
+            ch.c1 = c;
+            ch.s1 = call_seg0[c];
+            ch.p1 = start[ch.s1];
+            if (ch.p1 > ch.p0) chunks.push_back(ch);
+            else if (ch.s1 > ch.s0 && !chunks.empty()) chunks.back().c1 = ch.c1, chunks.back().s1 = ch.s1;  // empty calls ride along
+            else if (ch.s1 > ch.s0) chunks.push_back(ch);
+        }
+        // leading empty-call chunk followed by real ones: merge forward
+        if (chunks.size() > 1 && chunks[0].p1 == chunks[0].p0) {
+            chunks[1].c0 = chunks[0].c0, chunks[1].s0 = chunks[0].s0, chunks[1].p0 = chunks[0].p0;
+            chunks.erase(chunks.begin());
+        }
+    }
+    const int G = (int)chunks.size();
+    const bool multi = G > 1;
+    int n_max = 0, S_max = 0;
+    for (auto &ch : chunks) n_max = std::max(n_max, ch.p1 - ch.p0), S_max = std::max(S_max, ch.s1 - ch.s0);
+    const int slots = multi ? 2 : 1;
+
+    // ---- workspace: `slots` private work areas + call-wide cluster metadata ------------------------------
+    Work w[2];
+    float *center_all = nullptr, *d_radius = nullptr, *d_thresh = nullptr;
+    int *clt_sem_all = nullptr, *d_min_pts = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        if (pass == 1) ctx->arena.off = 0, ctx->arena.dry = false;
+        center_all = a.get<float>(3 * (size_t)n);
+        clt_sem_all = a.get<int>((size_t)n);
+        d_radius = a.get<float>(18);
+        d_thresh = a.get<float>(18);
+        d_min_pts = a.get<int>(18);
+        for (int k = 0; k < slots; k++) {
+            std::memset(&w[k], 0, sizeof(Work));
+            plan(a, w[k], n_max, S_max, host_io, center_cap, clt_sem_cap);
+        }
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+        }
+    }
+    // pinned scalars per chunk
+    if ((int)ctx->h_chunk_cap < G) {
+        if (ctx->h_chunk_scalars) cudaFreeHost(ctx->h_chunk_scalars);
+        if (ctx->h_chunk_counters) cudaFreeHost(ctx->h_chunk_counters);
+        ctx->h_chunk_scalars = nullptr, ctx->h_chunk_counters = nullptr, ctx->h_chunk_cap = 0;
+        PB_CUDA(cudaMallocHost(&ctx->h_chunk_scalars, sizeof(int) * 16 * (size_t)G));
+        PB_CUDA(cudaMallocHost(&ctx->h_chunk_counters, sizeof(unsigned long long) * 8 * (size_t)G));
+        ctx->h_chunk_cap = G;
+    }
+    const bool prof = ctx->profiling;
+    if (prof && (int)ctx->chunk_ev.size() < G * (ST_COUNT + 1)) {
+        size_t old = ctx->chunk_ev.size();
+        ctx->chunk_ev.resize((size_t)G * (ST_COUNT + 1));
+        for (size_t i = old; i < ctx->chunk_ev.size(); i++) cudaEventCreate(&ctx->chunk_ev[i]);
+    }
+    float thresh[18];
+    for (int i = 0; i < 18; i++) thresh[i] = kMeanCount[i] * para_f;  // fp32 multiply, binary.cu:256
+    PB_CUDA(cudaMemcpyAsync(d_radius, radius, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(d_min_pts, min_pts, sizeof(int) * 18, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(d_thresh, thresh, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
+
+    cudaStream_t cs[2] = {st, st};
+    if (multi) {
+        cs[0] = ctx->aux[0], cs[1] = ctx->aux[1];
+        PB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        PB_CUDA(cudaStreamWaitEvent(cs[0], ctx->ev_fork, 0));
+        PB_CUDA(cudaStreamWaitEvent(cs[1], ctx->ev_fork, 0));
+    }
+    std::vector<int> lstart, lcall;
+    for (int gi = 0; gi < G; gi++) {
+        const Chunk &ch = chunks[gi];
+        ChunkIO io;
+        io.n = ch.p1 - ch.p0;
+        io.S = ch.s1 - ch.s0;
+        lstart.assign(io.S + 1, 0);
+        lcall.assign(std::max(io.S, 1), 0);
+        for (int s = 0; s <= io.S; s++) lstart[s] = start[ch.s0 + s] - ch.p0;
+        for (int c = ch.c0; c < ch.c1; c++)
+            for (int s = call_seg0[c]; s < call_seg0[c + 1]; s++) lcall[s - ch.s0] = call_seg0[c] - ch.s0;
+        io.x = x + ch.p0, io.y = y + ch.p0, io.z = z + ch.p0, io.xo = xo + ch.p0, io.yo = yo + ch.p0, io.zo = zo + ch.p0;
+        io.sem = sem + ch.p0;
+        io.cluster_id = cluster_id + ch.p0, io.degree = degree + ch.p0, io.cluster_num = cluster_num + ch.s0;
+        io.start = lstart.data(), io.call_first = lcall.data();
+        io.center_out = center_all + 3 * (size_t)ch.p0, io.clt_sem_out = clt_sem_all + ch.p0;
+        io.h_scalars = ctx->h_chunk_scalars + 16 * gi, io.h_counters = ctx->h_chunk_counters + 8 * gi;
+        io.ev = prof ? &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)] : nullptr;
+        int rc = enqueue_chunk(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches);
+        if (rc) return rc;
+    }
+    if (multi) {
+        PB_CUDA(cudaEventRecord(ctx->ev_join[0], cs[0]));
+        PB_CUDA(cudaEventRecord(ctx->ev_join[1], cs[1]));
+        PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+        PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
+    }
     PB_CUDA(cudaStreamSynchronize(st));
-    const int errbits = ctx->h_scalars[0];
+    int errbits = 0;
+    long long K = 0;
+    for (int gi = 0; gi < G; gi++) errbits |= ctx->h_chunk_scalars[16 * gi], K += ctx->h_chunk_scalars[16 * gi + 3];
     if (errbits & pb::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "class id outside [2,19]");
     if (errbits & pb::kErrNonFinite) return fail(ctx, PB_ERR_NONFINITE, "non-finite coordinate");
     if (errbits & pb::kErrRange) return fail(ctx, PB_ERR_RANGE, "segment spans more than 16383 grid cells along an axis");
     if (errbits & pb::kErrMixed) return fail(ctx, PB_ERR_MIXED_CLASS, "segment mixes classes (unsupported)");
-    const int K = ctx->h_scalars[3];
     *n_clusters_out = K;
     if (K > 0) {
         if (!center || !clt_sem || 3LL * K > center_cap || K > clt_sem_cap)
             return fail(ctx, PB_ERR_CAPACITY, "center / clt_sem capacity too small for " + std::to_string(K) + " clusters");
         cudaMemcpyKind kind = host_io ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-        PB_CUDA(cudaMemcpyAsync(center, w.center, sizeof(float) * 3 * (size_t)K, kind, st));
-        PB_CUDA(cudaMemcpyAsync(clt_sem, w.clt_sem, sizeof(int) * (size_t)K, kind, st));
+        long long ko = 0;
+        for (int gi = 0; gi < G; gi++) {
+            long long kg = ctx->h_chunk_scalars[16 * gi + 3];
+            if (kg > 0) {
+                PB_CUDA(cudaMemcpyAsync(center + 3 * ko, center_all + 3 * (size_t)chunks[gi].p0, sizeof(float) * 3 * (size_t)kg, kind, st));
+                PB_CUDA(cudaMemcpyAsync(clt_sem + ko, clt_sem_all + chunks[gi].p0, sizeof(int) * (size_t)kg, kind, st));
+            }
+            ko += kg;
+        }
+        PB_CUDA(cudaStreamSynchronize(st));
     }
-    mark();  // end
-    PB_CUDA(cudaStreamSynchronize(st));
     if (call_clusters) {
-        // cluster counts per call: needs cluster_num on the host
         std::vector<int> cn(S);
         const int *src = cluster_num;
         if (!host_io) {
             PB_CUDA(cudaMemcpy(cn.data(), cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost));
             src = cn.data();
         }
-        int s = 0;
         for (int c = 0; c < n_calls; c++) {
             long long t = 0;
-            for (int k = 0; k < call_seg_counts[c]; k++) t += src[s + k];
+            for (int s = call_seg0[c]; s < call_seg0[c + 1]; s++) t += src[s];
             call_clusters[c] = t;
-            s += call_seg_counts[c];
         }
     }
     if (prof) {
-        for (int i = 0; i < ST_COUNT; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-        ctx->counters[0] = (int64_t)ctx->h_counters[0];
-        ctx->counters[1] = (int64_t)ctx->h_counters[1];
-        ctx->counters[2] = (int64_t)ctx->h_counters[2];
-        ctx->counters[3] = (int64_t)ctx->h_scalars[4];
-        ctx->counters[4] = (int64_t)ctx->h_scalars[1];
-        ctx->counters[5] = (int64_t)ctx->h_scalars[2];
+        for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+        for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
+        for (int gi = 0; gi < G; gi++) {
+            cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
+            for (int i = 0; i < ST_COUNT; i++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                ctx->stage_ms[i] += ms;
+            }
+            const unsigned long long *hc = ctx->h_chunk_counters + 8 * gi;
+            const int *hs = ctx->h_chunk_scalars + 16 * gi;
+            ctx->counters[0] += (int64_t)hc[0];
+            ctx->counters[1] += (int64_t)hc[1];
+            ctx->counters[2] += (int64_t)hc[2];
+            ctx->counters[3] += hs[4];
+            ctx->counters[4] += hs[1];
+            ctx->counters[5] += hs[2];
+        }
+        ctx->counters[6] = G;
     }
     return PB_OK;
 }
@@ -515,33 +686,6 @@ extern "C" int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, co
 // =================================================================================================
 #include "pb_voxel.cuh"
 
-namespace {
-int ensure_arena(pb_ctx *ctx, size_t need, cudaStream_t st) {
-    if (need > ctx->arena.cap) {
-        PB_CUDA(cudaStreamSynchronize(st));
-        if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
-        ctx->arena.base = nullptr;
-        ctx->arena.cap = 0;
-        size_t want = need + need / 4;
-        if (cudaMalloc(&ctx->arena.base, want) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(ctx, PB_ERR_NOMEM, "workspace allocation of " + std::to_string(want) + " bytes failed");
-        }
-        ctx->arena.cap = want;
-    }
-    ctx->arena.off = 0;
-    ctx->arena.dry = false;
-    return PB_OK;
-}
-
-void launch_scan(cudaStream_t st, const int *in, int n_host, const int *n_dev, int *out, int *total, int *blocks, int64_t &L) {
-    int nb = div_up(n_host, pb::kScanTile);
-    pb::k_scan_reduce<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks);
-    pb::k_scan_spine<<<1, pb::kScanThreads, 0, st>>>(blocks, nb, total);
-    pb::k_scan_down<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, blocks, out);
-    L += 3;
-}
-}  // namespace
 
 extern "C" int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int stride, int has_batch_col,
                            const int32_t *batch, int64_t n, double voxel_size, int32_t *vcoords, int64_t *index,

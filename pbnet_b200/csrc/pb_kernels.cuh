@@ -29,7 +29,16 @@ constexpr int kRowShift = 3 + kCoarseBits;     // 16: key >> 16 identifies (seg,
 constexpr int kRuns = 9;                       // 3 x 3 coarse stencil rows, each up to 3 coarse cells long
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHpBit = 0x80000000;
-constexpr int kWindow = 128;                   // query points per warp in k_degree (4 per lane)
+#ifndef PB_WINDOW
+#define PB_WINDOW 128
+#endif
+#ifndef PB_DEG_MINB
+#define PB_DEG_MINB 9
+#endif
+#ifndef PB_DEG_PIPE
+#define PB_DEG_PIPE 0
+#endif
+constexpr int kWindow = PB_WINDOW;             // query points per warp in k_degree (PB_WINDOW/32 per lane)
 
 enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8 };
 
@@ -397,6 +406,27 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
     for (int k = 0; k < kRuns; k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
         int j = b;
+#if PB_DEG_PIPE
+        if (j + 2 <= e) {  // software pipeline: the next 2 candidates are in flight while 2 are tested
+            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1);
+            j += 2;
+#pragma unroll 1
+            for (; j + 2 <= e; j += 2) {
+                float4 n0 = __ldg(pts4 + j), n1 = __ldg(pts4 + j + 1);
+#pragma unroll
+                for (int s = 0; s < Q; s++) {
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
+                }
+                q0 = n0, q1 = n1;
+            }
+#pragma unroll
+            for (int s = 0; s < Q; s++) {
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
+                count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
+            }
+        }
+#else
 #pragma unroll 1
         for (; j + 4 <= e; j += 4) {
             float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
@@ -408,6 +438,7 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
                 count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
             }
         }
+#endif
         for (; j < e; j++) {
             float4 q0 = __ldg(pts4 + j);
 #pragma unroll
@@ -421,7 +452,7 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PB_DEG_MINB)
 k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = lane_id();
@@ -461,10 +492,20 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
             unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
             tests += (unsigned long long)cand * (unsigned)total;
         }
-        if (total <= 32) degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
-        else if (total <= 64) degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
-        else if (total <= 96) degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
-        else degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted);
+        switch ((total + 31) >> 5) {
+            case 1: degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            case 2: degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            case 3: degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+#if PB_WINDOW > 128
+            case 4: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            case 5: degree_group<5>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            case 6: degree_group<6>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            case 7: degree_group<7>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+            default: degree_group<8>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+#else
+            default: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
+#endif
+        }
         pos = gend;
     }
     if (n_tests && lane == 0) atomicAdd(n_tests, tests);
@@ -508,13 +549,14 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     }
 }
 
-// true iff fine cells with keys ka, kb are within the 5x5x5 fine stencil of each other
-__device__ __forceinline__ bool fine_near(uint64_t ka, uint64_t kb) {
+// Chebyshev distance (in fine cells) between the cells with keys ka, kb; <= 2 means inside the 5x5x5 stencil
+__device__ __forceinline__ int fine_dist(uint64_t ka, uint64_t kb) {
     int ax, ay, az, bx, by, bz;
     key_fine(ka, ax, ay, az);
     key_fine(kb, bx, by, bz);
-    return abs(ax - bx) <= 2 && abs(ay - by) <= 2 && abs(az - bz) <= 2;
+    return max(max(abs(ax - bx), abs(ay - by)), abs(az - bz));
 }
+__device__ __forceinline__ bool fine_near(uint64_t ka, uint64_t kb) { return fine_dist(ka, kb) <= 2; }
 
 // cooperative search for ONE HP pair (a in A, b in B) within r; warp-uniform result
 __device__ __forceinline__ bool hp_pair_exists(const float4 *__restrict__ pts4, int a0, int a1, int b0, int b1,
@@ -538,9 +580,10 @@ __device__ __forceinline__ bool hp_pair_exists(const float4 *__restrict__ pts4, 
 // K10  HP connectivity (pass B): union-find over FINE cells.  One warp per HP-cell A; the lanes check
 //      32 stencil cells at a time (HP-bearing, inside the 5^3 fine stencil, ordinal > A, different
 //      root) and only the survivors pay a pair search that stops at the first HP pair within r.
+//      Launched twice: touching cells first, then the cells at fine distance 2.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp, int *parent) {
+k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp, int *parent, int far_pass) {
     int F = *g.d_F;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
@@ -564,7 +607,12 @@ k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__rest
             for (int fb = max(b, A + 1); fb < e; fb += 32) {
                 int B = fb + lane;
                 bool cand = false;
-                if (B < e && cell_hp[B] > 0 && fine_near(kA, g.fcell_key[B])) cand = uf_find(parent, B) != rootA;
+                if (B < e && cell_hp[B] > 0) {
+                    // pass 0 joins touching cells (almost always an immediate hit); pass 1 then finds most of
+                    // the distance-2 cells already in the same set and skips their (expensive) pair search
+                    int d = fine_dist(kA, g.fcell_key[B]);
+                    if (far_pass ? d == 2 : d <= 1) cand = uf_find(parent, B) != rootA;
+                }
                 unsigned m = __ballot_sync(kFull, cand);
                 while (m) {
                     int l = __ffs(m) - 1;

