@@ -45,8 +45,9 @@ def _sample_ellipsoid_surface(rng, n, half):
     return v * half
 
 
-def make_scene(seed: int, n_points: int = 150_000):
-    """Returns dict(xyz_orig f32[N,3], offset f32[N,3], sem i64[N], n_objects)."""
+def make_scene(seed: int, n_points: int = 150_000, hp_frac: float = 0.85):
+    """Returns dict(xyz_orig f32[N,3], offset f32[N,3], sem i64[N], n_objects).  ``hp_frac`` = fraction of
+    object points whose offset collapses them onto the object centroid (0.85 = SURVEY.md §8d C0/C1)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_bg = int(round(0.38 * n_points))
     n_fg = n_points - n_bg
@@ -87,7 +88,7 @@ def make_scene(seed: int, n_points: int = 150_000):
                            half[2] + rng.uniform(0.0, 0.5)])
         pts = pts + centre
         centroid = pts.mean(axis=0)
-        hp = rng.random(n) < 0.85
+        hp = rng.random(n) < hp_frac
         off = np.where(hp[:, None],
                        (centroid - pts) * rng.uniform(0.85, 1.0, size=(n, 1)) + rng.normal(0, 0.015, size=(n, 3)),
                        rng.normal(0, 0.03, size=(n, 3)))
@@ -147,3 +148,26 @@ def class_calls(scene: dict, copies: int = 1):
                           sem=np.full(orig.shape[0], sem_id, dtype=np.int64),
                           seg_counts=np.full(copies, ind.shape[0], dtype=np.int32), index=ind))
     return calls
+
+
+def make_dense_case(seed: int, n_points: int, hp_fraction: float, radius: float = RADIUS, blob_points: int = 2001,
+                    sem_id: int = 9):
+    """SURVEY.md §8d config C4 (dense-neighbour pathological case): one single-class segment;
+    ``hp_fraction`` of the points sit in tight Gaussian blobs (sigma = r/4, ``blob_points`` each, degree
+    ~ blob_points - 1), the rest is a uniform background whose expected degree stays below min_pts.
+    Returns (xyz_shift, xyz_orig, sem)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_hp = int(round(hp_fraction * n_points)) // blob_points * blob_points
+    n_bg = n_points - n_hp
+    # background density: expected neighbours in an r-ball = 8 -> volume per point = (4/3)pi r^3 / 8
+    side = (max(n_bg, 1) * (4.0 / 3.0) * np.pi * radius ** 3 / 8.0) ** (1.0 / 3.0)
+    side = max(side, 1.0)
+    bg = rng.uniform(0.0, side, size=(n_bg, 3))
+    k = n_hp // blob_points
+    centres = rng.uniform(0.0, side, size=(k, 3))
+    blobs = (centres[:, None, :] + rng.normal(0.0, radius / 4.0, size=(k, blob_points, 3))).reshape(-1, 3)
+    xs = np.concatenate([bg, blobs]).astype(np.float32)
+    perm = rng.permutation(n_points)
+    xs = xs[perm]
+    xo = (xs + rng.normal(0.0, 0.05, size=xs.shape)).astype(np.float32)  # original coords: smeared copies
+    return xs, xo, np.full(n_points, sem_id, dtype=np.int32)
