@@ -36,7 +36,7 @@ enum {
     PB_ERR_SEM_RANGE = 3,   /* a class id outside [2,19] (the reference indexes 18-entry tables with sem-2) */
     PB_ERR_NONFINITE = 4,   /* NaN / Inf coordinate */
     PB_ERR_RANGE = 5,       /* a segment spans more than 16383 grid cells along one axis */
-    PB_ERR_MIXED_CLASS = 6, /* a segment mixes classes (PBNet never does; not supported yet) */
+    PB_ERR_MIXED_CLASS = 6, /* a segment mixes classes whose radius table entries differ (undefined in the reference) */
     PB_ERR_CAPACITY = 7,    /* center / clt_sem capacity too small for the clusters found */
     PB_ERR_NOMEM = 8
 };
@@ -110,7 +110,8 @@ int pb_stage_count(void);
 const char *pb_stage_name(int i);
 float pb_stage_ms(const pb_ctx *ctx, int i);
 /* counters of the last call: [0] pair tests issued by the degree kernel, [1] sum of degrees,
- * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter */
+ * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter,
+ * [6] chunks, [7] 1 if the mixed-class kernels were needed */
 int64_t pb_counter(const pb_ctx *ctx, int i);
 
 /* ------------------------------------------------------------------------------------------------

@@ -81,7 +81,7 @@ class Context:
         return {self._lib.pb_stage_name(i).decode(): float(self._lib.pb_stage_ms(self._h, i)) for i in range(n)}
 
     def counters(self) -> dict:
-        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks"]
+        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode"]
         return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------------------------------------

@@ -177,6 +177,8 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     int2 *runs9;
     // per raw cluster (upper bound N)
     int *rep, *raw_count, *keep, *kscan, *clt_seg;
+    // mixed-class mode only: per (fine cell, class) and per (segment, class) tables
+    int *cell_min18, *comp_min18, *cell_gid18, *cnt18, *pos18, *lab_start18, *seg_lastlab;
     // scalars
     int *d_scalars;  // [0] err [1] C [2] R [3] K [4] Q [5] L
     unsigned long long *d_counters;
@@ -185,8 +187,13 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     size_t cub_bytes;
 };
 
-void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_cap, long long clt_cap) {
+void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
     size_t N = (size_t)n;
+    if (mixed) {
+        w.cell_min18 = a.get<int>(N * pb::kCls); w.comp_min18 = a.get<int>(N * pb::kCls); w.cell_gid18 = a.get<int>(N * pb::kCls);
+        w.cnt18 = a.get<int>((size_t)S * pb::kCls + 1); w.pos18 = a.get<int>((size_t)S * pb::kCls + 1);
+        w.lab_start18 = a.get<int>((size_t)S * pb::kCls + 1); w.seg_lastlab = a.get<int>(S);
+    }
     if (host_io) {
         w.x = a.get<float>(N); w.y = a.get<float>(N); w.z = a.get<float>(N);
         w.xo = a.get<float>(N); w.yo = a.get<float>(N); w.zo = a.get<float>(N);
@@ -220,14 +227,12 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, long long center_
     w.rep = a.get<int>(N); w.raw_count = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
     w.d_scalars = a.get<int>(16);
     w.d_counters = a.get<unsigned long long>(8);
-    w.scan_blocks = a.get<int>(N / pb::kScanTile + 2);
+    w.scan_blocks = a.get<int>(std::max(N, (size_t)S * pb::kCls) / pb::kScanTile + 2);
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
     w.cub_bytes = bytes;
     w.cub_tmp = a.get<char>(bytes);
-    (void)center_cap;
-    (void)clt_cap;
 }
 
 }  // namespace
@@ -278,6 +283,7 @@ struct ChunkIO {          // one chunk = a run of consecutive calls; all pointer
 };
 
 // Enqueues the whole launch sequence of one chunk on `st`.  No host synchronisation.
+template <bool MIXED>
 int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assign_lp, const float *d_radius,
                   const int *d_min_pts, const float *d_thresh, cudaStream_t st, int64_t &L) {
     const int n = io.n, S = io.S;
@@ -319,6 +325,10 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     PB_CUDA(cudaMemsetAsync(w.d_counters, 0, sizeof(unsigned long long) * 8, st));
     PB_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int) * (size_t)n, st));
     PB_CUDA(cudaMemsetAsync(w.raw_count, 0, sizeof(int) * (size_t)n, st));
+    if (MIXED) {
+        PB_CUDA(cudaMemsetAsync(w.cnt18, 0, sizeof(int) * ((size_t)S * pb::kCls + 1), st));
+        PB_CUDA(cudaMemsetAsync(w.seg_lastlab, 0xff, sizeof(int) * S, st));
+    }
     int *d_err = w.d_scalars, *d_F = w.d_scalars + 1, *d_R = w.d_scalars + 2, *d_K = w.d_scalars + 3,
         *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5, *d_Cc = w.d_scalars + 6, *d_rows = w.d_scalars + 7;
     unsigned long long *cnt = prof ? w.d_counters : nullptr;
@@ -330,7 +340,8 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     mark();  // PREP
     pb::k_prep_points<<<gN, T, 0, st>>>(n, S, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, d_err);
     pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, d_radius, d_min_pts);
-    pb::k_keys<<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err);
+    pb::k_keys<MIXED><<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err,
+                                        d_radius, w.cnt18);
     L += 3;
 
     mark();  // SORT
@@ -357,6 +368,10 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head_f, w.ex_f, w.head_c, w.ex_c, w.head_r, w.ex_r, w.fcell_of, w.row_of,
                                   w.fcell_start, w.fcell_key, w.fcell_cc, w.cc_pstart, w.cc_fstart, w.cc_key, w.parent,
                                   w.cell_hp, w.cell_minhp, w.comp_min, d_F, d_Cc);
+    if (MIXED) {  // per (fine cell, class) tables start at "no HP" (F <= n cells)
+        PB_CUDA(cudaMemsetAsync(w.cell_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
+        PB_CUDA(cudaMemsetAsync(w.comp_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
+    }
     pb::k_seg_cells<<<gS, T, 0, st>>>(n, S, w.sg, w.fcell_of, w.fcell_cc, d_Cc);
     pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
     L += 3;
@@ -369,30 +384,32 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     pb::k_degree<<<div_up(n, pb::kWindow * 4), 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
     L++;
     mark();  // HP
-    pb::k_hp_cells<<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
-                                     w.cell_minhp, cnt);
+    pb::k_hp_cells<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
+                                            w.cell_minhp, cnt, dsem, d_min_pts, w.cell_min18);
     L++;
     mark();  // UNION
     pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0);
     pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1);
     L += 2;
     mark();  // COMPONENTS
-    pb::k_comp_min<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min);
-    pb::k_flag_roots<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag);
+    pb::k_comp_min<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min, w.cell_min18, w.comp_min18);
+    pb::k_flag_roots<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag, w.comp_min18);
     L += 2;
     scan(w.flag, n, nullptr, w.gid_at, d_R);
-    pb::k_cell_gid<<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep);
+    pb::k_cell_gid<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep, w.comp_min18,
+                                                  w.cell_gid18);
     L++;
     mark();  // LABEL
-    pb::k_label<<<div_up(n, 128), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label, w.raw_count);
+    pb::k_label<MIXED><<<div_up(n, 128), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label, w.raw_count, dsem,
+                                                       w.cell_gid18);
     L++;
     mark();  // FILTER
-    pb::k_filter<<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, d_thresh, w.keep);
+    pb::k_filter<MIXED><<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, d_thresh, w.keep, dsem);
     L++;
     scan(w.keep, n, d_R, w.kscan, d_K);
     pb::k_seg_clusters<<<gS, T, 0, st>>>(n, S, w.sg, w.seg_call_first, w.gid_at, d_R, w.kscan, d_K, d_cluster_num);
-    pb::k_relabel<<<gN, T, 0, st>>>(n, w.sg, w.seg_of, w.raw_label, w.keep, w.kscan, assign_lp, d_cluster_id, w.qflag,
-                                    io.clt_sem_out, w.clt_seg, w.rep);
+    pb::k_relabel<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.seg_of, w.raw_label, w.keep, w.kscan, assign_lp, d_cluster_id, w.qflag,
+                                           io.clt_sem_out, w.clt_seg, w.rep, dsem, w.seg_lastlab);
     L += 2;
     mark();  // LP_BUILD
     if (assign_lp) {
@@ -402,14 +419,19 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         scan(w.labflag, n, nullptr, w.lpos, d_L);
         pb::k_compact<<<gN, T, 0, st>>>(n, w.qflag, w.qpos, w.qlist, w.order2, w.labflag, w.lpos, dxo, dyo, dzo, w.lab4);
         pb::k_seg_lab<<<gS, T, 0, st>>>(n, S, w.sg, w.lpos, d_L);
+        if (MIXED) {
+            scan(w.cnt18, S * pb::kCls, nullptr, w.pos18, w.d_scalars + 8);
+            pb::k_seg_lab18<<<div_up((long long)S * pb::kCls + 1, T), T, 0, st>>>(n, S, w.pos18, w.lpos, d_L, w.lab_start18);
+            L++;
+        }
         pb::k_lab_boxes<<<gPersist, T, 0, st>>>(d_L, w.lab4, w.box_lo, w.box_hi);
         pb::k_lab_boxes2<<<gPersist, T, 0, st>>>(d_L, w.box_lo, w.box_hi, w.box2_lo, w.box2_hi);
         L += 4;
     }
     mark();  // LP_NN
     if (assign_lp) {
-        pb::k_nn<<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, w.inv2, w.lpos, dxo, dyo, dzo, w.lab4, w.box_lo,
-                                         w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id);
+        pb::k_nn<MIXED><<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, w.inv2, w.lpos, dxo, dyo, dzo, w.lab4, w.box_lo,
+                                                w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id, dsem, w.lab_start18, w.seg_lastlab);
         L++;
     }
     mark();  // CENTRES
@@ -518,6 +540,11 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     for (auto &ch : chunks) n_max = std::max(n_max, ch.p1 - ch.p0), S_max = std::max(S_max, ch.s1 - ch.s0);
     const int slots = multi ? 2 : 1;
 
+    // Segments that mix classes (never produced by PBNet) are detected on the device by the first attempt;
+    // the call is then repeated with the per-(cell, class) tables of the mixed-class kernels.
+    for (int attempt = 0; attempt < 2; attempt++) {
+    const bool mixed = attempt == 1;
+    ctx->launches = 0;
     // ---- workspace: `slots` private work areas + call-wide cluster metadata ------------------------------
     Work w[2];
     float *center_all = nullptr, *d_radius = nullptr, *d_thresh = nullptr;
@@ -534,7 +561,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         d_min_pts = a.get<int>(18);
         for (int k = 0; k < slots; k++) {
             std::memset(&w[k], 0, sizeof(Work));
-            plan(a, w[k], n_max, S_max, host_io, center_cap, clt_sem_cap);
+            plan(a, w[k], n_max, S_max, host_io, mixed);
         }
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
@@ -587,7 +614,8 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         io.center_out = center_all + 3 * (size_t)ch.p0, io.clt_sem_out = clt_sem_all + ch.p0;
         io.h_scalars = ctx->h_chunk_scalars + 16 * gi, io.h_counters = ctx->h_chunk_counters + 8 * gi;
         io.ev = prof ? &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)] : nullptr;
-        int rc = enqueue_chunk(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches);
+        int rc = mixed ? enqueue_chunk<true>(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches)
+                       : enqueue_chunk<false>(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches);
         if (rc) return rc;
     }
     if (multi) {
@@ -603,7 +631,9 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     if (errbits & pb::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "class id outside [2,19]");
     if (errbits & pb::kErrNonFinite) return fail(ctx, PB_ERR_NONFINITE, "non-finite coordinate");
     if (errbits & pb::kErrRange) return fail(ctx, PB_ERR_RANGE, "segment spans more than 16383 grid cells along an axis");
-    if (errbits & pb::kErrMixed) return fail(ctx, PB_ERR_MIXED_CLASS, "segment mixes classes (unsupported)");
+    if (errbits & pb::kErrRadius)
+        return fail(ctx, PB_ERR_MIXED_CLASS, "a segment mixes classes with different radii (undefined in the reference)");
+    if ((errbits & pb::kErrMixed) && !mixed) continue;  // repeat with the mixed-class kernels
     *n_clusters_out = K;
     if (K > 0) {
         if (!center || !clt_sem || 3LL * K > center_cap || K > clt_sem_cap)
@@ -635,7 +665,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     if (prof) {
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
-        for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
+        for (int i = 0; i < 7; i++) ctx->counters[i] = 0;
         for (int gi = 0; gi < G; gi++) {
             cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
             for (int i = 0; i < ST_COUNT; i++) {
@@ -654,7 +684,10 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         }
         ctx->counters[6] = G;
     }
+    ctx->counters[7] = mixed;
     return PB_OK;
+    }  // attempt
+    return fail(ctx, PB_ERR_MIXED_CLASS, "unreachable");
 }
 
 extern "C" int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo,

@@ -40,7 +40,9 @@ constexpr int kHpBit = 0x80000000;
 #endif
 constexpr int kWindow = PB_WINDOW;             // query points per warp in k_degree (PB_WINDOW/32 per lane)
 
-enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8 };
+enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8, kErrRadius = 16 };
+constexpr int kCls = 18;  // classes 2..19
+constexpr int kInf18 = 0x7f7f7f7f;  // 'no HP' marker of the per-class tables (memset 0x7f)
 
 // The reference's square_dist as nvcc 12.9 compiles it for sm_100a (checked in SASS at all three call
 // sites, lib/PB_lib/src/pbnet/binary_cuda_functions.cu:85,160,279,305-308):
@@ -240,16 +242,28 @@ __global__ void k_seg_params(int n, int S, SegArrays sg, const int *__restrict__
 
 // K3  per point: 64-bit sort keys.  key1 = seg | coarse z,y,x | fine z,y,x bit (shifted space);
 //     key2 = seg | morton(original space, cell edge g) for the LP-assignment ordering
+//     MIXED (segments that mix classes — the API allows it, PBNet never does): key2 additionally groups
+//     by class so that every (segment, class) owns one contiguous labelled range
+template <bool MIXED>
 __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const float *__restrict__ y,
                        const float *__restrict__ z, const float *__restrict__ xo,
                        const float *__restrict__ yo, const float *__restrict__ zo,
                        const int *__restrict__ sem, const int *__restrict__ seg_of,
                        uint64_t *__restrict__ key1, uint64_t *__restrict__ key2,
-                       uint32_t *__restrict__ val, int *err) {
+                       uint32_t *__restrict__ val, int *err, const float *__restrict__ radius_tab,
+                       int *__restrict__ cnt18) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = seg_of[i];
-    if (sem[i] != sg.cls[s]) atomicOr(err, kErrMixed);
+    int myc = min(max(sem[i], 2), 19);
+    if (!MIXED) {
+        if (sem[i] != sg.cls[s]) atomicOr(err, kErrMixed);
+    } else {
+        // the reference looks the radius up with a sorted-position index (binary_cuda_functions.cu:35,110):
+        // only well defined when all classes of a segment share one radius
+        if (radius_tab[myc - 2] != radius_tab[sg.cls[s] - 2]) atomicOr(err, kErrRadius);
+        atomicAdd(cnt18 + (long long)s * kCls + (myc - 2), 1);
+    }
     float ih = sg.inv_h[s];
     float fx = __fmul_rn(__fsub_rn(x[i], sg.min_s[3 * s]), ih);
     float fy = __fmul_rn(__fsub_rn(y[i], sg.min_s[3 * s + 1]), ih);
@@ -270,7 +284,11 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
     uint32_t mx = (uint32_t)min((gx >= 0.f && gx < 1e9f) ? (int)gx : 0, kCellMax);
     uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kCellMax);
     uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kCellMax);
-    key2[i] = ((uint64_t)s << kSegShift) | spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
+    if (!MIXED)
+        key2[i] = ((uint64_t)s << kSegShift) | spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
+    else
+        key2[i] = ((uint64_t)s << kSegShift) | ((uint64_t)(myc - 2) << 37) | spread3(mx >> 2) | (spread3(my >> 2) << 1) |
+                  (spread3(mz >> 2) << 2);
     val[i] = (uint32_t)i;
 }
 
@@ -512,10 +530,12 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order
+template <bool MIXED>
 __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const int *__restrict__ fcell_of,
                            const uint64_t *__restrict__ fcell_key, const int *__restrict__ deg_sorted,
                            int *__restrict__ degree_out, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
-                           unsigned long long *__restrict__ counters) {
+                           unsigned long long *__restrict__ counters, const int *__restrict__ sem,
+                           const int *__restrict__ min_pts_tab, int *__restrict__ cell_min18) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     unsigned act = __ballot_sync(kFull, valid);
@@ -525,7 +545,14 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     int d = deg_sorted[i];
     int *w = reinterpret_cast<int *>(pts4 + i) + 3;
     int orig = *w;
-    bool hp = d >= sg.min_pts[s];  // binary_cuda_functions.cu:175-186
+    bool hp;  // binary_cuda_functions.cu:175-186
+    if (!MIXED) {
+        hp = d >= sg.min_pts[s];
+    } else {
+        int myc = sem[orig] - 2;
+        hp = d >= min_pts_tab[myc];
+        if (hp) atomicMin(cell_min18 + (long long)c * kCls + myc, orig);
+    }
     degree_out[orig] = d;
     if (hp) *w = orig | kHpBit;
     unsigned grp = __match_any_sync(act, c);
@@ -633,41 +660,79 @@ k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__rest
 }
 
 // K11  flatten + minimum HP index of every component
+//      (MIXED: one minimum per (component, class): a cluster is a component restricted to one class that
+//      owns an HP in it — binary.cu:206-213 labels only visited points of the seed's class)
+template <bool MIXED>
 __global__ void k_comp_min(const int *__restrict__ d_F, const int *__restrict__ cell_hp, int *parent,
-                           const int *__restrict__ cell_minhp, int *comp_min) {
+                           const int *__restrict__ cell_minhp, int *comp_min, const int *__restrict__ cell_min18,
+                           int *comp_min18) {
     int F = *d_F;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x) {
         if (cell_hp[c] == 0) continue;
         int r = uf_find(parent, c);
         if (r != c) __stcg(parent + c, r);
-        atomicMin(comp_min + r, cell_minhp[c]);
+        if (!MIXED) {
+            atomicMin(comp_min + r, cell_minhp[c]);
+        } else {
+            for (int k = 0; k < kCls; k++) {
+                int v = cell_min18[(long long)c * kCls + k];
+                if (v != kInf18) atomicMin(comp_min18 + (long long)r * kCls + k, v);
+            }
+        }
     }
 }
 
 // K12  flag the minimum-index HP of every component (cluster numbering = rank of that index,
 //      binary.cu:161-166: seeds are taken in ascending point order)
+template <bool MIXED>
 __global__ void k_flag_roots(const int *__restrict__ d_F, const int *__restrict__ cell_hp,
                              const int *__restrict__ parent, const int *__restrict__ comp_min,
-                             int *__restrict__ flag) {
+                             int *__restrict__ flag, const int *__restrict__ comp_min18) {
     int F = *d_F;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x)
-        if (cell_hp[c] > 0 && parent[c] == c) flag[comp_min[c]] = 1;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x) {
+        if (!(cell_hp[c] > 0 && parent[c] == c)) continue;
+        if (!MIXED) {
+            flag[comp_min[c]] = 1;
+        } else {
+            for (int k = 0; k < kCls; k++) {
+                int v = comp_min18[(long long)c * kCls + k];
+                if (v != kInf18) flag[v] = 1;
+            }
+        }
+    }
 }
 
 // K13  raw cluster id of every HP-cell; representative point of every raw cluster
+template <bool MIXED>
 __global__ void k_cell_gid(const int *__restrict__ d_F, const int *__restrict__ cell_hp,
                            const int *__restrict__ parent, const int *__restrict__ comp_min,
-                           const int *__restrict__ gid_at, int *__restrict__ cell_gid, int *__restrict__ rep) {
+                           const int *__restrict__ gid_at, int *__restrict__ cell_gid, int *__restrict__ rep,
+                           const int *__restrict__ comp_min18, int *__restrict__ cell_gid18) {
     int F = *d_F;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F; c += gridDim.x * blockDim.x) {
-        int gi = -1;
-        if (cell_hp[c] > 0) {
-            int r = parent[c];
-            int u = comp_min[r];
-            gi = gid_at[u];
-            if (r == c) rep[gi] = u;
+        if (!MIXED) {
+            int gi = -1;
+            if (cell_hp[c] > 0) {
+                int r = parent[c];
+                int u = comp_min[r];
+                gi = gid_at[u];
+                if (r == c) rep[gi] = u;
+            }
+            cell_gid[c] = gi;
+        } else {
+            int r = cell_hp[c] > 0 ? parent[c] : -1;
+            for (int k = 0; k < kCls; k++) {
+                int gi = -1;
+                if (r >= 0) {
+                    int u = comp_min18[(long long)r * kCls + k];
+                    if (u != kInf18) {
+                        gi = gid_at[u];
+                        if (r == c) rep[gi] = u;
+                    }
+                }
+                cell_gid18[(long long)c * kCls + k] = gi;
+            }
         }
-        cell_gid[c] = gi;
     }
 }
 
@@ -676,9 +741,11 @@ __global__ void k_cell_gid(const int *__restrict__ d_F, const int *__restrict__ 
 //      among components owning an HP within r (later BFS overwrites earlier, binary.cu:206-213);
 //      LPs with no HP neighbour stay -1.  Cluster sizes (incl. border LPs) are counted here.
 // ------------------------------------------------------------------------------------------------
+template <bool MIXED>
 __global__ void __launch_bounds__(128)
 k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp,
-        const int *__restrict__ cell_gid, int *__restrict__ raw_label, int *__restrict__ raw_count) {
+        const int *__restrict__ cell_gid, int *__restrict__ raw_label, int *__restrict__ raw_count,
+        const int *__restrict__ sem, const int *__restrict__ cell_gid18) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int lane = lane_id();
     bool valid = i < n;
@@ -686,7 +753,9 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
     int c = valid ? g.fcell_of[i] : -1;
     bool hp = valid && (__float_as_int(p.w) & kHpBit);
     int label = -1;
-    if (hp) label = cell_gid[c];
+    int myc = 0;
+    if (MIXED && valid) myc = sem[__float_as_int(p.w) & ~kHpBit] - 2;
+    if (hp) label = MIXED ? cell_gid18[(long long)c * kCls + myc] : cell_gid[c];
     unsigned todo = __ballot_sync(kFull, valid && !hp);
     while (todo) {
         int leader = __ffs(todo) - 1;
@@ -711,13 +780,15 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
             for (int fb = b; fb < e; fb += 32) {
                 int B = fb + lane;
                 int gB = -1;
-                if (B < e && cell_hp[B] > 0 && fine_near(kL, g.fcell_key[B])) gB = cell_gid[B];
+                bool okB = B < e && cell_hp[B] > 0 && fine_near(kL, g.fcell_key[B]);
+                if (okB) gB = MIXED ? 0x7ffffffe : cell_gid[B];  // MIXED: the id depends on the query's class
                 int bestmin = __reduce_min_sync(kFull, mine ? best : 0x7fffffff);  // smallest best among my LPs
                 unsigned m = __ballot_sync(kFull, gB > bestmin);
                 while (m) {
                     int l = __ffs(m) - 1;
                     m &= m - 1;
                     int gc = __shfl_sync(kFull, gB, l);
+                    if (MIXED) gc = mine ? cell_gid18[(long long)(fb + l) * kCls + myc] : -1;
                     bool pend = mine && best < gc;
                     if (!__any_sync(kFull, pend)) continue;
                     int Bc = fb + l;
@@ -746,13 +817,15 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
 }
 
 // K15  fragment filter (binary.cu:219-268): drop raw cluster g iff float(size) < mean_count*para_f
+template <bool MIXED>
 __global__ void k_filter(const int *__restrict__ d_R, SegArrays sg, const int *__restrict__ rep,
                          const int *__restrict__ seg_of, const int *__restrict__ raw_count,
-                         const float *__restrict__ thresh18, int *__restrict__ keep) {
+                         const float *__restrict__ thresh18, int *__restrict__ keep, const int *__restrict__ sem) {
     int R = *d_R;
     for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < R; gi += gridDim.x * blockDim.x) {
         int s = seg_of[rep[gi]];
-        float t = thresh18[sg.cls[s] - 2];
+        // class of a cluster = class of its highest-index member (binary.cu:245); all members share it
+        float t = thresh18[(MIXED ? sem[rep[gi]] : sg.cls[s]) - 2];
         keep[gi] = ((float)raw_count[gi] < t) ? 0 : 1;
     }
 }
@@ -781,10 +854,12 @@ __global__ void k_seg_clusters(int n, int S, SegArrays sg, const int *__restrict
 }
 
 // K17  final ids of HP-stage labels; query flags for LP assignment; per-cluster metadata
+template <bool MIXED>
 __global__ void k_relabel(int n, SegArrays sg, const int *__restrict__ seg_of, const int *__restrict__ raw_label,
                           const int *__restrict__ keep, const int *__restrict__ kscan, int assign_lp,
                           int *__restrict__ cluster_id, int *__restrict__ qflag, int *__restrict__ clt_sem,
-                          int *__restrict__ clt_seg, const int *__restrict__ rep) {
+                          int *__restrict__ clt_seg, const int *__restrict__ rep, const int *__restrict__ sem,
+                          int *__restrict__ seg_lastlab) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n) return;
     int gi = raw_label[u];
@@ -794,9 +869,10 @@ __global__ void k_relabel(int n, SegArrays sg, const int *__restrict__ seg_of, c
         int kk = kscan[gi];
         id = kk - sg.id_base[s];
         if (rep[gi] == u) {
-            clt_sem[kk] = sg.cls[s];
+            clt_sem[kk] = MIXED ? sem[u] : sg.cls[s];
             clt_seg[kk] = s;
         }
+        if (MIXED) atomicMax(seg_lastlab + s, u);  // fallback target of binary_cuda_functions.cu:287-300
     }
     cluster_id[u] = id;
     qflag[u] = (id < 0 && assign_lp && sg.cluster_num[s] > 0) ? 1 : 0;
@@ -833,6 +909,15 @@ __global__ void k_seg_lab(int n, int S, SegArrays sg, const int *__restrict__ lp
     if (s > S) return;
     int b = sg.start[s];
     sg.lab_start[s] = b < n ? lpos[b] : *d_L;
+}
+
+// MIXED: first labelled-list position of every (segment, class) block of order2
+__global__ void k_seg_lab18(int n, int S, const int *__restrict__ pos18, const int *__restrict__ lpos,
+                            const int *__restrict__ d_L, int *__restrict__ lab_start18) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > S * kCls) return;
+    int pos = e < S * kCls ? pos18[e] : n;
+    lab_start18[e] = pos < n ? lpos[pos] : *d_L;
 }
 
 // K19  bounding boxes of the labelled list: level 1 = 32 points, level 2 = 32 level-1 boxes
@@ -921,20 +1006,33 @@ __device__ __forceinline__ void nn_scan_group(int gi, int l0, int l1, int lane, 
     }
 }
 
+template <bool MIXED>
 __global__ void __launch_bounds__(256)
 k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, const int *__restrict__ seg_of,
      const int *__restrict__ inv2, const int *__restrict__ lpos, const float *__restrict__ xo,
      const float *__restrict__ yo, const float *__restrict__ zo, const float4 *__restrict__ lab4,
      const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, const float4 *__restrict__ box2_lo,
-     const float4 *__restrict__ box2_hi, int *cluster_id) {
+     const float4 *__restrict__ box2_hi, int *cluster_id, const int *__restrict__ sem,
+     const int *__restrict__ lab_start18, const int *__restrict__ seg_lastlab) {
     int Q = *d_Q;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
     for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Q; qi += warps) {
         int p = qlist[qi];
         int s = seg_of[p];
-        int l0 = sg.lab_start[s], l1 = sg.lab_start[s + 1];
-        if (l1 <= l0) continue;
+        int l0, l1;
+        if (!MIXED) {
+            l0 = sg.lab_start[s], l1 = sg.lab_start[s + 1];
+            if (l1 <= l0) continue;
+        } else {  // candidates = labelled points of the query's class (binary_cuda_functions.cu:275)
+            long long e = (long long)s * kCls + (sem[p] - 2);
+            l0 = lab_start18[e], l1 = lab_start18[e + 1];
+            if (l1 <= l0) {  // no labelled point of this class: the label of the LAST labelled point (:287-300)
+                int last = seg_lastlab[s];
+                if (lane == 0 && last >= 0) cluster_id[p] = cluster_id[last];
+                continue;
+            }
+        }
         float px = xo[p], py = yo[p], pz = zo[p];
         int g0 = l0 >> 5, g1 = (l1 - 1) >> 5;
         // first guess: the group where the query itself would sit in the sorted labelled list

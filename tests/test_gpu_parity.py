@@ -21,12 +21,6 @@ def test_golden_reference_vectors(ctx, path):
     """Outputs of the UNMODIFIED compiled reference (tests/golden/make_golden.py) on a B200."""
     d, ref = H.load_golden(path)
     seg = d["seg_counts"]
-    if not H.is_single_class(d["sem"], seg):
-        from pbnet_b200._lib import PBError
-        with pytest.raises(PBError) as e:
-            H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]))
-        assert e.value.code == 6  # PB_ERR_MIXED_CLASS: documented gap, fails loudly
-        return
     got = H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]))
     assert H.diff_report(got, ref) == []
 
@@ -91,6 +85,38 @@ def test_batched_equals_separate_calls(ctx, chunk_points, device):
         so += len(c["seg_counts"])
         ko += k
     assert got["n_clusters"] == ko
+
+
+@pytest.mark.parametrize("seed", [71, 72, 73])
+def test_mixed_class_segments_vs_oracle(ctx, seed):
+    """Segments that mix classes (allowed by the API, never produced by PBNet): class-agnostic connectivity,
+    one cluster per (component, class), per-class min_pts, same-class 1-NN with the reference's fallback."""
+    from oracle import pb_oracle as po
+    from pbnet_b200 import scenes
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sc = scenes.make_scene(seed, 40000)
+    fg = sc["sem"] >= 2
+    xs = (sc["xyz_orig"] + sc["offset"])[fg].astype(np.float32)
+    xo = sc["xyz_orig"][fg]
+    sem = sc["sem"][fg].astype(np.int32)
+    if seed == 73:  # a class with no surviving cluster at all exercises the last-labelled-point fallback
+        sem[rng.random(len(sem)) < 0.02] = 19
+    m18 = H.M18.copy()
+    m18[rng.integers(0, 18, size=6)] = rng.integers(3, 120, size=6)
+    n = len(sem)
+    seg = [n // 3, 0, n - n // 3]
+    want = po.oracle_binary_cluster(xs, xo, sem, seg, H.R18, m18)
+    for device in (False, True):
+        got = H.run_cuda(ctx, xs, xo, sem, seg, min_pts=m18, device=device)
+        assert H.diff_report(got, want) == []
+    assert ctx.counters()["mixed_mode"] == 1
+    # different radii inside one segment are undefined in the reference -> error, not a guess
+    from pbnet_b200._lib import PBError
+    r18 = H.R18.copy()
+    r18[int(sem[0]) - 2] = np.float32(0.05)
+    with pytest.raises(PBError) as e:
+        H.run_cuda(ctx, xs, xo, sem, seg, radius=r18)
+    assert e.value.code == 6
 
 
 def test_edge_cases(ctx):
