@@ -399,14 +399,23 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         cells = max(1, counters["cells"])
-        # algorithmic bytes of ONE k_degree launch: per point 16 B (float4 read) + 4 B (cell
-        # ordinal read) + 4 B (degree write); per occupied cell 200 B (25 stencil rows) + 8 B key + 4 B start
-        deg_bytes = 24.0 * n + 212.0 * cells
-        deg_ms = stage_ms.get("degree", 0.0)
+        chunks = max(1, counters.get("chunks", 1))
+        # algorithmic bytes of k_degree: per point 16 B pts4 + 4 B row_of read, 4 B degree write;
+        # per fine cell 12 B (key, coarse ordinal); per coarse cell 76 B (9 stencil rows + point offset)
+        deg_bytes = (24.0 * n + 12.0 * cells + 76.0 * counters.get("coarse_cells", 0)) / chunks   # per launch
+        traffic = None
+        try:  # dram__bytes_read+write per launch from the committed ncu --set full capture of the same workload
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_k_degree.json")))
+            if world == 1 and abs(prof["points_per_launch"] - n / chunks) < 0.02 * n:
+                traffic = prof["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        deg_ms_total = stage_ms.get("degree", 0.0)               # summed over the chunks of a step
+        deg_ms = deg_ms_total / chunks                           # average launch duration
         achieved = deg_bytes / (deg_ms * 1e-3) / 1e9 if deg_ms > 0 else None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         alu_peak = 148 * 128 * sm_mhz * 1e6 / 8.0  # 8 issue slots per pair test (3 FADD,FMUL,2 FFMA,FSETP,IADD)
-        tests_per_s = counters["pair_tests"] / (deg_ms * 1e-3) if deg_ms > 0 else None
+        tests_per_s = counters["pair_tests"] / (deg_ms_total * 1e-3) if deg_ms_total > 0 else None
         value = total_points / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -428,9 +437,10 @@ def main():
             "launches_per_step": int(launches_per_step),
             "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "k_degree", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "launches_per_step": chunks, "avg_launch_ms": deg_ms, "algorithmic_bytes_per_launch": deg_bytes,
                          "note": "k_degree is fp32-issue bound, not HBM bound: see roofline_alu"},
-            "roofline_alu": {"kernel": "k_degree", "pair_tests_per_launch": counters["pair_tests"],
+            "roofline_alu": {"kernel": "k_degree", "pair_tests_per_step": counters["pair_tests"],
                              "achieved": tests_per_s, "peak": alu_peak, "unit": "pair tests/s",
                              "frac": (tests_per_s / alu_peak) if tests_per_s else None,
                              "peak_def": "148 SM x 128 fp32 lanes x measured SM clock / 8 issue slots per test"},

@@ -111,7 +111,7 @@ const char *pb_stage_name(int i);
 float pb_stage_ms(const pb_ctx *ctx, int i);
 /* counters of the last call: [0] pair tests issued by the degree kernel, [1] sum of degrees,
  * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter,
- * [6] chunks, [7] 1 if the mixed-class kernels were needed */
+ * [6] chunks, [7] 1 if the mixed-class kernels were needed, [8] occupied coarse cells */
 int64_t pb_counter(const pb_ctx *ctx, int i);
 
 /* ------------------------------------------------------------------------------------------------

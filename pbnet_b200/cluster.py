@@ -18,6 +18,17 @@ from ._lib import PBError, lib
 PB_MEM_HOST, PB_MEM_DEVICE = 0, 1
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the explicit handle of the default stream (a NULL stream argument
+#                         means "the context's own stream" in the C ABI)
+
+
+def stream_handle(stream) -> int:
+    """cudaStream_t value for the C ABI from a torch stream / raw handle; torch's default stream (handle 0)
+    maps to cudaStreamLegacy so the call is ordered with the tensors' producers and consumers."""
+    h = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    return h if h else CUDA_STREAM_LEGACY
+
+
 def _addr(a):
     if a is None:
         return None
@@ -81,7 +92,7 @@ class Context:
         return {self._lib.pb_stage_name(i).decode(): float(self._lib.pb_stage_ms(self._h, i)) for i in range(n)}
 
     def counters(self) -> dict:
-        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode"]
+        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode", "coarse_cells"]
         return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------------------------------------
@@ -140,9 +151,8 @@ class Context:
             clt_sem = new(cap, torch.int32, np.int32, pinned)
         nclt = ctypes.c_int64(0)
         kind = PB_MEM_DEVICE if on_device else PB_MEM_HOST
-        sptr = None
-        if stream is not None:
-            sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        sptr = stream_handle(stream) if stream is not None else (stream_handle(torch.cuda.current_stream(x.device))
+                                                                 if on_device else None)
         if call_seg_counts is None:
             call_clusters = None
             rc = self._lib.pb_binary_cluster(

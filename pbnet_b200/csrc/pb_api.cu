@@ -54,7 +54,7 @@ struct pb_ctx {
     bool profiling = false;
     cudaEvent_t ev[ST_COUNT + 1] = {};
     float stage_ms[ST_COUNT] = {};
-    int64_t counters[8] = {};
+    int64_t counters[16] = {};
     // pinned scratch for scalars read back at the end of a call
     int *h_scalars = nullptr;  // [0] err bits [1] C [2] R [3] K [4] Q [5] L
     unsigned long long *h_counters = nullptr;
@@ -148,7 +148,7 @@ extern "C" void pb_set_chunk_points(pb_ctx *ctx, int64_t points) {
 extern "C" int pb_stage_count(void) { return ST_COUNT; }
 extern "C" const char *pb_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 extern "C" float pb_stage_ms(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < ST_COUNT) ? ctx->stage_ms[i] : 0.f; }
-extern "C" int64_t pb_counter(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < 8) ? ctx->counters[i] : 0; }
+extern "C" int64_t pb_counter(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < 16) ? ctx->counters[i] : 0; }
 
 // ------------------------------------------------------------------------------------------------
 namespace {
@@ -666,6 +666,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     if (prof) {
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
         for (int i = 0; i < 7; i++) ctx->counters[i] = 0;
+        ctx->counters[8] = 0;
         for (int gi = 0; gi < G; gi++) {
             cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
             for (int i = 0; i < ST_COUNT; i++) {
@@ -681,6 +682,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ctx->counters[3] += hs[4];
             ctx->counters[4] += hs[1];
             ctx->counters[5] += hs[2];
+            ctx->counters[8] += hs[6];
         }
         ctx->counters[6] = G;
     }

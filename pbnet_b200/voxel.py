@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ._lib import PBError, lib
-from .cluster import PB_MEM_DEVICE, PB_MEM_HOST, default_context
+from .cluster import PB_MEM_DEVICE, PB_MEM_HOST, default_context, stream_handle
 
 
 def _bind():
@@ -83,7 +83,7 @@ def voxel_map(coordinates, quantization_size=None, batch=None) -> VoxelMap:
     if batch is not None:
         b = torch.as_tensor(batch).to(device=dev, dtype=torch.int32).contiguous()
     nv = ctypes.c_int64(0)
-    sptr = torch.cuda.current_stream(dev).cuda_stream if c.is_cuda else None
+    sptr = stream_handle(torch.cuda.current_stream(dev)) if c.is_cuda else None
     rc = L.pb_voxelize(ctx._h, c.data_ptr(), int(c.dtype == torch.float64), stride, int(stride == 4 and b is None),
                        b.data_ptr() if b is not None else None, n,
                        float(quantization_size) if quantization_size else 0.0, vcoords.data_ptr(), index.data_ptr(),
@@ -104,7 +104,7 @@ def voxel_rows(rows: torch.Tensor, vm: VoxelMap, mode: str = "pick") -> torch.Te
     V = vm.n_voxels
     out = torch.empty((V, C), dtype=torch.float32, device=rows.device)
     kind = PB_MEM_DEVICE if rows.is_cuda else PB_MEM_HOST
-    sptr = torch.cuda.current_stream(rows.device).cuda_stream if rows.is_cuda else None
+    sptr = stream_handle(torch.cuda.current_stream(rows.device)) if rows.is_cuda else None
     order, vstart = vm.order.to(rows.device), vm.vox_start.to(rows.device)
     rc = L.pb_voxel_rows(ctx._h, rows.data_ptr(), n, C, order.data_ptr(), vstart.data_ptr(), V,
                          {"pick": 0, "mean": 1, "sum": 2}[mode], out.data_ptr(), kind, sptr)
@@ -121,7 +121,7 @@ def devoxelize_raw(vfeat: torch.Tensor, inverse: torch.Tensor) -> torch.Tensor:
     ctx = _ctx_for(vfeat)
     out = torch.empty((n, C), dtype=torch.float32, device=vfeat.device)
     kind = PB_MEM_DEVICE if vfeat.is_cuda else PB_MEM_HOST
-    sptr = torch.cuda.current_stream(vfeat.device).cuda_stream if vfeat.is_cuda else None
+    sptr = stream_handle(torch.cuda.current_stream(vfeat.device)) if vfeat.is_cuda else None
     rc = L.pb_devoxelize(ctx._h, vfeat.data_ptr(), V, C, inverse.data_ptr(), n, out.data_ptr(), kind, sptr)
     _check(ctx, rc)
     return out
