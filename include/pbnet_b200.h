@@ -103,6 +103,12 @@ int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const
  * Results do not depend on the chunking. */
 void pb_set_chunk_points(pb_ctx *ctx, int64_t points);
 
+/* Device self-test of the centre kernel's division (k_centres replays the reference's running mean
+ * M += (x - M) / n, lib/PB_lib/src/pbnet/binary_cuda_functions.cu:237-239, with a reciprocal-based
+ * correctly rounded quotient): compares it bit for bit with div.rn.f32 on n_samples pseudo-random and
+ * adversarial (dividend, count) pairs and returns the number of mismatches (expected 0). */
+int pb_selftest_division(pb_ctx *ctx, int64_t n_samples, int64_t seed, int64_t *mismatches);
+
 /* Optional per-stage device timings (ms, CUDA events) of the last call when enabled; stage names via
  * pb_stage_name.  Off by default (events add launch overhead). */
 void pb_set_profiling(pb_ctx *ctx, int on);

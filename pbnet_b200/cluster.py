@@ -83,6 +83,14 @@ class Context:
         """Chunk size (points) of the two-stream pipelining of large batched calls; 0 = automatic."""
         self._lib.pb_set_chunk_points(self._h, int(points))
 
+    def selftest_division(self, n_samples: int = 1 << 28, seed: int = 0) -> int:
+        """Mismatches between k_centres' reciprocal-based quotient and div.rn.f32 (expected 0)."""
+        bad = ctypes.c_int64(-1)
+        rc = self._lib.pb_selftest_division(self._h, int(n_samples), int(seed), ctypes.byref(bad))
+        if rc != 0:
+            raise PBError(rc, self._lib.pb_last_error(self._h).decode())
+        return int(bad.value)
+
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.pb_last_launch_count(self._h))

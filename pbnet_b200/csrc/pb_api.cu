@@ -145,6 +145,20 @@ extern "C" void pb_set_profiling(pb_ctx *ctx, int on) {
 extern "C" void pb_set_chunk_points(pb_ctx *ctx, int64_t points) {
     if (ctx) ctx->chunk_points = points;
 }
+extern "C" int pb_selftest_division(pb_ctx *ctx, int64_t n_samples, int64_t seed, int64_t *mismatches) {
+    if (!ctx || !mismatches || n_samples < 0) return PB_ERR_ARG;
+    PB_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    PB_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    PB_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+    pb::k_selftest_division<<<148 * 8, 256, 0, ctx->stream>>>((unsigned long long)n_samples, (unsigned long long)seed, d);
+    unsigned long long h = 0;
+    PB_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PB_CUDA(cudaFree(d));
+    *mismatches = (int64_t)h;
+    return PB_OK;
+}
 extern "C" int pb_stage_count(void) { return ST_COUNT; }
 extern "C" const char *pb_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 extern "C" float pb_stage_ms(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < ST_COUNT) ? ctx->stage_ms[i] : 0.f; }
@@ -435,7 +449,8 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         L++;
     }
     mark();  // CENTRES
-    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out);
+    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
+                                                            w.d_scalars + 9);
     L++;
     mark();  // D2H
     PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));

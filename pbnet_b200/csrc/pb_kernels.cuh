@@ -1071,50 +1071,125 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
 
 // ------------------------------------------------------------------------------------------------
 // K21  cluster centres (binary_cuda_functions.cu:217-246): sequential running mean in ascending
-//      point order, M += (x - M) / n with IEEE division — replayed exactly.  One warp per cluster:
-//      the warp streams its segment, compacts the member coordinates into a shared-memory buffer and
-//      lanes 0,1,2 then run the x, y, z recurrences side by side (one instruction stream for all
-//      three chains).
+//      point order, M += (x - M) / n with IEEE fp32 division — replayed exactly.  One warp per cluster
+//      (clusters are handed out through an atomic counter, so a warp that drew a small cluster takes the
+//      next one): the warp streams its segment, compacts the member coordinates into a shared-memory
+//      buffer and lanes 0,1,2 then run the x, y, z recurrences side by side (one instruction stream for
+//      all three chains).  The kernel is bound by the latency of that chain for the largest cluster.
+//      A warp issues in order, so every instruction of div.rn.f32 (MUFU.RCP, Newton steps, range check:
+//      ~240 cycles per member measured) sits on that chain.  div_by_count() keeps only what depends on
+//      the running mean on it: with y = RN(1/n) prepared by the other lanes (__frcp_rn),
+//          q0 = a*y;  r0 = fma(-n,q0,a);  q1 = fma(r0,y,q0);  r1 = fma(-n,q1,a);  q2 = fma(r1,y,q1)
+//      q1 is a faithful quotient, hence r1 is exact and q2 = RN(a/n) (Markstein's theorem; its one
+//      exception, an all-ones divisor significand, is n = 2^24-1, which takes the plain division, as do
+//      dividends outside [1e-30, 1e30]).  pb_selftest_division compares it with div.rn.f32 on the device.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCtrWarps = 4;
 constexpr int kCtrBuf = 256;  // buffered members per warp (3 floats each)
 
+__device__ __forceinline__ float div_by_count(float a, float fn, float y) {
+    float aa = fabsf(a);
+    if (!(aa > 1e-30f && aa < 1e30f)) return __fdiv_rn(a, fn);
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-fn, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-fn, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
+// device self-test: div_by_count vs div.rn.f32 on pseudo-random and adversarial (dividend, count) pairs
+__global__ void k_selftest_division(unsigned long long n_samples, unsigned long long seed,
+                                    unsigned long long *__restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long h = (i + seed) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32; h *= 0x94D049BB133111EBULL; h ^= h >> 29;
+        unsigned lo = (unsigned)h, hi = (unsigned)(h >> 32);
+        int n = 1 + (int)(hi % ((1u << 24) - 2));            // 1 .. 2^24-2
+        if ((i & 7) == 1) n = 1 + (int)(hi % 4096u);         // small counts dominate real clusters
+        float fn = (float)n;
+        float a;
+        unsigned mant = lo & 0x7fffffu, sign = lo & 0x80000000u;
+        int e = 127 - 40 + (int)((lo >> 23) % 60u);          // magnitudes 2^-40 .. 2^19
+        a = __uint_as_float(sign | ((unsigned)e << 23) | mant);
+        if ((i & 3) == 2) {                                  // adversarial: quotient next to a float / a midpoint
+            float m = __uint_as_float(((unsigned)(127 - 20 + (int)(hi % 30u)) << 23) | mant);
+            a = __fmul_rn(m, fn);
+            if (i & 4) a = __uint_as_float(__float_as_uint(a) + ((lo >> 30) & 1u ? 1u : 0xffffffffu));
+        }
+        float want = __fdiv_rn(a, fn);
+        float got = div_by_count(a, fn, __frcp_rn(fn));
+        bad += __float_as_uint(want) != __float_as_uint(got);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 __global__ void __launch_bounds__(kCtrWarps * 32)
 k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
           const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
-          const float *__restrict__ z, float *__restrict__ center) {
-    __shared__ float buf[kCtrWarps][3][kCtrBuf + 32];
+          const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster) {
+    __shared__ float buf[kCtrWarps][3][kCtrBuf + 128];
+    __shared__ float rcp[kCtrWarps][kCtrBuf + 128];
     int K = *d_K;
     int lane = lane_id(), wid = threadIdx.x >> 5;
-    int warps = (gridDim.x * blockDim.x) >> 5;
-    float(*mybuf)[kCtrBuf + 32] = buf[wid];
+    float(*mybuf)[kCtrBuf + 128] = buf[wid];
+    float *myrcp = rcp[wid];
     int coord = lane < 3 ? lane : 0;
-    for (int kk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; kk < K; kk += warps) {
+    while (true) {
+        int kk = 0;
+        if (lane == 0) kk = atomicAdd(next_cluster, 1);
+        kk = __shfl_sync(kFull, kk, 0);
+        if (kk >= K) break;
         int s = clt_seg[kk];
         int local = kk - sg.id_base[s];
         int b = sg.start[s], e = sg.start[s + 1];
         float M = 0.f;  // lane c < 3 carries coordinate c
         int cnt = 0;
         int fill = 0;
-        for (int ub = b; ub < e; ub += 32) {
-            int u = ub + lane;
-            bool hit = (u < e) && (cluster_id[u] == local);
-            unsigned m = __ballot_sync(kFull, hit);
-            if (hit) {
-                int o = fill + __popc(m & ((1u << lane) - 1));
-                mybuf[0][o] = x[u];
-                mybuf[1][o] = y[u];
-                mybuf[2][o] = z[u];
+        for (int ub = b; ub < e; ub += 128) {
+            // 128 points per trip, all 16 loads in flight together (the scan is pure memory latency)
+            int id[4];
+            float vx[4], vy[4], vz[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int u = ub + 32 * j + lane;
+                bool ok = u < e;
+                id[j] = ok ? cluster_id[u] : -2;
+                vx[j] = ok ? x[u] : 0.f;
+                vy[j] = ok ? y[u] : 0.f;
+                vz[j] = ok ? z[u] : 0.f;
             }
-            fill += __popc(m);
-            if (fill >= kCtrBuf || ub + 32 >= e) {  // flush: lanes 0..2 replay the recurrence in order
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                bool hit = id[j] == local;
+                unsigned m = __ballot_sync(kFull, hit);
+                if (hit) {
+                    int o = fill + __popc(m & ((1u << lane) - 1));
+                    mybuf[0][o] = vx[j];
+                    mybuf[1][o] = vy[j];
+                    mybuf[2][o] = vz[j];
+                }
+                fill += __popc(m);
+            }
+            if (fill >= kCtrBuf || ub + 128 >= e) {  // flush: lanes 0..2 replay the recurrence in order
+                for (int t = lane; t < fill; t += 32) myrcp[t] = __frcp_rn((float)(cnt + t + 1));
                 __syncwarp();
                 const float *src = mybuf[coord];
+                if (cnt + fill < (1 << 24) - 1) {
 #pragma unroll 4
-                for (int t = 0; t < fill; t++) {
-                    float v = src[t];
-                    cnt++;
-                    M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
+                    for (int t = 0; t < fill; t++) {
+                        float v = src[t];
+                        float y = myrcp[t];
+                        cnt++;
+                        M = __fadd_rn(M, div_by_count(__fsub_rn(v, M), (float)cnt, y));
+                    }
+                } else {
+                    for (int t = 0; t < fill; t++) {
+                        float v = src[t];
+                        cnt++;
+                        M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
+                    }
                 }
                 fill = 0;
                 __syncwarp();

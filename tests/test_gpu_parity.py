@@ -119,6 +119,13 @@ def test_mixed_class_segments_vs_oracle(ctx, seed):
     assert e.value.code == 6
 
 
+def test_centre_division_is_exact(ctx):
+    """k_centres' quotient (reciprocal + 2 FMA corrections, Markstein) == div.rn.f32, bit for bit, on 2^30
+    pseudo-random + adversarial (dividend, count) pairs."""
+    assert ctx.selftest_division(1 << 30, seed=12345) == 0
+    assert ctx.selftest_division(1 << 26, seed=7) == 0
+
+
 def test_edge_cases(ctx):
     from oracle import pb_oracle as po
     from pbnet_b200._lib import PBError
