@@ -367,9 +367,11 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key1, w.key1_alt, w.val, w.order1, n, 0, end_bit, st));
         if (assign_lp) {
             bytes = w.cub_bytes;
-            PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit, st));
+            int end_bit2 = pb::kKey2SegShift + seg_bits + (MIXED ? 5 : 0);
+            PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit2, st));
+            L += 2 + (end_bit2 + 7) / 8;
         }
-        L += assign_lp ? 2 * (2 + (end_bit + 7) / 8) : (2 + (end_bit + 7) / 8);  // histogram + onesweep passes
+        L += 2 + (end_bit + 7) / 8;  // histogram + exclusive sum + onesweep passes
     }
     const uint64_t *skey = w.key1_alt;
 

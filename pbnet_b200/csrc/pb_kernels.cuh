@@ -26,6 +26,9 @@ constexpr int kCoarseBits = kCellBits - 1;     // 13
 constexpr int kCoarseMax = (1 << kCoarseBits) - 1;
 constexpr int kSegShift = 3 * kCellBits;       // 42: key = seg<<42 | cz'<<29 | cy'<<16 | cx'<<3 | fine bits
 constexpr int kRowShift = 3 + kCoarseBits;     // 16: key >> 16 identifies (seg, cz', cy') = one coarse row
+constexpr int kMortonBits = 9;                 // LP-assignment order: Morton bits per axis
+constexpr int kMortonMax = (1 << kMortonBits) - 1;
+constexpr int kKey2SegShift = 3 * kMortonBits; // key2 = seg<<27 | morton27  (mixed: seg<<32 | class<<27 | morton27)
 constexpr int kRuns = 9;                       // 3 x 3 coarse stencil rows, each up to 3 coarse cells long
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHpBit = 0x80000000;
@@ -34,9 +37,6 @@ constexpr int kHpBit = 0x80000000;
 #endif
 #ifndef PB_DEG_MINB
 #define PB_DEG_MINB 9
-#endif
-#ifndef PB_DEG_PIPE
-#define PB_DEG_PIPE 0
 #endif
 constexpr int kWindow = PB_WINDOW;             // query points per warp in k_degree (PB_WINDOW/32 per lane)
 
@@ -234,9 +234,9 @@ __global__ void k_seg_params(int n, int S, SegArrays sg, const int *__restrict__
         sg.min_o[3 * s + k] = mo;
         ext = fmaxf(ext, Mo - mo);
     }
-    // LP-assignment sort grid (ordering only, never a correctness filter): 1 cm cells unless the
-    // segment is too large for 14 bits per axis
-    float g = fmaxf(0.01f, ext / 16000.0f);
+    // LP-assignment sort grid (ordering only, never a correctness filter): 512 cells along the longest
+    // axis of the segment's box -> 27 Morton bits, a 5-pass instead of a 7-pass radix sort
+    float g = fmaxf(ext / (float)kMortonMax, 1e-6f);
     sg.inv_g[s] = 1.0f / g;
 }
 
@@ -281,14 +281,14 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
     float ig = sg.inv_g[s];
     float gx = (xo[i] - sg.min_o[3 * s]) * ig, gy = (yo[i] - sg.min_o[3 * s + 1]) * ig,
           gz = (zo[i] - sg.min_o[3 * s + 2]) * ig;
-    uint32_t mx = (uint32_t)min((gx >= 0.f && gx < 1e9f) ? (int)gx : 0, kCellMax);
-    uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kCellMax);
-    uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kCellMax);
+    uint32_t mx = (uint32_t)min((gx >= 0.f && gx < 1e9f) ? (int)gx : 0, kMortonMax);
+    uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kMortonMax);
+    uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kMortonMax);
+    uint64_t mort = spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
     if (!MIXED)
-        key2[i] = ((uint64_t)s << kSegShift) | spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
+        key2[i] = ((uint64_t)s << kKey2SegShift) | mort;
     else
-        key2[i] = ((uint64_t)s << kSegShift) | ((uint64_t)(myc - 2) << 37) | spread3(mx >> 2) | (spread3(my >> 2) << 1) |
-                  (spread3(mz >> 2) << 2);
+        key2[i] = ((uint64_t)s << (kKey2SegShift + 5)) | ((uint64_t)(myc - 2) << kKey2SegShift) | mort;
     val[i] = (uint32_t)i;
 }
 
@@ -424,27 +424,6 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
     for (int k = 0; k < kRuns; k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
         int j = b;
-#if PB_DEG_PIPE
-        if (j + 2 <= e) {  // software pipeline: the next 2 candidates are in flight while 2 are tested
-            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1);
-            j += 2;
-#pragma unroll 1
-            for (; j + 2 <= e; j += 2) {
-                float4 n0 = __ldg(pts4 + j), n1 = __ldg(pts4 + j + 1);
-#pragma unroll
-                for (int s = 0; s < Q; s++) {
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
-                }
-                q0 = n0, q1 = n1;
-            }
-#pragma unroll
-            for (int s = 0; s < Q; s++) {
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
-            }
-        }
-#else
 #pragma unroll 1
         for (; j + 4 <= e; j += 4) {
             float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
@@ -456,7 +435,6 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
                 count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
             }
         }
-#endif
         for (; j < e; j++) {
             float4 q0 = __ldg(pts4 + j);
 #pragma unroll
