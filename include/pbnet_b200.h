@@ -148,6 +148,26 @@ int pb_voxel_rows(pb_ctx *ctx, const float *rows, int64_t n_rows, int C, const i
 int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, const int64_t *inverse, int64_t n, float *out,
                   int mem_kind, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * proposal-vs-instance IoU and mask labels (training-time scoring; device pointers only, asynchronous on
+ * `stream`).  Replace
+ *   void get_iou(at::Tensor x5, int nInstance, int nProposal)                    lib/PB_lib/src/iou/get_iou.h:16,
+ *        bound at lib/PB_lib/src/PB_lib_api.cpp:8, called from lib/PB_lib/torch_io/pbnet_ops.py:101 (PBNet.py:410)
+ *   void cal_iou_and_masklabel(at::Tensor x5, int, int, at::Tensor, at::Tensor, int mode)
+ *        lib/PB_lib/src/cal_iou_and_masklabel/cal_iou_and_masklabel.h, bound at PB_lib_api.cpp:9
+ * proposals_idx i32[sumNPoint], proposals_offset i32[nProposal+1], instance_labels i64[N] (-100 = ignore),
+ * instance_pointnum i32[nInstance]; proposals_iou f32[nProposal*nInstance] (out);
+ * mode 0: IoU of the whole proposal, mode 1: of its points with mask_scores_sigmoid > 0.5;
+ * mask_label f32[sumNPoint] (in/out, caller pre-fills -1): 1/0 where the best IoU exceeds 0.5.
+ */
+int pb_get_iou(pb_ctx *ctx, const int32_t *proposals_idx, const int32_t *proposals_offset,
+               const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
+               int32_t nInstance, int32_t nProposal, void *stream);
+int pb_cal_iou_and_masklabel(pb_ctx *ctx, const int32_t *proposals_idx, const int32_t *proposals_offset,
+                             const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
+                             int32_t nInstance, int32_t nProposal, const float *mask_scores_sigmoid,
+                             float *mask_label, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

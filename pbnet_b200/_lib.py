@@ -15,7 +15,7 @@ ERR_NAMES = {1: "PB_ERR_ARG", 2: "PB_ERR_CUDA", 3: "PB_ERR_SEM_RANGE", 4: "PB_ER
 # every symbol include/pbnet_b200.h declares
 SYMBOLS = ["pb_create", "pb_destroy", "pb_last_error", "pb_last_launch_count", "pb_binary_cluster",
            "pb_binary_cluster_batched", "pb_set_profiling", "pb_stage_count", "pb_stage_name", "pb_stage_ms",
-           "pb_counter", "pb_set_chunk_points", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize"]
+           "pb_counter", "pb_set_chunk_points", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize", "pb_get_iou", "pb_cal_iou_and_masklabel"]
 
 
 class PBError(RuntimeError):
@@ -56,6 +56,10 @@ def lib():
     L.pb_set_chunk_points.restype = None
     L.pb_selftest_division.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     L.pb_selftest_division.restype = ctypes.c_int
+    L.pb_get_iou.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
+    L.pb_get_iou.restype = ctypes.c_int
+    L.pb_cal_iou_and_masklabel.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_int, vp]
+    L.pb_cal_iou_and_masklabel.restype = ctypes.c_int
     L.pb_stage_count.argtypes = []
     L.pb_stage_count.restype = ctypes.c_int
     L.pb_stage_name.argtypes = [ctypes.c_int]

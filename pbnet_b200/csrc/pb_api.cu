@@ -913,3 +913,53 @@ extern "C" int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, 
     if (host_io) PB_CUDA(cudaStreamSynchronize(st));
     return PB_OK;
 }
+
+// =================================================================================================
+// proposal IoU / mask labels — see pb_iou.cuh.  Device pointers only (the reference
+// asserts is_cuda on every argument, lib/PB_lib/torch_io/pbnet_ops.py:91-94,120-124).
+// =================================================================================================
+#include "pb_iou.cuh"
+
+extern "C" int pb_cal_iou_and_masklabel(pb_ctx *ctx, const int32_t *proposals_idx, const int32_t *proposals_offset,
+                                        const int64_t *instance_labels, const int32_t *instance_pointnum,
+                                        float *proposals_iou, int32_t nInstance, int32_t nProposal,
+                                        const float *mask_scores_sigmoid, float *mask_label, int mode, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (nInstance < 0 || nProposal < 0 || (mode != 0 && mode != 1)) return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (nInstance == 0 || nProposal == 0) return PB_OK;
+    if (!proposals_idx || !proposals_offset || !instance_labels || !instance_pointnum || !proposals_iou ||
+        (mode == 1 && !mask_scores_sigmoid))
+        return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    int rc = ensure_arena(ctx, sizeof(int) * (size_t)nProposal + 4096, st);
+    if (rc) return rc;
+    int *ptotal = ctx->arena.get<int>((size_t)nProposal);
+    long long total = (long long)nProposal * nInstance;
+    PB_CUDA(cudaMemsetAsync(proposals_iou, 0, sizeof(float) * (size_t)total, st));
+    PB_CUDA(cudaMemsetAsync(ptotal, 0, sizeof(int) * (size_t)nProposal, st));
+    pbi::k_iou_count<<<std::min(nProposal, 148 * 16), 256, 0, st>>>(nInstance, nProposal, proposals_idx, proposals_offset,
+                                                                    (const long long *)instance_labels, mask_scores_sigmoid,
+                                                                    mode, reinterpret_cast<int *>(proposals_iou), ptotal);
+    pbi::k_iou_finish<<<(int)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(nInstance, total, instance_pointnum,
+                                                                                              ptotal, proposals_iou);
+    ctx->launches = 2;
+    if (mask_label) {
+        pbi::k_mask_label<<<std::min((nProposal + 7) / 8, 148 * 8), 256, 0, st>>>(nInstance, nProposal, proposals_idx,
+                                                                                   proposals_offset,
+                                                                                   (const long long *)instance_labels,
+                                                                                   proposals_iou, mask_label);
+        ctx->launches = 3;
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_get_iou(pb_ctx *ctx, const int32_t *proposals_idx, const int32_t *proposals_offset,
+                          const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
+                          int32_t nInstance, int32_t nProposal, void *stream) {
+    return pb_cal_iou_and_masklabel(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum,
+                                    proposals_iou, nInstance, nProposal, nullptr, nullptr, 0, stream);
+}

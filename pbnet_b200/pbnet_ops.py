@@ -43,3 +43,60 @@ class Cluster(Function):
 
 
 cluster = Cluster.apply
+
+
+def _iou_call(proposals_idx, proposals_offset, instance_labels, instance_pointnum, mask_scores, mask_label, mode):
+    from .cluster import stream_handle
+    from ._lib import PBError
+    dev = proposals_idx.device
+    if dev.type != "cuda":
+        raise TypeError("get_iou / cal_iou_and_masklabel take CUDA tensors (as the reference asserts)")
+    pb = default_context(dev.index)
+    n_inst = int(instance_pointnum.size(0))
+    n_prop = int(proposals_offset.size(0)) - 1
+    iou = torch.zeros((n_prop, n_inst), dtype=torch.float32, device=dev)
+    idx = proposals_idx.to(torch.int32).contiguous()
+    off = proposals_offset.to(torch.int32).contiguous()
+    lab = instance_labels.to(torch.int64).contiguous()
+    pnum = instance_pointnum.to(torch.int32).contiguous()
+    rc = pb._lib.pb_cal_iou_and_masklabel(pb._h, idx.data_ptr(), off.data_ptr(), lab.data_ptr(), pnum.data_ptr(),
+                                          iou.data_ptr(), n_inst, n_prop,
+                                          mask_scores.data_ptr() if mask_scores is not None else None,
+                                          mask_label.data_ptr() if mask_label is not None else None, int(mode),
+                                          stream_handle(torch.cuda.current_stream(dev)))
+    if rc != 0:
+        raise PBError(rc, pb._lib.pb_last_error(pb._h).decode())
+    return iou
+
+
+class GetIoU(Function):
+    """Mirror of pbnet_ops.get_iou (lib/PB_lib/torch_io/pbnet_ops.py:85-111; network/PBNet.py:410)."""
+
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum):
+        return _iou_call(proposals_idx, proposals_offset, instance_labels, instance_pointnum, None, None, 0)
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+get_iou = GetIoU.apply
+
+
+class CalIoUAndMasklabel(Function):
+    """Mirror of pbnet_ops.cal_iou_and_masklabel (lib/PB_lib/torch_io/pbnet_ops.py:114-141)."""
+
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum, mask_scores_sigmoid, mode):
+        ms = mask_scores_sigmoid.to(torch.float32).contiguous()
+        mask_label = torch.full(ms.shape, -1.0, dtype=torch.float32, device=ms.device)
+        iou = _iou_call(proposals_idx, proposals_offset, instance_labels, instance_pointnum, ms, mask_label, mode)
+        return iou, mask_label
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None, None, None
+
+
+cal_iou_and_masklabel = CalIoUAndMasklabel.apply

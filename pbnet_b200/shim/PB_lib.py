@@ -48,6 +48,33 @@ def _not_on_path(name, where):
     return f
 
 
-get_iou = _not_on_path("get_iou", "lib/PB_lib/src/iou/get_iou.cu")
-cal_iou_and_masklabel = _not_on_path("cal_iou_and_masklabel", "lib/PB_lib/src/cal_iou_and_masklabel")
+def _iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, n_inst, n_prop,
+         mask_scores, mask_label, mode):
+    from pbnet_b200._lib import PBError
+    from pbnet_b200.cluster import stream_handle
+    dev = proposals_iou.device
+    pb = default_context(dev.index)
+    rc = pb._lib.pb_cal_iou_and_masklabel(
+        pb._h, proposals_idx.data_ptr(), proposals_offset.data_ptr(), instance_labels.data_ptr(),
+        instance_pointnum.data_ptr(), proposals_iou.data_ptr(), int(n_inst), int(n_prop),
+        mask_scores.data_ptr() if mask_scores is not None else None,
+        mask_label.data_ptr() if mask_label is not None else None, int(mode),
+        stream_handle(torch.cuda.current_stream(dev)))
+    if rc != 0:
+        raise PBError(rc, pb._lib.pb_last_error(pb._h).decode())
+
+
+def get_iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, nInstance, nProposal):
+    """lib/PB_lib/src/iou/get_iou.cpp:9 — int32 / int32 / int64 / int32 CUDA tensors, float output in place."""
+    _iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, nInstance, nProposal,
+         None, None, 0)
+
+
+def cal_iou_and_masklabel(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou,
+                          nInstance, nProposal, mask_scores_sigmoid, mask_label, mode):
+    """lib/PB_lib/src/cal_iou_and_masklabel/cal_iou_and_masklabel.cpp — outputs in place."""
+    _iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, nInstance, nProposal,
+         mask_scores_sigmoid, mask_label, mode)
+
+
 cal_normal_line = _not_on_path("cal_normal_line", "lib/PB_lib/src/normal/cal_normal.cu")

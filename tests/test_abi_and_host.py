@@ -99,7 +99,9 @@ def test_dropin_surfaces_match_reference():
     assert list(inspect.signature(pbnet_ops.Cluster.forward).parameters)[1:] == [
         "ins_offseted", "ins_orig", "sem", "ins_bp", "radius", "min_pts", "batch_size"]
     with pytest.raises(NotImplementedError):
-        PB_lib.get_iou()
+        PB_lib.cal_normal_line()  # dead code in the reference (both call sites commented out)
+    assert len(inspect.signature(PB_lib.get_iou).parameters) == 7
+    assert len(inspect.signature(PB_lib.cal_iou_and_masklabel).parameters) == 10
     ref_ops = "/root/reference/lib/PB_lib/torch_io/pbnet_ops.py"
     if os.path.exists(ref_ops):  # the UNMODIFIED reference wrapper imports against the shim
         import importlib.util
