@@ -178,3 +178,33 @@ def test_dropin_pbnet_ops_surface(ctx):
                               torch.from_numpy(c["sem"]).to(dev), torch.from_numpy(c["seg_counts"]), 0.04, 31, 3)
         for g, w in zip(a, want):
             assert np.array_equal(g.cpu().numpy().view(np.uint32), np.asarray(w).view(np.uint32))
+
+
+def test_fused_class_loop_equals_reference_loop(ctx):
+    """pbnet_b200.grouping.group_instances (row f1) == the per-class loop of network/PBNet.py:151-179 run
+    through pbnet_ops.cluster, class by class."""
+    import torch
+    from pbnet_b200 import grouping, pbnet_ops, scenes
+    sc = scenes.make_scene(81, 60000)
+    copies = 3
+    xyz = np.concatenate(scenes.rotate_copies(sc["xyz_orig"], copies))
+    off = np.concatenate(scenes.rotate_copies(sc["offset"], copies))
+    sem = np.tile(sc["sem"], copies)
+    bh = np.repeat(np.arange(copies), len(sc["sem"]))
+    t = lambda a: torch.from_numpy(a).cuda()
+    X, O, S, B = t(xyz), t(off), t(sem), t(bh)
+    fused = grouping.group_instances(X, O, S, B, 0.04, 31, copies)
+    seen = 0
+    for sem_id in range(2, 20):                      # the reference loop
+        ins_ind = torch.sort(torch.nonzero(S == sem_id).view(-1))[0]
+        if ins_ind.shape[0] < scenes.COUNT_MEAN[sem_id] * 0.05:
+            continue
+        ins_orig, ins_off = X[ins_ind], O[ins_ind]
+        bp = torch.stack([(B[ins_ind] == i).sum() for i in range(copies)]).int()
+        cid, cnum, den, ctr = pbnet_ops.cluster(ins_orig + ins_off, ins_orig, S[ins_ind], bp.cpu(), 0.04, 31, copies)
+        f = fused[seen]
+        assert f["sem_id"] == sem_id and torch.equal(f["ins_ind"], ins_ind)
+        assert torch.equal(f["cluster_id"], cid) and torch.equal(f["cluster_num"], cnum) and torch.equal(f["den_queue"], den)
+        assert torch.equal(f["clt_ctr"].reshape(-1).view(torch.int32), ctr.view(torch.int32))
+        seen += 1
+    assert seen == len(fused) and seen > 5
