@@ -357,34 +357,39 @@ def main():
                   "api": "pbnet_b200.pbnet_ops.cluster per (scene, class), CPU tensors in/out (reference call pattern)",
                   "us_per_call": 1e6 * dt / max(1, len(calls))}
 
-    # ---- voxelize / devoxelize (rows a12-a14): HBM-bound scatter-gather, rank 0 only
+    # ---- voxelize / devoxelize (rows a12-a14): the HBM-bound scatter-gather of the path, rank 0 only
     vox = None
     if rank == 0:
         from pbnet_b200 import voxel
         nv = min(n, 8_000_000)
         coords = torch.stack([d_in[3][:nv], d_in[4][:nv], d_in[5][:nv]], 1).contiguous()  # original xyz
         bcol = torch.zeros(nv, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        vm = voxel.voxel_map(coords, scenes.VOXEL_SIZE, batch=bcol)
-        ev[0].record()
-        vm = voxel.voxel_map(coords, scenes.VOXEL_SIZE, batch=bcol)
-        ev[1].record()
+        peak_v, _ = measured_peaks()
+
+        def timed(f, reps):
+            f()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                r = f()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps * 1e-3, r
+        t_vox, vm = timed(lambda: voxel.voxel_map(coords, scenes.VOXEL_SIZE, batch=bcol), 3)
         C = 76  # 32 + 20 + 20 + 3 + 1 channels gathered at network/PBNet.py:130-134
         vfeat = torch.randn((vm.n_voxels, C), device=dev)
-        o = voxel.devoxelize_raw(vfeat, vm.inverse)
-        ev[2].record()
-        for _ in range(5):
-            o = voxel.devoxelize_raw(vfeat, vm.inverse)
-        ev[3].record()
-        torch.cuda.synchronize()
-        t_vox = ev[0].elapsed_time(ev[1]) * 1e-3
-        t_dev = ev[2].elapsed_time(ev[3]) * 1e-3 / 5
-        gbytes = (nv * C * 4 + vm.n_voxels * C * 4 + nv * 8) / 1e9
-        peak_v, _ = measured_peaks()
+        t_dev, o = timed(lambda: voxel.devoxelize_raw(vfeat, vm.inverse), 5)
+        t_bwd, _ = timed(lambda: voxel.voxel_rows(o, vm, "sum"), 5)
+        gb_f = (nv * C * 4 + vm.n_voxels * C * 4 + nv * 8) / 1e9
+        gb_b = (nv * C * 4 + vm.n_voxels * C * 4 + nv * 4 + vm.n_voxels * 4) / 1e9
         vox = {"points": nv, "voxels": vm.n_voxels, "voxelize_points_per_s": nv / t_vox,
-               "devoxelize": {"channels": C, "ms": t_dev * 1e3, "algorithmic_gb": gbytes, "achieved_gbs": gbytes / t_dev,
-                              "frac_of_hbm_peak": gbytes / t_dev / peak_v}}
+               "devoxelize": {"channels": C, "ms": t_dev * 1e3, "algorithmic_gb": gb_f, "achieved_gbs": gb_f / t_dev,
+                              "frac_of_hbm_copy_peak": gb_f / t_dev / peak_v,
+                              "note": "write-dominated (n*C*4 B written): the copy peak counts read+write, a pure write "
+                                      "stream tops out near half of it"},
+               "devoxelize_backward": {"ms": t_bwd * 1e3, "algorithmic_gb": gb_b, "achieved_gbs": gb_b / t_bwd,
+                                       "frac_of_hbm_copy_peak": gb_b / t_bwd / peak_v}}
         del vfeat, o, coords
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only

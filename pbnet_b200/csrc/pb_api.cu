@@ -864,10 +864,15 @@ extern "C" int pb_voxel_rows(pb_ctx *ctx, const float *rows, int64_t n_rows, int
         d_rows = r, d_out = o, d_order = od, d_vs = vs;
     }
     const int T = 256;
-    const int g = div_up(V * C, T);
-    if (mode == 0) pbv::k_vox_rows<0><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
-    else if (mode == 1) pbv::k_vox_rows<1><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
-    else pbv::k_vox_rows<2><<<g, T, 0, st>>>(d_rows, C, d_order, d_vs, V, d_out);
+    const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rows) | reinterpret_cast<uintptr_t>(d_out)) % 16 == 0);
+    const unsigned width = (unsigned)(vec4 ? C / 4 : C);
+    const unsigned long long total = (unsigned long long)V * width;
+    const int g = (int)std::min<unsigned long long>((total + T - 1) / T, 148ULL * 64);
+#define PB_ROWS(M)                                                                                                   \
+    if (vec4) pbv::k_vox_rows<M, float4><<<g, T, 0, st>>>((const float4 *)d_rows, width, d_order, d_vs, total, (float4 *)d_out); \
+    else pbv::k_vox_rows<M, float><<<g, T, 0, st>>>(d_rows, width, d_order, d_vs, total, d_out);
+    if (mode == 0) { PB_ROWS(0) } else if (mode == 1) { PB_ROWS(1) } else { PB_ROWS(2) }
+#undef PB_ROWS
     ctx->launches = 1;
     if (host_io) PB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)V * C * 4, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaGetLastError());
@@ -901,11 +906,15 @@ extern "C" int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, 
     }
     const int T = 256;
     bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_v) | reinterpret_cast<uintptr_t>(d_out)) % 16 == 0);
-    if (vec4) {
-        int C4 = C / 4;
-        pbv::k_devox<float4><<<div_up(n * C4, T), T, 0, st>>>((const float4 *)d_v, C4, d_inv, n, (float4 *)d_out);
+    const long long width = vec4 ? C / 4 : C;
+    const long long total = n * width;
+    const int grid = (int)std::min<long long>((total + T - 1) / T, 148LL * 64);  // grid-stride, 64 blocks per SM
+    if (total < (1LL << 32)) {
+        if (vec4) pbv::k_devox<float4, uint32_t><<<grid, T, 0, st>>>((const float4 *)d_v, (uint32_t)width, d_inv, (uint32_t)total, (float4 *)d_out);
+        else pbv::k_devox<float, uint32_t><<<grid, T, 0, st>>>(d_v, (uint32_t)width, d_inv, (uint32_t)total, d_out);
     } else {
-        pbv::k_devox<float><<<div_up(n * C, T), T, 0, st>>>(d_v, C, d_inv, n, d_out);
+        if (vec4) pbv::k_devox<float4, unsigned long long><<<grid, T, 0, st>>>((const float4 *)d_v, (unsigned long long)width, d_inv, (unsigned long long)total, (float4 *)d_out);
+        else pbv::k_devox<float, unsigned long long><<<grid, T, 0, st>>>(d_v, (unsigned long long)width, d_inv, (unsigned long long)total, d_out);
     }
     ctx->launches = 1;
     if (host_io) PB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * C * 4, cudaMemcpyDeviceToHost, st));

@@ -97,32 +97,45 @@ __global__ void k_vox_table(const int4 *__restrict__ q, const uint32_t *__restri
 
 // K-V4  per-voxel row reduction over the points of the voxel in ascending point order (deterministic):
 //       MODE 0 = pick the representative, 1 = mean (UNWEIGHTED_AVERAGE), 2 = sum (devoxelize backward)
-template <int MODE>
-__global__ void k_vox_rows(const float *__restrict__ rows, int C, const int *__restrict__ order,
-                           const int *__restrict__ vox_start, long long V, float *__restrict__ out) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= V * C) return;
-    long long v = t / C;
-    int c = (int)(t - v * C);
-    int b = vox_start[v], e = vox_start[v + 1];
-    if (MODE == 0) {
-        out[t] = rows[(long long)order[b] * C + c];
-        return;
+__device__ __forceinline__ float vsum_init(float) { return 0.f; }
+__device__ __forceinline__ float4 vsum_init(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vadd(float &a, float b) { a += b; }
+__device__ __forceinline__ void vadd(float4 &a, float4 b) { a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w; }
+__device__ __forceinline__ float vdiv(float a, float d) { return a / d; }
+__device__ __forceinline__ float4 vdiv(float4 a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+
+template <int MODE, class V4>
+__global__ void __launch_bounds__(256)
+k_vox_rows(const V4 *__restrict__ rows, unsigned C4, const int *__restrict__ order, const int *__restrict__ vox_start,
+           unsigned long long total, V4 *__restrict__ out) {
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        unsigned v = (unsigned)(t / C4);
+        unsigned c = (unsigned)(t - (unsigned long long)v * C4);
+        int b = vox_start[v], e = vox_start[v + 1];
+        if (MODE == 0) {
+            out[t] = __ldg(rows + (long long)order[b] * C4 + c);
+            continue;
+        }
+        V4 s = vsum_init(V4());
+        for (int i = b; i < e; i++) vadd(s, __ldg(rows + (long long)order[i] * C4 + c));
+        out[t] = MODE == 1 ? vdiv(s, (float)(e - b)) : s;
     }
-    float s = 0.f;
-    for (int i = b; i < e; i++) s += rows[(long long)order[i] * C + c];
-    out[t] = MODE == 1 ? s / (float)(e - b) : s;
 }
 
-// K-V5  devoxelize: out[p, :] = vfeat[inverse[p], :]   (network/PBNet.py:130-134,250)
-template <class V4>
-__global__ void k_devox(const V4 *__restrict__ vfeat, int C4, const long long *__restrict__ inverse, long long n,
-                        V4 *__restrict__ out) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * C4) return;
-    long long p = t / C4;
-    int c = (int)(t - p * C4);
-    out[t] = __ldg(vfeat + inverse[p] * C4 + c);
+// K-V5  devoxelize: out[p, :] = vfeat[inverse[p], :]   (network/PBNet.py:130-134,250).  Pure HBM traffic:
+//       n*C*4 B written + the gathered rows read + 8 B/point of `inverse`.  IDX = uint32_t while n*C4 < 2^32
+//       (a 64-bit divide per thread would make the kernel instruction-bound).
+template <class V4, class IDX>
+__global__ void __launch_bounds__(256)
+k_devox(const V4 *__restrict__ vfeat, IDX C4, const long long *__restrict__ inverse, IDX total, V4 *__restrict__ out) {
+    IDX t = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+    IDX stride = (IDX)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        IDX p = t / C4;
+        IDX c = t - p * C4;
+        __stcs(out + t, __ldg(vfeat + inverse[p] * (long long)C4 + c));  // streaming store: the output is write-once
+    }
 }
 
 }  // namespace pbv
