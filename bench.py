@@ -265,11 +265,12 @@ def main():
 
     # gather of proposals to rank 0 (the only collective; NCCL over NVLink) — pbnet_b200/sharding.py
     from pbnet_b200 import sharding
+    gather_ids = sharding.Rank0Gather(n, torch.int32, dev)  # size exchange + padded buffers once, not per step
 
     def step_device():
         out = ctx.binary_cluster(*d_in, seg, r18, m18, 0.05, True, call_seg_counts=csc, stream=stream, **d_out)
         if world > 1:
-            sharding.gather_to_rank0(d_out["cluster_id"])
+            gather_ids(d_out["cluster_id"])
         return out
 
     def barrier():
