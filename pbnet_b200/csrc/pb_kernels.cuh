@@ -1154,15 +1154,35 @@ k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt
                 for (int t = lane; t < fill; t += 32) myrcp[t] = __frcp_rn((float)(cnt + t + 1));
                 __syncwarp();
                 const float *src = mybuf[coord];
-                if (cnt + fill < (1 << 24) - 1) {
+                bool fast = cnt + fill < (1 << 24) - 1;
+                if (fast) {
+                    // branch-free chain (FSUB, FMUL, 4 FFMA, FADD per member); the range guard of div_by_count
+                    // is evaluated off the chain and, if it ever trips, the flush is replayed with div.rn.f32
+                    float M0 = M;
+                    bool odd = false;
 #pragma unroll 4
                     for (int t = 0; t < fill; t++) {
                         float v = src[t];
                         float y = myrcp[t];
-                        cnt++;
-                        M = __fadd_rn(M, div_by_count(__fsub_rn(v, M), (float)cnt, y));
+                        float fn = (float)(cnt + t + 1);
+                        float a = __fsub_rn(v, M);
+                        float q = __fmul_rn(a, y);
+                        float r = __fmaf_rn(-fn, q, a);
+                        q = __fmaf_rn(r, y, q);
+                        r = __fmaf_rn(-fn, q, a);
+                        q = __fmaf_rn(r, y, q);
+                        float aa = fabsf(a);
+                        odd |= !(aa > 1e-30f && aa < 1e30f) && a != 0.f;
+                        M = __fadd_rn(M, q);
                     }
-                } else {
+                    if (odd) {
+                        M = M0;
+                        fast = false;
+                    } else {
+                        cnt += fill;
+                    }
+                }
+                if (!fast) {
                     for (int t = 0; t < fill; t++) {
                         float v = src[t];
                         cnt++;
