@@ -397,7 +397,13 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
 
     mark();  // DEGREE
-    pb::k_degree<<<div_up(n, pb::kWindow * 4), 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+    {
+        // small problems: several warps share one 128-point window and split its candidate stream
+        const int windows = div_up(n, pb::kWindow);
+        const int nslice = std::max(1, std::min(32, (148 * 16) / windows));
+        if (nslice > 1) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
+        pb::k_degree<<<dim3(div_up(n, pb::kWindow * 4), nslice), 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+    }
     L++;
     mark();  // HP
     pb::k_hp_cells<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,

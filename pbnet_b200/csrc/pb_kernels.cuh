@@ -32,13 +32,10 @@ constexpr int kKey2SegShift = 3 * kMortonBits; // key2 = seg<<27 | morton27  (mi
 constexpr int kRuns = 9;                       // 3 x 3 coarse stencil rows, each up to 3 coarse cells long
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHpBit = 0x80000000;
-#ifndef PB_WINDOW
-#define PB_WINDOW 128
-#endif
 #ifndef PB_DEG_MINB
 #define PB_DEG_MINB 9
 #endif
-constexpr int kWindow = PB_WINDOW;             // query points per warp in k_degree (PB_WINDOW/32 per lane)
+constexpr int kWindow = 128;                   // query points per warp in k_degree (4 per lane)
 
 enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8, kErrRadius = 16 };
 constexpr int kCls = 18;  // classes 2..19
@@ -410,7 +407,7 @@ __device__ __forceinline__ void count_le(int &cnt, float d, float r2) {
 
 template <int Q>
 __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, int g0, int total, int lane, float r2,
-                                             int jb, int je, int *__restrict__ deg_sorted) {
+                                             int jb, int je, int *__restrict__ deg_sorted, int slice, int nslice) {
     float px[Q], py[Q], pz[Q];
     int cnt[Q];
 #pragma unroll
@@ -423,33 +420,41 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
 #pragma unroll 1
     for (int k = 0; k < kRuns; k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
-        int j = b;
+        // batches of 4 candidates; with nslice > 1 (small problems) the batches are dealt round-robin to the
+        // nslice warps that share this window, so one long candidate stream is not one warp's latency
 #pragma unroll 1
-        for (; j + 4 <= e; j += 4) {
-            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+        for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
+            if (j + 4 <= e) {
+                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
 #pragma unroll
-            for (int s = 0; s < Q; s++) {
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q2.x, q2.y, q2.z), r2);
-                count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
+                for (int s = 0; s < Q; s++) {
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q2.x, q2.y, q2.z), r2);
+                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
+                }
+            } else {
+                for (int jj = j; jj < e; jj++) {
+                    float4 q0 = __ldg(pts4 + jj);
+#pragma unroll
+                    for (int s = 0; s < Q; s++) count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
+                }
             }
-        }
-        for (; j < e; j++) {
-            float4 q0 = __ldg(pts4 + j);
-#pragma unroll
-            for (int s = 0; s < Q; s++) count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
         }
     }
 #pragma unroll
     for (int s = 0; s < Q; s++) {
         int o = 32 * s + lane;
-        if (o < total) deg_sorted[g0 + o] = cnt[s] - 1;  // binary_cuda_functions.cu:88  ans - 1 (self)
+        if (o < total) {  // binary_cuda_functions.cu:88  ans - 1 (self)
+            if (nslice == 1) deg_sorted[g0 + o] = cnt[s] - 1;
+            else atomicAdd(deg_sorted + g0 + o, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
+        }
     }
 }
 
 __global__ void __launch_bounds__(128, PB_DEG_MINB)
 k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
+    const int slice = blockIdx.y, nslice = gridDim.y;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = lane_id();
     long long base = (long long)warp * kWindow;
@@ -484,23 +489,15 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
                 je = g.cc_pstart[c1];
             }
         }
-        if (n_tests) {
+        if (n_tests && slice == 0) {
             unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
             tests += (unsigned long long)cand * (unsigned)total;
         }
         switch ((total + 31) >> 5) {
-            case 1: degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            case 2: degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            case 3: degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-#if PB_WINDOW > 128
-            case 4: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            case 5: degree_group<5>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            case 6: degree_group<6>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            case 7: degree_group<7>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-            default: degree_group<8>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-#else
-            default: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted); break;
-#endif
+            case 1: degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+            case 2: degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+            case 3: degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+            default: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
         }
         pos = gend;
     }
