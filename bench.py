@@ -420,7 +420,9 @@ def main():
         deg_ms = deg_ms_total / chunks                           # average launch duration
         achieved = deg_bytes / (deg_ms * 1e-3) / 1e9 if deg_ms > 0 else None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        alu_peak = 148 * 128 * sm_mhz * 1e6 / 8.0  # 8 issue slots per pair test (3 FADD,FMUL,2 FFMA,FSETP,IADD)
+        # ceiling of the packed fp32x2 pair test measured with tools/microbench/pipes.cu on this pool's B200
+        # (profiles/microbench_pipes_r01.txt): 0.576 warp-tests/clk/SM, FFMA2-pipe bound (scalar form: 0.5, issue bound)
+        alu_peak = 148 * 32 * 0.576 * sm_mhz * 1e6
         tests_per_s = counters["pair_tests"] / (deg_ms_total * 1e-3) if deg_ms_total > 0 else None
         value = total_points / (ms_step * 1e-3)
         line = {
@@ -449,7 +451,8 @@ def main():
             "roofline_alu": {"kernel": "k_degree", "pair_tests_per_step": counters["pair_tests"],
                              "achieved": tests_per_s, "peak": alu_peak, "unit": "pair tests/s",
                              "frac": (tests_per_s / alu_peak) if tests_per_s else None,
-                             "peak_def": "148 SM x 128 fp32 lanes x measured SM clock / 8 issue slots per test"},
+                             "peak_def": "148 SM x 32 lanes x 0.576 warp-tests/clk/SM (packed fp32x2 pair-test ceiling, "
+                                         "tools/microbench/pipes.cu) x measured SM clock"},
             "io_roofline": {"bytes_per_point": 36, "achieved_gbs": value * 36 / 1e9, "frac_of_hbm": value * 36 / 1e9 / peak},
             "counters": counters,
             "voxel": vox,

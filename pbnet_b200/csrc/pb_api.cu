@@ -185,6 +185,7 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     uint64_t *key1, *key1_alt, *key2, *key2_alt;
     uint32_t *val, *order1, *order2;
     float4 *pts4, *lab4, *box_lo, *box_hi, *box2_lo, *box2_hi;
+    float *sx, *sy, *sz;
     // per fine cell / coarse cell (upper bound N)
     int *fcell_start, *fcell_cc, *cc_pstart, *cc_fstart, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid;
     uint64_t *fcell_key, *cc_key;
@@ -232,6 +233,7 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
     w.key1 = a.get<uint64_t>(N); w.key1_alt = a.get<uint64_t>(N); w.key2 = a.get<uint64_t>(N); w.key2_alt = a.get<uint64_t>(N);
     w.val = a.get<uint32_t>(N); w.order1 = a.get<uint32_t>(N); w.order2 = a.get<uint32_t>(N);
     w.pts4 = a.get<float4>(N); w.lab4 = a.get<float4>(N);
+    w.sx = a.get<float>(N + 2); w.sy = a.get<float>(N + 2); w.sz = a.get<float>(N + 2);
     w.box_lo = a.get<float4>(N / 32 + 2); w.box_hi = a.get<float4>(N / 32 + 2);
     w.box2_lo = a.get<float4>(N / 1024 + 2); w.box2_hi = a.get<float4>(N / 1024 + 2);
     w.fcell_start = a.get<int>(N + 1); w.fcell_cc = a.get<int>(N); w.cc_pstart = a.get<int>(N + 1); w.cc_fstart = a.get<int>(N + 1);
@@ -376,7 +378,7 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     const uint64_t *skey = w.key1_alt;
 
     mark();  // GRID
-    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.head_f, w.head_c, w.head_r);
+    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.sx, w.sy, w.sz, w.head_f, w.head_c, w.head_r);
     L++;
     scan(w.head_f, n, nullptr, w.ex_f, d_F);  // d_F / d_Cc are rewritten by k_cells with the same values
     scan(w.head_c, n, nullptr, w.ex_c, d_Cc);
@@ -392,7 +394,7 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
     L += 3;
     pb::Grid grid;
-    grid.pts4 = w.pts4; grid.fcell_of = w.fcell_of; grid.row_of = w.row_of; grid.fcell_start = w.fcell_start;
+    grid.pts4 = w.pts4; grid.sx = w.sx; grid.sy = w.sy; grid.sz = w.sz; grid.fcell_of = w.fcell_of; grid.row_of = w.row_of; grid.fcell_start = w.fcell_start;
     grid.fcell_key = w.fcell_key; grid.fcell_cc = w.fcell_cc; grid.cc_pstart = w.cc_pstart; grid.cc_fstart = w.cc_fstart;
     grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
 

@@ -35,7 +35,7 @@ constexpr int kHpBit = 0x80000000;
 #ifndef PB_DEG_MINB
 #define PB_DEG_MINB 9
 #endif
-constexpr int kWindow = 128;                   // query points per warp in k_degree (4 per lane)
+constexpr int kWindow = 128;                   // query points per warp in k_degree (2 adjacent pairs per lane)
 
 enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8, kErrRadius = 16 };
 constexpr int kCls = 18;  // classes 2..19
@@ -80,6 +80,7 @@ struct SegArrays {
 
 struct Grid {             // two-level cell table (device pointers)
     const float4 *pts4;
+    const float *sx, *sy, *sz; // [N+2] sorted coordinates as SoA (k_degree loads query PAIRS with one 64-bit load)
     const int *fcell_of;      // [N] fine-cell ordinal of every sorted point
     const int *row_of;        // [N] coarse-row ordinal of every sorted point
     const int *fcell_start;   // [F+1] first sorted point of every fine cell
@@ -292,12 +293,16 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
 // K4  after sort 1: gather coordinates into cell order, flag fine-cell / coarse-cell / row heads
 __global__ void k_gather_heads(int n, const uint64_t *__restrict__ skey, const uint32_t *__restrict__ order,
                                const float *__restrict__ x, const float *__restrict__ y,
-                               const float *__restrict__ z, float4 *__restrict__ pts4, int *__restrict__ head_f,
+                               const float *__restrict__ z, float4 *__restrict__ pts4, float *__restrict__ sx,
+                               float *__restrict__ sy, float *__restrict__ sz, int *__restrict__ head_f,
                                int *__restrict__ head_c, int *__restrict__ head_r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t o = order[i];
-    pts4[i] = make_float4(x[o], y[o], z[o], __int_as_float((int)o));
+    float vx = x[o], vy = y[o], vz = z[o];
+    pts4[i] = make_float4(vx, vy, vz, __int_as_float((int)o));
+    sx[i] = vx, sy[i] = vy, sz[i] = vz;
+    if (i == n - 1) sx[n] = sx[n + 1] = sy[n] = sy[n + 1] = sz[n] = sz[n + 1] = 0.f;  // pad for 64-bit pair loads
     uint64_t k = skey[i], p = i ? skey[i - 1] : ~k;
     head_f[i] = (k != p) ? 1 : 0;
     head_c[i] = ((k >> 3) != (p >> 3)) ? 1 : 0;
@@ -396,26 +401,85 @@ __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const 
 //     One warp owns a window of 128 consecutive sorted points and splits it into groups of points of
 //     the same coarse ROW.  A group shares one candidate stream: the 9 stencil rows widened to
 //     [cx'min-1, cx'max+1] (any superset of the r-ball is valid, the accept test is the exact
-//     predicate).  Every candidate is ONE broadcast 16-B load tested against up to 4 query points per
-//     lane (register tiling: the LSU write-back of a uniform LDG.128 costs 4 cycles/warp, so one load
-//     per 32 tests made the first version LSU-bound at 94 % — profiles/ncu_r01_degree_v1.txt).
+//     predicate).  Every candidate is ONE broadcast 16-B load tested against 4 query points per lane.
+//     History (profiles/): v1, one load per 32 tests, was LSU write-back bound at 94 %; register tiling made
+//     it issue-bound (8 slots per test); v4 uses Blackwell's packed fp32x2 pipe (FADD2/FMUL2/FFMA2): the
+//     two ADJACENT sorted points a lane owns form one 64-bit operand, the candidate coordinate is a
+//     broadcast scalar operand -> 3 FADD2 + FMUL2 + 2 FFMA2 + 2 FSETP + 2 IADD3 per TWO tests (5 slots per
+//     test).  tools/microbench/pipes.cu: the packed pair test tops out at 0.576 warp-tests/clk/SM
+//     (FFMA2-pipe bound) vs 0.5 for the scalar form (issue bound).
 // ------------------------------------------------------------------------------------------------
 // cnt += (d <= r2) as FSETP.LE + predicated IADD3 (nvcc emits FSETP.GTU + 2 IADD3 for the C expression)
 __device__ __forceinline__ void count_le(int &cnt, float d, float r2) {
     asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(d), "f"(r2));
 }
 
-template <int Q>
-__device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, int g0, int total, int lane, float r2,
-                                             int jb, int je, int *__restrict__ deg_sorted, int slice, int nslice) {
-    float px[Q], py[Q], pz[Q];
-    int cnt[Q];
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, IEEE round-to-nearest per element) -----------
+// Two query points share one instruction; the candidate coordinate enters as a broadcast scalar operand
+// (ptxas folds {c,c} into the .F32 operand form).  Per element this is the same rounding sequence as sqd():
+// dx = fl(c - q) = -fl(q - c) exactly, and only squares of the differences are used.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// tests candidate q against the query pairs (P pairs = 2P query points); counts go to cnt[2p], cnt[2p+1]
+template <int P>
+__device__ __forceinline__ void test_candidate(const unsigned long long (&qx)[P], const unsigned long long (&qy)[P],
+                                               const unsigned long long (&qz)[P], float4 q, float r2, int (&cnt)[2 * P]) {
+    unsigned long long cx = pack2(q.x, q.x), cy = pack2(q.y, q.y), cz = pack2(q.z, q.z);
 #pragma unroll
-    for (int s = 0; s < Q; s++) {
-        int o = 32 * s + lane;
-        float4 p = pts4[g0 + (o < total ? o : 0)];
-        px[s] = p.x, py[s] = p.y, pz[s] = p.z;
-        cnt[s] = 0;
+    for (int p = 0; p < P; p++) {
+        unsigned long long dx = sub2(cx, qx[p]), dy = sub2(cy, qy[p]), dz = sub2(cz, qz[p]);
+        unsigned long long d = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        float d0, d1;
+        unpack2(d, d0, d1);
+        count_le(cnt[2 * p], d0, r2);
+        count_le(cnt[2 * p + 1], d1, r2);
+    }
+}
+
+__device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-byte aligned pair of floats
+    unsigned long long v;
+    asm("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// One group of up to 128 query points [g0, g0+total).  Lane l of pair p owns the two ADJACENT sorted points
+// base + 64p + 2l and +1 (base = g0 rounded down to even), fetched with one 64-bit load per coordinate: the
+// loaded register pair is directly the packed operand of FADD2 (no re-packing moves).
+template <int P>
+__device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
+                                             int *__restrict__ deg_sorted, int slice, int nslice) {
+    const float4 *__restrict__ pts4 = g.pts4;
+    const int base = g0 & ~1;
+    unsigned long long qx[P], qy[P], qz[P];
+    int cnt[2 * P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        int i = base + 64 * p + 2 * lane;
+        if (i >= g0 + total) i = base;  // stay inside the arrays; the result is masked below
+        qx[p] = ldg_pair(g.sx + i), qy[p] = ldg_pair(g.sy + i), qz[p] = ldg_pair(g.sz + i);
+        cnt[2 * p] = cnt[2 * p + 1] = 0;
     }
 #pragma unroll 1
     for (int k = 0; k < kRuns; k++) {
@@ -426,28 +490,21 @@ __device__ __forceinline__ void degree_group(const float4 *__restrict__ pts4, in
         for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
             if (j + 4 <= e) {
                 float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-#pragma unroll
-                for (int s = 0; s < Q; s++) {
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q1.x, q1.y, q1.z), r2);
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q2.x, q2.y, q2.z), r2);
-                    count_le(cnt[s], sqd(px[s], py[s], pz[s], q3.x, q3.y, q3.z), r2);
-                }
+                test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q3, r2, cnt);
             } else {
-                for (int jj = j; jj < e; jj++) {
-                    float4 q0 = __ldg(pts4 + jj);
-#pragma unroll
-                    for (int s = 0; s < Q; s++) count_le(cnt[s], sqd(px[s], py[s], pz[s], q0.x, q0.y, q0.z), r2);
-                }
+                for (int jj = j; jj < e; jj++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
             }
         }
     }
 #pragma unroll
-    for (int s = 0; s < Q; s++) {
-        int o = 32 * s + lane;
-        if (o < total) {  // binary_cuda_functions.cu:88  ans - 1 (self)
-            if (nslice == 1) deg_sorted[g0 + o] = cnt[s] - 1;
-            else atomicAdd(deg_sorted + g0 + o, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
+    for (int s = 0; s < 2 * P; s++) {
+        int i = base + 64 * (s >> 1) + 2 * lane + (s & 1);
+        if (i >= g0 && i < g0 + total) {  // binary_cuda_functions.cu:88  ans - 1 (self)
+            if (nslice == 1) deg_sorted[i] = cnt[s] - 1;
+            else atomicAdd(deg_sorted + i, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
         }
     }
 }
@@ -493,11 +550,10 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
             unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
             tests += (unsigned long long)cand * (unsigned)total;
         }
-        switch ((total + 31) >> 5) {
-            case 1: degree_group<1>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
-            case 2: degree_group<2>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
-            case 3: degree_group<3>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
-            default: degree_group<4>(g.pts4, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+        switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
+            case 1: degree_group<1>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+            case 2: degree_group<2>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+            default: degree_group<3>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
         }
         pos = gend;
     }

@@ -1,0 +1,172 @@
+// Pipe-rate microbenchmark for the k_degree instruction mix on sm_100a:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu && ./pipes
+// Each kernel runs ILP independent dependency chains per thread; reports warp-instructions per cycle per SM.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITERS 4096
+template <int MODE>
+__global__ void k(float *out, float a, float b, unsigned long long *cyc) {
+    float x[8], y[8];
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 0.001f + i, y[i] = a + i;
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(a), "f"(b));          // FFMA 3 distinct regs
+            if (MODE == 1) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(a));                        // FADD
+            if (MODE == 2) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(a));                        // FMUL
+            if (MODE == 3) asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(x[i]) : "f"(y[i]));                 // FFMA d = y*y + d
+            if (MODE == 4) {  // packed: two fp32 FMAs per instruction
+                unsigned long long p, q = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(b);
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x[i]), "f"(y[i]));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p) : "l"(q));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x[i]), "=f"(y[i]) : "l"(p));
+            }
+        }
+    }
+    unsigned long long t1 = clock64();
+    float s = 0;
+    for (int i = 0; i < 8; i++) s += x[i] + y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// packed chain kept in 64-bit registers (no repacking)
+__global__ void k_packed(float *out, float a, float b, unsigned long long *cyc) {
+    unsigned long long p[8], q = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(b);
+    for (int i = 0; i < 8; i++) p[i] = ((unsigned long long)__float_as_uint(threadIdx.x * 0.001f + i) << 32) | __float_as_uint(a + i);
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p[i]) : "l"(q));
+    }
+    unsigned long long t1 = clock64();
+    unsigned long long s = 0;
+    for (int i = 0; i < 8; i++) s ^= p[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((unsigned)s);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// the k_degree test itself: 3 FADD, FMUL, 2 FFMA, FSETP, predicated IADD on 8 independent (query,candidate) pairs
+__global__ void k_test(float *out, float a, float b, unsigned long long *cyc) {
+    float qx[8], cx = a, cy = b, cz = a + b;
+    int cnt[8];
+    for (int i = 0; i < 8; i++) qx[i] = threadIdx.x * 0.001f + i, cnt[i] = 0;
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float dx = __fsub_rn(qx[i], cx), dy = __fsub_rn(qx[i], cy), dz = __fsub_rn(qx[i], cz);
+            float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d), "f"(b));
+        }
+        cx += 1e-7f;
+    }
+    unsigned long long t1 = clock64();
+    int s = 0;
+    for (int i = 0; i < 8; i++) s += cnt[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// packed variant of the pair test: two candidates (cx0,cx1) per instruction against a duplicated query
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__global__ void k_test2(float *out, float a, float b, unsigned long long *cyc) {
+    unsigned long long qq[8];      // query coordinate duplicated in both halves
+    int cnt[8];
+    for (int i = 0; i < 8; i++) qq[i] = pk(threadIdx.x * 0.001f + i, threadIdx.x * 0.001f + i), cnt[i] = 0;
+    unsigned long long cx = pk(a, a + 0.01f), cy = pk(b, b + 0.01f), cz = pk(a + b, a - b);
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned long long dx, dy, dz, d;
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(qq[i]), "l"(cx));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(qq[i]), "l"(cy));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(qq[i]), "l"(cz));
+            asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(dy));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dx));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dz));
+            float d0, d1;
+            asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d0), "f"(b));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d1), "f"(b));
+        }
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(cy));
+    }
+    unsigned long long t1 = clock64();
+    int s = 0;
+    for (int i = 0; i < 8; i++) s += cnt[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// variant: sign bits of (r2 - d) shifted into a mask with one funnel shift per test, POPC at the end
+__global__ void k_test3(float *out, float a, float b, unsigned long long *cyc) {
+    unsigned long long qq[8];
+    unsigned mask[8];
+    for (int i = 0; i < 8; i++) qq[i] = pk(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f + i), mask[i] = 0;
+    unsigned long long cx = pk(a, a), cy = pk(b, b), cz = pk(a + b, a + b), rr = pk(b, b);
+    int cnt = 0;
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned long long dx, dy, dz, d;
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(cx), "l"(qq[i]));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(cy), "l"(qq[i]));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(cz), "l"(qq[i]));
+            asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(dy));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dx));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dz));
+            asm volatile("sub.rn.f32x2 %0, %1, %0;" : "+l"(d) : "l"(rr));
+            unsigned t0b, t1b;
+            asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(t0b), "=r"(t1b) : "l"(d));
+            asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(mask[i]) : "r"(t0b));
+            asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(mask[i]) : "r"(t1b));
+        }
+        if ((it & 15) == 15) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) cnt += 32 - __popc(mask[i]), mask[i] = 0;
+        }
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(cy));
+    }
+    unsigned long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)cnt;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+int main() {
+    float *out;
+    unsigned long long *cyc, h;
+    cudaMalloc(&out, 148 * 1024 * 4 * sizeof(float));
+    cudaMalloc(&cyc, 8);
+    const char *names[] = {"FFMA x=x*a+b", "FADD", "FMUL", "FFMA x=y*y+x", "FFMA2 with repack (3 instr)"};
+    for (int warps = 4; warps <= 32; warps *= 2) {
+        int threads = warps * 32;  // per SM (one block per SM)
+        printf("--- %d warps per SM\n", warps);
+#define RUN(MODE) k<MODE><<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("%-30s %.3f warp-instr/cycle/SM\n", names[MODE], (double)ITERS * 8 * warps * (MODE == 4 ? 3 : 1) / h);
+        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
+        k_packed<<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-30s %.3f warp-instr/cycle/SM  (= %.3f fp32 FMA-lanes x32 /cycle)\n", "FFMA2 (64-bit regs)", (double)ITERS * 8 * warps / h, 2.0 * ITERS * 8 * warps / h);
+        k_test<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-30s %.3f warp-tests/cycle/SM  (8 instr each -> %.3f instr/cycle/SM)\n", "k_degree pair test", (double)ITERS * 8 * warps / h, 8.0 * ITERS * 8 * warps / h);
+        k_test2<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-30s %.3f warp-tests/cycle/SM  (packed f32x2, 5 instr per test)\n", "pair test, f32x2", (double)ITERS * 16 * warps / h);
+        k_test3<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-30s %.3f warp-tests/cycle/SM  (packed + sign-bit funnel shift, 4.5 instr per test)\n", "pair test, f32x2+SHF", (double)ITERS * 16 * warps / h);
+    }
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
