@@ -171,36 +171,60 @@ __global__ void k_prep_points(int n, int S, SegArrays sg, const float *__restric
             e |= kErrNonFinite;
         if (e) atomicOr(err, e);
     }
+    // bounding boxes: reduce in the warp, then in the block when the whole block lies in one segment (the usual
+    // case: 9 atomics per 256 points instead of per 32 — the kernel is bound by same-address atomics otherwise)
+    __shared__ unsigned sh[9][8];
+    __shared__ int sh_seg[8];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
     unsigned act = __ballot_sync(kFull, valid);
+    unsigned e[9];
+    e[0] = enc_f(vx), e[1] = enc_f(vy), e[2] = enc_f(vz), e[3] = enc_f(ox), e[4] = enc_f(oy), e[5] = enc_f(oz);
+    e[6] = e[3], e[7] = e[4], e[8] = e[5];
+    bool uniform = false;
+    int s0 = 0;
+    if (valid) {  // only the lanes named in `act` may take part in the *_sync calls
+        s0 = __shfl_sync(act, s, __ffs(act) - 1);
+        uniform = __all_sync(act, s == s0);
+    }
+    if (valid && uniform) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) e[k] = __reduce_min_sync(act, e[k]);
+#pragma unroll
+        for (int k = 6; k < 9; k++) e[k] = __reduce_max_sync(act, e[k]);
+    }
+    int first = act ? __ffs(act) - 1 : 0;
+    if (lane == first) {
+        sh_seg[wid] = (valid && uniform) ? s0 : -1 - wid;  // distinct negative tags never compare equal
+        if (valid && uniform)
+            for (int k = 0; k < 9; k++) sh[k][wid] = e[k];
+    }
+    __syncthreads();
+    bool block_uniform = true;
+    for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) block_uniform &= sh_seg[w2] == sh_seg[0];
+    block_uniform &= sh_seg[0] >= 0;
+    if (block_uniform) {
+        if (threadIdx.x < 9) {
+            int k = threadIdx.x;
+            unsigned v = sh[k][0];
+            for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) v = k < 6 ? min(v, sh[k][w2]) : max(v, sh[k][w2]);
+            int sb = sh_seg[0];
+            if (k < 3) atomicMin(sg.enc_min_s + 3 * sb + k, v);
+            else if (k < 6) atomicMin(sg.enc_min_o + 3 * sb + (k - 3), v);
+            else atomicMax(sg.enc_max_o + 3 * sb + (k - 6), v);
+        }
+        return;
+    }
     if (!valid) return;
-    int s0 = __shfl_sync(act, s, __ffs(act) - 1);
-    bool uniform = __all_sync(act, s == s0);
-    unsigned e0 = enc_f(vx), e1 = enc_f(vy), e2 = enc_f(vz), e3 = enc_f(ox), e4 = enc_f(oy), e5 = enc_f(oz);
     if (uniform) {
-        unsigned m0 = __reduce_min_sync(act, e0), m1 = __reduce_min_sync(act, e1), m2 = __reduce_min_sync(act, e2);
-        unsigned m3 = __reduce_min_sync(act, e3), m4 = __reduce_min_sync(act, e4), m5 = __reduce_min_sync(act, e5);
-        unsigned M3 = __reduce_max_sync(act, e3), M4 = __reduce_max_sync(act, e4), M5 = __reduce_max_sync(act, e5);
-        if (lane_id() == __ffs(act) - 1) {
-            atomicMin(sg.enc_min_s + 3 * s, m0);
-            atomicMin(sg.enc_min_s + 3 * s + 1, m1);
-            atomicMin(sg.enc_min_s + 3 * s + 2, m2);
-            atomicMin(sg.enc_min_o + 3 * s, m3);
-            atomicMin(sg.enc_min_o + 3 * s + 1, m4);
-            atomicMin(sg.enc_min_o + 3 * s + 2, m5);
-            atomicMax(sg.enc_max_o + 3 * s, M3);
-            atomicMax(sg.enc_max_o + 3 * s + 1, M4);
-            atomicMax(sg.enc_max_o + 3 * s + 2, M5);
+        if (lane == first) {
+            for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_s + 3 * s + k, e[k]);
+            for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_o + 3 * s + k, e[3 + k]);
+            for (int k = 0; k < 3; k++) atomicMax(sg.enc_max_o + 3 * s + k, e[6 + k]);
         }
     } else {
-        atomicMin(sg.enc_min_s + 3 * s, e0);
-        atomicMin(sg.enc_min_s + 3 * s + 1, e1);
-        atomicMin(sg.enc_min_s + 3 * s + 2, e2);
-        atomicMin(sg.enc_min_o + 3 * s, e3);
-        atomicMin(sg.enc_min_o + 3 * s + 1, e4);
-        atomicMin(sg.enc_min_o + 3 * s + 2, e5);
-        atomicMax(sg.enc_max_o + 3 * s, e3);
-        atomicMax(sg.enc_max_o + 3 * s + 1, e4);
-        atomicMax(sg.enc_max_o + 3 * s + 2, e5);
+        for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_s + 3 * s + k, e[k]);
+        for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_o + 3 * s + k, e[3 + k]);
+        for (int k = 0; k < 3; k++) atomicMax(sg.enc_max_o + 3 * s + k, e[6 + k]);
     }
 }
 

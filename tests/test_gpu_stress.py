@@ -69,7 +69,7 @@ def test_full_size_properties(ctx):
     no unlabelled point in a segment that has clusters, idempotence of a second run."""
     from pbnet_b200 import scenes, workload
     sizes = scenes.scene_sizes(24)
-    w = workload.build(range(24), sizes, 1, cache_dir=None)
+    w = workload.build(range(24), sizes, 1, workers=1, cache_dir=None)  # no fork() once CUDA is initialised
     args = (np.stack([w["x"], w["y"], w["z"]], 1), np.stack([w["xo"], w["yo"], w["zo"]], 1), w["sem"], w["seg_counts"])
     a = H.run_cuda(ctx, *args, call_seg_counts=w["call_seg_counts"], device=True)
     b = H.run_cuda(ctx, *args, call_seg_counts=w["call_seg_counts"], device=True)
