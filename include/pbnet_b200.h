@@ -168,6 +168,39 @@ int pb_cal_iou_and_masklabel(pb_ctx *ctx, const int32_t *proposals_idx, const in
                              int32_t nInstance, int32_t nProposal, const float *mask_scores_sigmoid,
                              float *mask_label, int mode, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "local scene" proposal lists and get_proposal (device pointers only; the device-resident continuation of
+ * pb_binary_cluster_batched).  Replace the Python loops of
+ *   network/PBNet.py:180-234   per cluster: member list (torch.nonzero over the segment), cdist/topk of the centres,
+ *                              members of the para_k nearest clusters appended with weights peak_v[k] for clusters
+ *                              larger than count_mean[sem]*0.2; training: torch.mode of the instance labels, -100 skip,
+ *                              ground-truth mask
+ *   network/PBNet.py:317-346   get_proposal: mask score threshold, renumbering of the non-empty proposals
+ *
+ * pb_local_scenes_plan   cluster_id i32[n_pts] / cluster_num i32[n_seg] / center f32[3*n_clusters] exactly as written by
+ *                        pb_binary_cluster_batched on the device (ids restart in every call); seg_counts, call_seg_counts,
+ *                        call_sem (class of every call), big_thresh20 (= fp32(count_mean[c]*0.2)), k_max20 are HOST tables;
+ *                        ins_label i64[n_pts] (device, or NULL = inference).  Returns the number of proposals and of list
+ *                        entries (one host synchronisation) and keeps the plan in the context workspace.
+ * pb_local_scenes_fill   must directly follow _plan: writes prop_offsets i64[P+1], prop_cluster i32[P] (global cluster
+ *                        index, optional), prop_index i64[E] (position of the listed point in the n_pts input, or
+ *                        point_map[position] when point_map i64[n_pts] is given), prop_dpn f32[E] (weights), prop_gt
+ *                        i32[E] (training: 1 / 0 / -1, optional), prop_id i32[E] (proposal of every entry, optional).
+ * pb_get_proposal        prop_offsets i64[P+1], point_idx i64[E], mask_score f32[E] -> proposals_idx i64[<=E][2],
+ *                        proposals_offset i64[<=P+1], cluster_id_v i64[<=P], proposals_ms f32[<=E] (capacities E / P+1 / P);
+ *                        returns the kept entry count and the number of non-empty proposals.
+ */
+int pb_local_scenes_plan(pb_ctx *ctx, const int32_t *cluster_id, const int32_t *seg_counts, int32_t n_seg,
+                         const int32_t *call_seg_counts, const int32_t *call_sem, int32_t n_calls, int64_t n_pts,
+                         const int32_t *cluster_num, const float *center, int64_t n_clusters, const float *big_thresh20,
+                         const int32_t *k_max20, const int64_t *ins_label, int64_t *n_proposals_out, int64_t *n_entries_out,
+                         void *stream);
+int pb_local_scenes_fill(pb_ctx *ctx, const int64_t *point_map, int64_t *prop_offsets, int32_t *prop_cluster,
+                         int64_t *prop_index, float *prop_dpn, int32_t *prop_gt, int32_t *prop_id, void *stream);
+int pb_get_proposal(pb_ctx *ctx, const int64_t *prop_offsets, int64_t n_proposals, const int64_t *point_idx,
+                    const float *mask_score, int64_t n_entries, float thd, int64_t *proposals_idx, int64_t *proposals_offset,
+                    int64_t *cluster_id_v, float *proposals_ms, int64_t *n_kept_out, int64_t *n_nonempty_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

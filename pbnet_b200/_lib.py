@@ -15,7 +15,8 @@ ERR_NAMES = {1: "PB_ERR_ARG", 2: "PB_ERR_CUDA", 3: "PB_ERR_SEM_RANGE", 4: "PB_ER
 # every symbol include/pbnet_b200.h declares
 SYMBOLS = ["pb_create", "pb_destroy", "pb_last_error", "pb_last_launch_count", "pb_binary_cluster",
            "pb_binary_cluster_batched", "pb_set_profiling", "pb_stage_count", "pb_stage_name", "pb_stage_ms",
-           "pb_counter", "pb_set_chunk_points", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize", "pb_get_iou", "pb_cal_iou_and_masklabel"]
+           "pb_counter", "pb_set_chunk_points", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize", "pb_get_iou", "pb_cal_iou_and_masklabel",
+           "pb_local_scenes_plan", "pb_local_scenes_fill", "pb_get_proposal"]
 
 
 class PBError(RuntimeError):
@@ -60,6 +61,14 @@ def lib():
     L.pb_get_iou.restype = ctypes.c_int
     L.pb_cal_iou_and_masklabel.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_int, vp]
     L.pb_cal_iou_and_masklabel.restype = ctypes.c_int
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    L.pb_local_scenes_plan.argtypes = [vp, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, ctypes.c_int64, vp, vp, ctypes.c_int64,
+                                       vp, vp, vp, i64p, i64p, vp]
+    L.pb_local_scenes_plan.restype = ctypes.c_int
+    L.pb_local_scenes_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pb_local_scenes_fill.restype = ctypes.c_int
+    L.pb_get_proposal.argtypes = [vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_float, vp, vp, vp, vp, i64p, i64p, vp]
+    L.pb_get_proposal.restype = ctypes.c_int
     L.pb_stage_count.argtypes = []
     L.pb_stage_count.restype = ctypes.c_int
     L.pb_stage_name.argtypes = [ctypes.c_int]

@@ -254,8 +254,10 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+static void invalidate_scene_state();  // the arena is about to be reused (pb_local_scenes_plan keeps pointers into it)
 namespace {
 int ensure_arena(pb_ctx *ctx, size_t need, cudaStream_t st) {
+    invalidate_scene_state();
     if (need > ctx->arena.cap) {
         PB_CUDA(cudaStreamSynchronize(st));
         if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
@@ -979,4 +981,227 @@ extern "C" int pb_get_iou(pb_ctx *ctx, const int32_t *proposals_idx, const int32
                           int32_t nInstance, int32_t nProposal, void *stream) {
     return pb_cal_iou_and_masklabel(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum,
                                     proposals_iou, nInstance, nProposal, nullptr, nullptr, 0, stream);
+}
+
+// =================================================================================================
+// local scenes + get_proposal (network/PBNet.py:180-234, 317-346) — see pb_scenes.cuh.
+// Device pointers only (this is the device-resident continuation of pb_binary_cluster_batched).
+// =================================================================================================
+#include "pb_scenes.cuh"
+
+struct pb_scene_state {  // device pointers into the context arena, valid from _plan until the next call on the context
+    bool ready = false;
+    const pb_ctx *owner = nullptr;
+    int K = 0, n = 0, train = 0;
+    int64_t P = 0, E = 0;
+    int *d_scal = nullptr;  // [0] err [1] P [2] E [3] total members
+    int *para = nullptr, *nb = nullptr, *size = nullptr, *mstart = nullptr, *mode = nullptr, *prop_cluster = nullptr;
+    long long *prop_offsets = nullptr;
+    uint32_t *members = nullptr;
+    const long long *label = nullptr;
+};
+static thread_local pb_scene_state g_scene;  // one context per host thread (pb_create)
+static void invalidate_scene_state() { g_scene.ready = false; }
+
+extern "C" int pb_local_scenes_plan(pb_ctx *ctx, const int32_t *cluster_id, const int32_t *seg_counts, int32_t n_seg,
+                                    const int32_t *call_seg_counts, const int32_t *call_sem, int32_t n_calls, int64_t n_pts,
+                                    const int32_t *cluster_num, const float *center, int64_t n_clusters,
+                                    const float *big_thresh20, const int32_t *k_max20, const int64_t *ins_label,
+                                    int64_t *n_proposals_out, int64_t *n_entries_out, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    g_scene.ready = false;
+    if (n_seg < 0 || n_calls < 0 || n_pts < 0 || n_clusters < 0 || !n_proposals_out || !n_entries_out || !big_thresh20 || !k_max20 ||
+        (n_seg > 0 && (!seg_counts || !cluster_num)) || (n_calls > 0 && (!call_seg_counts || !call_sem)))
+        return fail(ctx, PB_ERR_ARG, "null / negative argument");
+    *n_proposals_out = 0, *n_entries_out = 0;
+    int kmax_all = 0;
+    for (int c = 0; c < 20; c++) {
+        if (k_max20[c] < 0 || k_max20[c] > pbs::kMaxK) return fail(ctx, PB_ERR_ARG, "K_max must be in [0, 16]");
+        kmax_all = std::max(kmax_all, (int)k_max20[c]);
+    }
+    if (n_pts * (1 + (int64_t)kmax_all) >= ((int64_t)1 << 31)) return fail(ctx, PB_ERR_ARG, "n_pts * (1 + K_max) must be below 2^31");
+    const int S = n_seg, n = (int)n_pts, K = (int)n_clusters;
+    std::vector<int> h_start(S + 1, 0), h_first(S, 0), h_sem(S, 2);
+    {
+        int s = 0;
+        for (int c = 0; c < n_calls; c++) {
+            if (call_seg_counts[c] < 0 || s + call_seg_counts[c] > S) return fail(ctx, PB_ERR_ARG, "bad call_seg_counts");
+            if (call_sem[c] < 0 || call_sem[c] > 19) return fail(ctx, PB_ERR_SEM_RANGE, "call_sem outside [0,19]");
+            for (int k = 0; k < call_seg_counts[c]; k++) h_first[s + k] = s, h_sem[s + k] = call_sem[c];
+            s += call_seg_counts[c];
+        }
+        if (s != S) return fail(ctx, PB_ERR_ARG, "sum(call_seg_counts) != n_seg");
+        for (int i = 0; i < S; i++) {
+            if (seg_counts[i] < 0 || (int64_t)h_start[i] + seg_counts[i] > n_pts) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+            h_start[i + 1] = h_start[i] + seg_counts[i];
+        }
+        if ((S ? h_start[S] : 0) != n) return fail(ctx, PB_ERR_ARG, "sum(seg_counts) != n_pts");
+    }
+    if (K == 0 || n == 0) {
+        g_scene = pb_scene_state();
+        g_scene.ready = true, g_scene.owner = ctx;
+        return PB_OK;
+    }
+    if (!cluster_id || !center) return fail(ctx, PB_ERR_ARG, "null data pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const bool train = ins_label != nullptr;
+    const size_t N = (size_t)n;
+    int64_t &L = ctx->launches;
+    pb_scene_state stt;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        int *d_start = a.get<int>(S + 1), *d_first = a.get<int>(S), *d_sem = a.get<int>(S), *gstart = a.get<int>(S + 2);
+        float *d_thr = a.get<float>(20);
+        int *d_kmax = a.get<int>(20);
+        int *d_scal = a.get<int>(16);
+        uint32_t *key = a.get<uint32_t>(N), *key_alt = a.get<uint32_t>(N), *val = a.get<uint32_t>(N), *members = a.get<uint32_t>(N);
+        int *size = a.get<int>((size_t)K + 1), *mstart = a.get<int>((size_t)K + 2), *cseg = a.get<int>(K);
+        int *para = a.get<int>(K), *nb = a.get<int>((size_t)K * pbs::kMaxK), *len = a.get<int>(K), *valid = a.get<int>(K);
+        int *mode = a.get<int>(K), *pidx = a.get<int>((size_t)K + 1), *off_g = a.get<int>((size_t)K + 1), *prop_cluster = a.get<int>(K);
+        long long *prop_offsets = a.get<long long>((size_t)K + 1);
+        unsigned long long *best = a.get<unsigned long long>(K);
+        uint64_t *lkey = train ? a.get<uint64_t>(N) : nullptr, *lkey_alt = train ? a.get<uint64_t>(N) : nullptr;
+        int *blocks = a.get<int>(std::max(N, (size_t)K) / pb::kScanTile + 2);
+        size_t cub_bytes = 0, cub64 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32);
+        if (train) cub::DeviceRadixSort::SortKeys(nullptr, cub64, (const uint64_t *)nullptr, (uint64_t *)nullptr, n, 0, 64);
+        cub_bytes = std::max(cub_bytes, cub64);
+        void *cub_tmp = a.get<char>(cub_bytes);
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+            continue;
+        }
+        const int T = 256;
+        PB_CUDA(cudaMemcpyAsync(d_start, h_start.data(), sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(d_first, h_first.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(d_sem, h_sem.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(d_thr, big_thresh20, sizeof(float) * 20, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(d_kmax, k_max20, sizeof(int) * 20, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemsetAsync(d_scal, 0, sizeof(int) * 16, st));
+        PB_CUDA(cudaMemsetAsync(size, 0, sizeof(int) * ((size_t)K + 1), st));
+        PB_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)K, st));
+        // global cluster index of the first cluster of every segment; its total must be n_clusters
+        launch_scan(st, cluster_num, S, nullptr, gstart, d_scal + 4, blocks, L);
+        PB_CUDA(cudaMemcpyAsync(gstart + S, d_scal + 4, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        pbs::k_point_keys<<<div_up(n, T), T, 0, st>>>(n, S, d_start, d_first, gstart, cluster_id, K, key, val, size, d_scal);
+        pbs::k_cluster_seg<<<div_up(S, T), T, 0, st>>>(S, gstart, cseg);
+        int bits = 1;
+        while ((1 << bits) <= K) bits++;
+        size_t cb = cub_bytes;
+        PB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, key, key_alt, val, members, n, 0, bits, st));
+        L += 2 + 2 + (bits + 7) / 8;
+        launch_scan(st, size, K + 1, nullptr, mstart, d_scal + 3, blocks, L);
+        if (train) {
+            pbs::k_label_keys<<<div_up(n, T), T, 0, st>>>(n, key, (const long long *)ins_label, K, lkey, d_scal);
+            cb = cub_bytes;
+            PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, lkey, lkey_alt, n, 0, 32 + bits, st));
+            pbs::k_label_mode<<<div_up(n, T), T, 0, st>>>(n, lkey_alt, K, best);
+            L += 2 + 2 + (32 + bits + 7) / 8;
+        }
+        pbs::k_cluster_plan<<<div_up(K, 128), 128, 0, st>>>(K, cseg, gstart, d_sem, center, size, d_thr, d_kmax, best, train ? 1 : 0,
+                                                            para, nb, len, valid, mode);
+        L++;
+        launch_scan(st, valid, K, nullptr, pidx, d_scal + 1, blocks, L);
+        launch_scan(st, len, K, nullptr, off_g, d_scal + 2, blocks, L);
+        pbs::k_proposals<<<div_up(K, T), T, 0, st>>>(K, valid, pidx, off_g, d_scal + 2, d_scal + 1, prop_offsets, prop_cluster);
+        L++;
+        PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_scal, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->h_scalars[0] & pbs::kErrId) return fail(ctx, PB_ERR_ARG, "a cluster id lies outside the id range of its segment (cluster_num / call tables do not match cluster_id)");
+        if (ctx->h_scalars[0] & pbs::kErrLabel) return fail(ctx, PB_ERR_ARG, "instance label outside the int32 range");
+        if (ctx->h_scalars[4] != K) return fail(ctx, PB_ERR_ARG, "sum(cluster_num) != n_clusters");
+        stt.K = K, stt.n = n, stt.train = train ? 1 : 0, stt.P = ctx->h_scalars[1], stt.E = ctx->h_scalars[2];
+        stt.d_scal = d_scal, stt.para = para, stt.nb = nb, stt.size = size, stt.mstart = mstart, stt.mode = mode;
+        stt.prop_cluster = prop_cluster, stt.prop_offsets = prop_offsets, stt.members = members;
+        stt.label = (const long long *)ins_label;
+        stt.ready = true, stt.owner = ctx;
+    }
+    g_scene = stt;
+    *n_proposals_out = stt.P;
+    *n_entries_out = stt.E;
+    return PB_OK;
+}
+
+extern "C" int pb_local_scenes_fill(pb_ctx *ctx, const int64_t *point_map, int64_t *prop_offsets, int32_t *prop_cluster,
+                                    int64_t *prop_index, float *prop_dpn, int32_t *prop_gt, int32_t *prop_id, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    const pb_scene_state &s = g_scene;
+    if (!s.ready || s.owner != ctx) return fail(ctx, PB_ERR_ARG, "pb_local_scenes_fill must directly follow a successful pb_local_scenes_plan on this thread");
+    if (!prop_offsets) return fail(ctx, PB_ERR_ARG, "null prop_offsets");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (s.P == 0) {
+        PB_CUDA(cudaMemsetAsync(prop_offsets, 0, sizeof(int64_t), st));
+        return PB_OK;
+    }
+    if (!prop_index || !prop_dpn || (prop_gt && !s.train)) return fail(ctx, PB_ERR_ARG, "null output / prop_gt without instance labels");
+    PB_CUDA(cudaMemcpyAsync(prop_offsets, s.prop_offsets, sizeof(int64_t) * (size_t)(s.P + 1), cudaMemcpyDeviceToDevice, st));
+    if (prop_cluster) PB_CUDA(cudaMemcpyAsync(prop_cluster, s.prop_cluster, sizeof(int) * (size_t)s.P, cudaMemcpyDeviceToDevice, st));
+    if (s.E > 0) {
+        const int T = 256;
+        int grid = (int)std::min<int64_t>((s.E + T - 1) / T, 148 * 16);
+        pbs::k_fill<<<grid, T, 0, st>>>(s.d_scal + 2, s.d_scal + 1, s.prop_offsets, s.prop_cluster, s.para, s.nb, s.size, s.mstart,
+                                        s.members, (const long long *)point_map, s.label, s.mode, (long long *)prop_index, prop_dpn,
+                                        prop_gt, prop_id);
+        ctx->launches = 1;
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_get_proposal(pb_ctx *ctx, const int64_t *prop_offsets, int64_t n_proposals, const int64_t *point_idx,
+                               const float *mask_score, int64_t n_entries, float thd, int64_t *proposals_idx,
+                               int64_t *proposals_offset, int64_t *cluster_id_v, float *proposals_ms, int64_t *n_kept_out,
+                               int64_t *n_nonempty_out, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_proposals < 0 || n_entries < 0 || !n_kept_out || !n_nonempty_out || n_entries >= ((int64_t)1 << 31) ||
+        n_proposals >= ((int64_t)1 << 31))
+        return fail(ctx, PB_ERR_ARG, "bad argument");
+    *n_kept_out = 0, *n_nonempty_out = 0;
+    if (!proposals_offset) return fail(ctx, PB_ERR_ARG, "null proposals_offset");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (n_proposals == 0 || n_entries == 0) {
+        PB_CUDA(cudaMemsetAsync(proposals_offset, 0, sizeof(int64_t), st));
+        return PB_OK;
+    }
+    if (!prop_offsets || !point_idx || !mask_score || !proposals_idx || !cluster_id_v || !proposals_ms)
+        return fail(ctx, PB_ERR_ARG, "null pointer");
+    const int E = (int)n_entries, P = (int)n_proposals;
+    int64_t &L = ctx->launches;
+    size_t need = sizeof(int) * ((size_t)2 * E + (size_t)3 * P + (size_t)std::max(E, P) / pb::kScanTile + 64) + 8192;
+    int rc = ensure_arena(ctx, need, st);
+    if (rc) return rc;
+    Arena &a = ctx->arena;
+    int *flag = a.get<int>(E), *kpos = a.get<int>(E), *nonempty = a.get<int>(P), *newid = a.get<int>(P), *kstart = a.get<int>(P);
+    int *d_scal = a.get<int>(16);
+    int *blocks = a.get<int>((size_t)std::max(E, P) / pb::kScanTile + 2);
+    const int T = 256;
+    pbs::k_score_flags<<<div_up(E, T), T, 0, st>>>(E, mask_score, thd, flag);
+    launch_scan(st, flag, E, nullptr, kpos, d_scal, blocks, L);
+    pbs::k_prop_counts<<<div_up(P, T), T, 0, st>>>(P, E, (const long long *)prop_offsets, kpos, d_scal, nonempty, kstart);
+    launch_scan(st, nonempty, P, nullptr, newid, d_scal + 1, blocks, L);
+    pbs::k_prop_write<<<div_up(P, T), T, 0, st>>>(P, nonempty, newid, kstart, d_scal, d_scal + 1, (long long *)proposals_offset,
+                                                  (long long *)cluster_id_v);
+    pbs::k_prop_entries<<<div_up(E, T), T, 0, st>>>(E, flag, kpos, (const long long *)prop_offsets, P, newid,
+                                                    (const long long *)point_idx, mask_score, (long long *)proposals_idx, proposals_ms);
+    L += 4;
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_scal, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    *n_kept_out = ctx->h_scalars[0];
+    *n_nonempty_out = ctx->h_scalars[1];
+    return PB_OK;
 }
