@@ -200,6 +200,11 @@ int pb_local_scenes_fill(pb_ctx *ctx, const int64_t *point_map, int64_t *prop_of
 int pb_get_proposal(pb_ctx *ctx, const int64_t *prop_offsets, int64_t n_proposals, const int64_t *point_idx,
                     const float *mask_score, int64_t n_entries, float thd, int64_t *proposals_idx, int64_t *proposals_offset,
                     int64_t *cluster_id_v, float *proposals_ms, int64_t *n_kept_out, int64_t *n_nonempty_out, void *stream);
+/* Feature rows of the proposal lists (network/PBNet.py:195,231 torch.cat of gathered rows): out f32[E][C+2] =
+ * [ point_feat[index[e]] (C channels) | sem_score[index[e]][prop_sem[prop_id[e]]] | dpn[e] ].  Device pointers, asynchronous. */
+int pb_scene_features(pb_ctx *ctx, const float *point_feat, int32_t C, const float *sem_score, int32_t n_cls,
+                      const int64_t *index, const int32_t *prop_id, const int32_t *prop_sem, const float *dpn,
+                      int64_t n_entries, float *out, void *stream);
 
 #ifdef __cplusplus
 }

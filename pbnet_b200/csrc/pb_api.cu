@@ -1205,3 +1205,22 @@ extern "C" int pb_get_proposal(pb_ctx *ctx, const int64_t *prop_offsets, int64_t
     *n_nonempty_out = ctx->h_scalars[1];
     return PB_OK;
 }
+
+extern "C" int pb_scene_features(pb_ctx *ctx, const float *point_feat, int32_t C, const float *sem_score, int32_t n_cls,
+                                 const int64_t *index, const int32_t *prop_id, const int32_t *prop_sem, const float *dpn,
+                                 int64_t n_entries, float *out, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_entries < 0 || C < 1 || n_cls < 1) return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (n_entries == 0) return PB_OK;
+    if (!point_feat || !sem_score || !index || !prop_id || !prop_sem || !dpn || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const int T = 256;
+    int grid = (int)std::min<int64_t>((n_entries * 32 + T - 1) / T, 148 * 32);
+    pbs::k_scene_feat<<<grid, T, 0, st>>>(n_entries, C, n_cls, point_feat, sem_score, (const long long *)index, prop_id, prop_sem, dpn, out);
+    ctx->launches = 1;
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}

@@ -190,6 +190,23 @@ __global__ void k_fill(const int *__restrict__ d_E, const int *__restrict__ d_P,
     }
 }
 
+// list_feat rows (PBNet.py:195,231): [ point_feat[idx] (C channels) | softmax score of the proposal's class | weight ]
+// one warp per entry: the C-channel row is read and written as coalesced 128-B segments
+__global__ void k_scene_feat(long long E, int C, int n_cls, const float *__restrict__ feat, const float *__restrict__ score,
+                             const long long *__restrict__ index, const int *__restrict__ prop_id,
+                             const int *__restrict__ prop_sem, const float *__restrict__ dpn, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < E; e += warps) {
+        const long long i = index[e];
+        const float *__restrict__ src = feat + i * C;
+        float *__restrict__ dst = out + e * (C + 2);
+        for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
+        if (lane == 0) dst[C] = __ldg(score + i * n_cls + prop_sem[prop_id[e]]);
+        if (lane == 1) dst[C + 1] = dpn[e];
+    }
+}
+
 // ---- get_proposal (PBNet.py:317-346) ------------------------------------------------------------------------
 __global__ void k_score_flags(int E, const float *__restrict__ score, float thd, int *__restrict__ flag) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;

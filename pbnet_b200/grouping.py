@@ -171,3 +171,57 @@ def get_proposal(offsets: torch.Tensor, index: torch.Tensor, mask_score: torch.T
         raise PBError(rc, L.pb_last_error(ctx._h).decode())
     M, P2 = int(M.value), int(P2.value)
     return pidx[:M], poff[:P2 + 1], ids[:P2], pms[:M]
+
+
+def scene_features(point_feat: torch.Tensor, sem_score: torch.Tensor, index: torch.Tensor, proposal: torch.Tensor,
+                   proposal_sem: torch.Tensor, dpn: torch.Tensor) -> torch.Tensor:
+    """``list_feat`` of network/PBNet.py:195,231 in one gather: rows ``[point_feat[i] | sem_score[i, class of the proposal] |
+    dpn]`` for every list entry (``index``/``proposal``/``dpn`` from ``build_local_scenes(..., want_proposal_id=True)``;
+    ``proposal_sem`` i32[P] = class of every proposal)."""
+    dev = point_feat.device
+    ctx = default_context(dev.index)
+    L = ctx._lib
+    pf = point_feat.to(torch.float32).contiguous()
+    sc = sem_score.to(torch.float32).contiguous()
+    ps = proposal_sem.to(device=dev, dtype=torch.int32).contiguous()
+    E, C = int(index.shape[0]), int(pf.shape[1])
+    out = torch.empty((E, C + 2), dtype=torch.float32, device=dev)
+    rc = L.pb_scene_features(ctx._h, pf.data_ptr(), C, sc.data_ptr(), int(sc.shape[1]), index.data_ptr(), proposal.data_ptr(),
+                             ps.data_ptr(), dpn.data_ptr(), E, out.data_ptr(), stream_handle(torch.cuda.current_stream(dev)))
+    if rc != 0:
+        raise PBError(rc, L.pb_last_error(ctx._h).decode())
+    return out
+
+
+def propose(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem_pred_p: torch.Tensor, batch_head_p: torch.Tensor,
+            point_feat_p: torch.Tensor, sem_score_sfp: torch.Tensor, radius: float, min_pts: int, cluster_batch: int,
+            ins_label: torch.Tensor | None = None, voxel_size: float = 0.02, k_max=K_MAX, count_mean=COUNT_MEAN):
+    """The whole cluster stage of ``PBNet.forward`` up to the second sparse tensor (network/PBNet.py:144-247) on the device:
+    grouping of all classes (one batched call), local-scene lists, feature rows and the voxelization of the proposals.
+
+    Returns dict(groups, scenes, features f32[E,C+2], voxel_features, voxel_coords i32[V,4], voxel_map) where
+    ``voxel_map.inverse`` is ``inputs_v2.inverse_mapping`` (:247) and ``scenes['index']`` is ``cat(list_ins_idx)``."""
+    from . import voxel
+    groups = group_instances(xyz_original, offset_pred_p, sem_pred_p, batch_head_p, radius, min_pts, cluster_batch, count_mean)
+    if not groups:
+        return dict(groups=[], scenes=None, features=None, voxel_features=None, voxel_coords=None, voxel_map=None)
+    cid = torch.cat([g["cluster_id"] for g in groups])
+    cnum = torch.cat([g["cluster_num"] for g in groups])
+    ctr = torch.cat([g["clt_ctr"].reshape(-1) for g in groups])
+    pmap = torch.cat([g["ins_ind"] for g in groups])
+    seg = np.concatenate([g["seg_counts"] for g in groups])
+    csem = np.array([g["sem_id"] for g in groups], np.int32)
+    calls = np.full(len(groups), cluster_batch, np.int32)
+    lab = ins_label[pmap].contiguous() if ins_label is not None else None   # ins_ins_label = ins_label[ins_ind] (:163)
+    sc = build_local_scenes(cid, cnum, ctr, seg, calls, csem, point_map=pmap, ins_label=lab, k_max=k_max,
+                            count_mean=count_mean, want_proposal_id=True)
+    # class of every proposal: clusters are numbered call-major, so the class follows from the per-call cluster counts
+    per_call = torch.stack([g["cluster_num"].sum() for g in groups]).to(torch.int64)
+    cl_sem = torch.repeat_interleave(torch.as_tensor(csem, device=cid.device), per_call)
+    prop_sem = cl_sem[sc["cluster"].to(torch.int64)]
+    feats = scene_features(point_feat_p, sem_score_sfp, sc["index"], sc["proposal"], prop_sem, sc["dpn"])
+    coords = xyz_original[sc["index"]].to(torch.float32) / voxel_size       # :236 sem_xyz / 0.02
+    vm = voxel.voxel_map(coords, None, batch=sc["proposal"])
+    vfeat = voxel.voxel_rows(feats, vm, "pick")
+    return dict(groups=groups, scenes=sc, proposal_sem=prop_sem, features=feats, voxel_features=vfeat, voxel_coords=vm.vcoords,
+                voxel_map=vm)

@@ -94,3 +94,31 @@ def test_local_scenes_empty():
     out = grouping.build_local_scenes(cid, torch.zeros(1, dtype=torch.int32).cuda(), torch.zeros(0, dtype=torch.float32).cuda(),
                                       [10], [1], [4])
     assert out["offsets"].cpu().tolist() == [0] and out["index"].numel() == 0
+
+
+def test_propose_chain_matches_piecewise_torch():
+    """grouping.propose (network/PBNet.py:144-247 on the device) vs the same steps spelled out with torch indexing."""
+    import torch
+    from pbnet_b200 import grouping, scenes
+    sc = scenes.make_scene(777, 80_000)
+    copies = 3
+    xyz = _dev(np.concatenate(scenes.rotate_copies(sc["xyz_orig"], copies)))
+    off = _dev(np.concatenate(scenes.rotate_copies(sc["offset"], copies)))
+    sem = _dev(np.tile(sc["sem"], copies))
+    bh = _dev(np.repeat(np.arange(copies), sc["sem"].shape[0]).astype(np.int32))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feat = torch.rand((xyz.shape[0], 32), device="cuda", generator=g)
+    sfp = torch.softmax(torch.rand((xyz.shape[0], 20), device="cuda", generator=g), dim=1)
+    out = grouping.propose(xyz, off, sem, bh, feat, sfp, scenes.RADIUS, scenes.MIN_PTS, copies)
+    s = out["scenes"]
+    idx, pid = s["index"], s["proposal"].to(torch.int64)
+    want = torch.cat([feat[idx], sfp[idx, out["proposal_sem"].to(torch.int64)[pid]][:, None], s["dpn"][:, None]], dim=1)
+    assert out["features"].shape == (idx.shape[0], 34) and torch.equal(out["features"], want)
+    # class of every proposal = class of its member points
+    assert torch.equal(sem[idx[s["offsets"][:-1]]].to(torch.int32), out["proposal_sem"])
+    # voxelization contract (ME semantics, parity unpinned): floor(xyz/0.02) per proposal, unique rows, inverse map
+    q = torch.cat([pid[:, None], torch.floor(xyz[idx] / 0.02).to(torch.int64)], dim=1)
+    vm = out["voxel_map"]
+    assert torch.equal(out["voxel_coords"].to(torch.int64)[vm.inverse], q)
+    assert out["voxel_coords"].shape[0] == torch.unique(q, dim=0).shape[0]
+    assert torch.equal(out["voxel_features"], want[vm.index])
