@@ -206,6 +206,26 @@ int pb_scene_features(pb_ctx *ctx, const float *point_feat, int32_t C, const flo
                       const int64_t *index, const int32_t *prop_id, const int32_t *prop_sem, const float *dpn,
                       int64_t n_entries, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation post-processing of the proposals (device pointers only).  Replaces the dense-matrix / CPU code of
+ *   eval_map.py:63-121          class of a proposal, fold of the rotated scene copies (index % (point_num/3)), score and
+ *                               point-count thresholds, cross IoU (dense fp32 mm), per-point labels, rebuilt clusters
+ *   tools/mIOU.py:77-87         non_max_suppression (greedy, CPU numpy)
+ *   tools/getins.py:72-98       align_superpoint_label (scipy coo_matrix on the CPU)
+ * in   proposals_idx i64[n_entries][2], proposals_offset i64[n_proposals+1], clt_score f32[n_proposals] (get_proposal /
+ *      the score head), pred_sem i64[point_num], superpoint i64[point_num/copies] with ids in [0, n_superpoints),
+ *      sem_table i64[n_table] (HOST; eval_map.py:32 semantic_label_idx)
+ * out  label i32[point_num/copies]: final cluster of every point or -100 (clusters are disjoint after the alignment, so this
+ *      IS the reference's `clusters` matrix: clusters[c] = (label == c)); cluster_scores f32, cluster_sem i64,
+ *      cluster_proposal i32 (proposal index of every final cluster), capacity `cap` >= number of proposals passing the
+ *      thresholds; *n_clusters_out.  Two host synchronisations.
+ */
+int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, int64_t n_entries, const int64_t *proposals_offset,
+                        int64_t n_proposals, const float *clt_score, const int64_t *pred_sem, int64_t point_num, int32_t copies,
+                        const int64_t *superpoint, int64_t n_superpoints, const int64_t *sem_table, int32_t n_table,
+                        float score_thresh, int32_t npoint_thresh, float nms_thresh, int32_t *label, float *cluster_scores,
+                        int64_t *cluster_sem, int32_t *cluster_proposal, int64_t cap, int64_t *n_clusters_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1224,3 +1224,139 @@ extern "C" int pb_scene_features(pb_ctx *ctx, const float *point_feat, int32_t C
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
+
+// =================================================================================================
+// evaluation post-processing of proposals (eval_map.py:63-121, tools/mIOU.py:77-87,
+// tools/getins.py:72-98) — see pb_eval.cuh.  Device pointers only.
+// =================================================================================================
+#include "pb_eval.cuh"
+
+static int bit_width_u64(unsigned long long v) {
+    int b = 0;
+    while (v) b++, v >>= 1;
+    return std::max(b, 1);
+}
+
+extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, int64_t n_entries, const int64_t *proposals_offset,
+                                   int64_t n_proposals, const float *clt_score, const int64_t *pred_sem, int64_t point_num,
+                                   int32_t copies, const int64_t *superpoint, int64_t n_superpoints, const int64_t *sem_table,
+                                   int32_t n_table, float score_thresh, int32_t npoint_thresh, float nms_thresh, int32_t *label,
+                                   float *cluster_scores, int64_t *cluster_sem, int32_t *cluster_proposal, int64_t cap,
+                                   int64_t *n_clusters_out, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (!n_clusters_out || n_entries < 0 || n_proposals < 0 || point_num < 0 || copies < 1 || n_superpoints < 0 || n_table < 1 ||
+        n_entries >= ((int64_t)1 << 31) || n_proposals >= ((int64_t)1 << 24) || point_num >= ((int64_t)1 << 31) || point_num % copies != 0)
+        return fail(ctx, PB_ERR_ARG, "bad argument (sizes must be non-negative, point_num a multiple of copies)");
+    *n_clusters_out = 0;
+    const int n3 = (int)(point_num / copies), P = (int)n_proposals, nsp = (int)n_superpoints;
+    const long long M = n_entries;
+    if (n3 == 0) return PB_OK;
+    if (!label || !superpoint || !sem_table) return fail(ctx, PB_ERR_ARG, "null pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const int T = 256;
+    int64_t &L = ctx->launches;
+    if (P == 0 || M == 0) {
+        pbe::k_fill_i32<<<div_up(n3, T), T, 0, st>>>(n3, -100, label);
+        L = 1;
+        PB_CUDA(cudaGetLastError());
+        return PB_OK;
+    }
+    if (!proposals_idx || !proposals_offset || !clt_score || !pred_sem || !cluster_scores || !cluster_sem || !cluster_proposal)
+        return fail(ctx, PB_ERR_ARG, "null pointer");
+    const int vmax = std::min(P, pbe::kMaxValid);
+    const size_t Mz = (size_t)std::max<long long>(M, n3);
+    // ---- workspace -------------------------------------------------------------------------------------------------
+    uint64_t *key = nullptr, *key_alt = nullptr, *key2 = nullptr, *key2_alt = nullptr;
+    int *head = nullptr, *npoint = nullptr, *valid = nullptr, *vid = nullptr, *vlist = nullptr, *d_scal = nullptr, *blocks = nullptr;
+    int *inter = nullptr, *order = nullptr, *pick_rank = nullptr, *picked = nullptr, *alive = nullptr, *newid = nullptr;
+    long long *prop_sem = nullptr, *d_table = nullptr;
+    unsigned long long *best = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        key = a.get<uint64_t>(Mz), key_alt = a.get<uint64_t>(Mz), key2 = a.get<uint64_t>(Mz), key2_alt = a.get<uint64_t>(Mz);
+        head = a.get<int>((size_t)M), npoint = a.get<int>(P), valid = a.get<int>(P), vid = a.get<int>((size_t)P + 1), vlist = a.get<int>(P);
+        prop_sem = a.get<long long>(P), d_table = a.get<long long>(n_table);
+        d_scal = a.get<int>(16), blocks = a.get<int>(Mz / pb::kScanTile + 2);
+        inter = a.get<int>((size_t)vmax * vmax), order = a.get<int>(vmax), pick_rank = a.get<int>(vmax), picked = a.get<int>(vmax);
+        alive = a.get<int>(vmax), newid = a.get<int>((size_t)vmax + 1);
+        best = a.get<unsigned long long>((size_t)std::max(nsp, 1));
+        cub_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)Mz, 0, 64);
+        cub_tmp = a.get<char>(cub_bytes);
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+        }
+    }
+    PB_CUDA(cudaMemcpyAsync(d_table, sem_table, sizeof(long long) * n_table, cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(d_scal, 0, sizeof(int) * 16, st));
+    PB_CUDA(cudaMemsetAsync(npoint, 0, sizeof(int) * (size_t)P, st));
+    int *d_err = d_scal, *d_V = d_scal + 1, *d_C = d_scal + 2, *d_C2 = d_scal + 3;
+    // ---- distinct (proposal, folded point) pairs, thresholds -----------------------------------------------------------
+    pbe::k_pair_keys<<<div_up(std::max<long long>(M, P), T), T, 0, st>>>(M, P, point_num, n3, (const long long *)proposals_idx,
+                                                                          (const long long *)proposals_offset, (const long long *)pred_sem,
+                                                                          d_table, n_table, key, prop_sem, d_err);
+    size_t cb = cub_bytes;
+    int bits1 = bit_width_u64((unsigned long long)P * (unsigned long long)n3 + 1);
+    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, (int)M, 0, bits1, st));
+    pbe::k_pair_heads<<<div_up(M, T), T, 0, st>>>(M, n3, key_alt, head, npoint);
+    pbe::k_valid<<<div_up(P, T), T, 0, st>>>(P, clt_score, score_thresh, npoint, npoint_thresh, valid);
+    L += 3 + 2 + (bits1 + 7) / 8;
+    launch_scan(st, valid, P, nullptr, vid, d_V, blocks, L);
+    pbe::k_valid_list<<<div_up(P, T), T, 0, st>>>(P, valid, vid, vlist);
+    L++;
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_scal, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_scalars[0] & pbe::kErrProp) return fail(ctx, PB_ERR_ARG, "proposals_idx[:,0] outside [0, n_proposals)");
+    if (ctx->h_scalars[0] & pbe::kErrPoint) return fail(ctx, PB_ERR_ARG, "proposals_idx[:,1] outside [0, point_num)");
+    if (ctx->h_scalars[0] & pbe::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "pred_sem outside the class table");
+    const int V = ctx->h_scalars[1];
+    if (V > pbe::kMaxValid) return fail(ctx, PB_ERR_CAPACITY, "more than 4096 proposals pass the score / point-count thresholds");
+    if (V == 0) {  // eval_map.py:88-89, 101-103: nothing to pick
+        pbe::k_fill_i32<<<div_up(n3, T), T, 0, st>>>(n3, -100, label);
+        L++;
+        PB_CUDA(cudaGetLastError());
+        return PB_OK;
+    }
+    if (cap < V) return fail(ctx, PB_ERR_CAPACITY, "output capacity below the number of proposals that pass the thresholds");
+    // ---- cross intersections, NMS ------------------------------------------------------------------------------------------
+    PB_CUDA(cudaMemsetAsync(inter, 0, sizeof(int) * (size_t)V * V, st));
+    pbe::k_point_keys<<<div_up(M, T), T, 0, st>>>(M, n3, key_alt, head, valid, vid, d_V, key2);
+    int bits2 = bit_width_u64((unsigned long long)n3 * (unsigned long long)V + 1);
+    cb = cub_bytes;
+    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key2, key2_alt, (int)M, 0, bits2, st));
+    pbe::k_intersections<<<div_up(M, T), T, 0, st>>>(M, key2_alt, d_V, inter);
+    pbe::k_nms<<<1, 1024, 0, st>>>(d_V, vlist, clt_score, inter, nms_thresh, order, pick_rank, picked, d_C);
+    // ---- per-point labels, superpoint vote, rebuilt clusters ---------------------------------------------------------------
+    pbe::k_fill_i32<<<div_up(n3, T), T, 0, st>>>(n3, -1, label);
+    pbe::k_paint<<<div_up(M, T), T, 0, st>>>(M, key2_alt, d_V, pick_rank, label);
+    pbe::k_vote_keys<<<div_up(n3, T), T, 0, st>>>(n3, (const long long *)superpoint, nsp, label, d_C, key, d_err);
+    int bits3 = bit_width_u64((unsigned long long)std::max(nsp, 1) * (unsigned long long)(V + 1) + 1);
+    cb = cub_bytes;
+    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, n3, 0, bits3, st));
+    PB_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)std::max(nsp, 1), st));
+    PB_CUDA(cudaMemsetAsync(alive, 0, sizeof(int) * (size_t)V, st));
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars + 4, d_scal, sizeof(int), cudaMemcpyDeviceToHost, st));  // superpoint range check
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_scalars[4] & pbe::kErrSuper) return fail(ctx, PB_ERR_ARG, "superpoint id outside [0, n_superpoints)");
+    pbe::k_vote_count<<<div_up(n3, T), T, 0, st>>>(n3, key_alt, d_C, best);
+    pbe::k_align<<<div_up(n3, T), T, 0, st>>>(n3, (const long long *)superpoint, best, d_C, label, alive);
+    L += 9 + 4 + (bits2 + 7) / 8 + (bits3 + 7) / 8;
+    launch_scan(st, alive, V, nullptr, newid, d_C2, blocks, L);
+    pbe::k_finish<<<div_up(std::max(n3, V), T), T, 0, st>>>(n3, d_C, alive, newid, picked, clt_score, prop_sem, label, cluster_scores,
+                                                            (long long *)cluster_sem, cluster_proposal);
+    L++;
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_scal, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    *n_clusters_out = ctx->h_scalars[3];
+    return PB_OK;
+}
