@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=312)
     ap.add_argument("--copies", type=int, default=1)
     ap.add_argument("--ref-scenes", type=int, default=8, help="scenes per step of the reference arm (bounded sample)")
-    ap.add_argument("--cpu-sample-points", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-points", type=int, default=10_000_000, help="bounded CPU-baseline sample (~10-20 s on 16 cores)")
     ap.add_argument("--dropin-calls", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -393,6 +393,40 @@ def main():
                                        "frac_of_hbm_copy_peak": gb_b / t_bwd / peak_v}}
         del vfeat, o, coords
 
+    # ---- the callers either side of the path on ONE scene with three rotated copies, the unit
+    #      eval_map.py processes per iteration: grouping + local scenes + feature rows + proposal voxelization
+    #      (grouping.propose), get_proposal, evaluation post-processing; rank 0 only
+    nxt = None
+    if rank == 0:
+        from pbnet_b200 import evalpost, grouping
+        sc0 = scenes.make_scene(scenes.BASE_SEED, int(sizes[0]))
+        cp3 = 3
+        t_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        xyz3 = t_(np.concatenate(scenes.rotate_copies(sc0["xyz_orig"], cp3)))
+        off3 = t_(np.concatenate(scenes.rotate_copies(sc0["offset"], cp3)))
+        sem3 = t_(np.tile(sc0["sem"], cp3))
+        bh3 = t_(np.repeat(np.arange(cp3), sc0["sem"].shape[0]).astype(np.int32))
+        gen = torch.Generator(device=dev).manual_seed(22)
+        feat3 = torch.rand((xyz3.shape[0], 32), device=dev, generator=gen)
+        sfp3 = torch.softmax(torch.rand((xyz3.shape[0], 20), device=dev, generator=gen), dim=1)
+        t_prop, pr = timed(lambda: grouping.propose(xyz3, off3, sem3, bh3, feat3, sfp3, scenes.RADIUS, scenes.MIN_PTS, cp3), 5)
+        scn = pr["scenes"]
+        E3, P3 = int(scn["index"].shape[0]), int(scn["offsets"].shape[0]) - 1
+        ms3 = torch.rand(E3, device=dev, generator=gen)
+        t_gp, gp = timed(lambda: grouping.get_proposal(scn["offsets"], scn["index"], ms3), 5)
+        score3 = torch.rand(int(gp[1].shape[0]) - 1, device=dev, generator=gen)
+        n3 = xyz3.shape[0] // cp3
+        # superpoints: 10 cm voxels of the original coordinates (spatially coherent, compressed ids)
+        sp3 = torch.unique(torch.floor(xyz3[:n3] / 0.1).to(torch.int64), dim=0, return_inverse=True)[1].contiguous()
+        t_ev, ev = timed(lambda: evalpost.postprocess(gp[0], gp[1], score3, sem3, sp3, int(xyz3.shape[0])), 5)
+        nxt = {"unit": "one scene x 3 rotated copies (the per-iteration unit of eval_map.py)", "points": int(xyz3.shape[0]),
+               "proposals": P3, "list_entries": E3, "voxels": int(pr["voxel_coords"].shape[0]),
+               "propose_ms": t_prop * 1e3, "propose_api": "grouping.propose = network/PBNet.py:144-247 (class loop, local scenes, "
+                                                          "feature rows, proposal voxelization)",
+               "get_proposal_ms": t_gp * 1e3, "kept_entries": int(gp[0].shape[0]),
+               "eval_postprocess_ms": t_ev * 1e3, "final_clusters": int(ev["scores"].shape[0])}
+        del xyz3, off3, sem3, bh3, feat3, sfp3, pr, scn
+
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -421,8 +455,9 @@ def main():
         achieved = deg_bytes / (deg_ms * 1e-3) / 1e9 if deg_ms > 0 else None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         # ceiling of the packed fp32x2 pair test measured with tools/microbench/pipes.cu on this pool's B200
-        # (profiles/microbench_pipes_r01.txt): 0.576 warp-tests/clk/SM, FFMA2-pipe bound (scalar form: 0.5, issue bound)
-        alu_peak = 148 * 32 * 0.576 * sm_mhz * 1e6
+        # (profiles/microbench_pipes_r01_v2.txt, slowest-warp timing, no loop-invariant operands): 0.485 warp-tests/clk/SM
+        # — the fp32 pipe retires 6 operations per test (3 FADD, FMUL, 2 FFMA); the scalar form tops out at 0.332
+        alu_peak = 148 * 32 * 0.485 * sm_mhz * 1e6
         tests_per_s = counters["pair_tests"] / (deg_ms_total * 1e-3) if deg_ms_total > 0 else None
         value = total_points / (ms_step * 1e-3)
         line = {
@@ -451,11 +486,12 @@ def main():
             "roofline_alu": {"kernel": "k_degree", "pair_tests_per_step": counters["pair_tests"],
                              "achieved": tests_per_s, "peak": alu_peak, "unit": "pair tests/s",
                              "frac": (tests_per_s / alu_peak) if tests_per_s else None,
-                             "peak_def": "148 SM x 32 lanes x 0.576 warp-tests/clk/SM (packed fp32x2 pair-test ceiling, "
-                                         "tools/microbench/pipes.cu) x measured SM clock"},
+                             "peak_def": "148 SM x 32 lanes x 0.485 warp-tests/clk/SM (measured ceiling of the packed fp32x2 pair test, "
+                                         "tools/microbench/pipes.cu, profiles/microbench_pipes_r01_v2.txt) x measured SM clock"},
             "io_roofline": {"bytes_per_point": 36, "achieved_gbs": value * 36 / 1e9, "frac_of_hbm": value * 36 / 1e9 / peak},
             "counters": counters,
             "voxel": vox,
+            "next_rows": nxt,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

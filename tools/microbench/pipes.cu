@@ -30,7 +30,7 @@ __global__ void k(float *out, float a, float b, unsigned long long *cyc) {
     float s = 0;
     for (int i = 0; i < 8; i++) s += x[i] + y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
 // packed chain kept in 64-bit registers (no repacking)
@@ -47,7 +47,7 @@ __global__ void k_packed(float *out, float a, float b, unsigned long long *cyc) 
     unsigned long long s = 0;
     for (int i = 0; i < 8; i++) s ^= p[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((unsigned)s);
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
 // the k_degree test itself: 3 FADD, FMUL, 2 FFMA, FSETP, predicated IADD on 8 independent (query,candidate) pairs
@@ -64,13 +64,13 @@ __global__ void k_test(float *out, float a, float b, unsigned long long *cyc) {
             float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
             asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d), "f"(b));
         }
-        cx += 1e-7f;
+        cx += 1e-7f, cy += 2e-7f, cz -= 1e-7f;  // all three differences change every iteration (nothing to hoist)
     }
     unsigned long long t1 = clock64();
     int s = 0;
     for (int i = 0; i < 8; i++) s += cnt[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
 // packed variant of the pair test: two candidates (cx0,cx1) per instruction against a duplicated query
@@ -83,7 +83,7 @@ __global__ void k_test2(float *out, float a, float b, unsigned long long *cyc) {
     unsigned long long qq[8];      // query coordinate duplicated in both halves
     int cnt[8];
     for (int i = 0; i < 8; i++) qq[i] = pk(threadIdx.x * 0.001f + i, threadIdx.x * 0.001f + i), cnt[i] = 0;
-    unsigned long long cx = pk(a, a + 0.01f), cy = pk(b, b + 0.01f), cz = pk(a + b, a - b);
+    unsigned long long cx = pk(a, a + 0.01f), cy = pk(b, b + 0.01f), cz = pk(a + b, a - b), step = pk(1e-7f, 2e-7f);
     unsigned long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
@@ -101,13 +101,15 @@ __global__ void k_test2(float *out, float a, float b, unsigned long long *cyc) {
             asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d0), "f"(b));
             asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[i]) : "f"(d1), "f"(b));
         }
-        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(cy));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(step));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cy) : "l"(step));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cz) : "l"(step));
     }
     unsigned long long t1 = clock64();
     int s = 0;
     for (int i = 0; i < 8; i++) s += cnt[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
 // variant: sign bits of (r2 - d) shifted into a mask with one funnel shift per test, POPC at the end
@@ -139,13 +141,17 @@ __global__ void k_test3(float *out, float a, float b, unsigned long long *cyc) {
 #pragma unroll
             for (int i = 0; i < 8; i++) cnt += 32 - __popc(mask[i]), mask[i] = 0;
         }
-        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(cy));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(rr));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cy) : "l"(rr));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cz) : "l"(rr));
     }
     unsigned long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)cnt;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
+// every launch is preceded by a reset of the cycle counter (atomicMax over all warps)
+#define RESET() cudaMemset(cyc, 0, 8)
 int main() {
     float *out;
     unsigned long long *cyc, h;
@@ -155,16 +161,16 @@ int main() {
     for (int warps = 4; warps <= 32; warps *= 2) {
         int threads = warps * 32;  // per SM (one block per SM)
         printf("--- %d warps per SM\n", warps);
-#define RUN(MODE) k<MODE><<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+#define RUN(MODE) RESET(); k<MODE><<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
         printf("%-30s %.3f warp-instr/cycle/SM\n", names[MODE], (double)ITERS * 8 * warps * (MODE == 4 ? 3 : 1) / h);
         RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
-        k_packed<<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        RESET(); k_packed<<<148, threads>>>(out, 1.0001f, 0.5f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-instr/cycle/SM  (= %.3f fp32 FMA-lanes x32 /cycle)\n", "FFMA2 (64-bit regs)", (double)ITERS * 8 * warps / h, 2.0 * ITERS * 8 * warps / h);
-        k_test<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        RESET(); k_test<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-tests/cycle/SM  (8 instr each -> %.3f instr/cycle/SM)\n", "k_degree pair test", (double)ITERS * 8 * warps / h, 8.0 * ITERS * 8 * warps / h);
-        k_test2<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        RESET(); k_test2<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-tests/cycle/SM  (packed f32x2, 5 instr per test)\n", "pair test, f32x2", (double)ITERS * 16 * warps / h);
-        k_test3<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        RESET(); k_test3<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-tests/cycle/SM  (packed + sign-bit funnel shift, 4.5 instr per test)\n", "pair test, f32x2+SHF", (double)ITERS * 16 * warps / h);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
