@@ -329,7 +329,8 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     const int T = 256;
     const int gN = div_up(n, T);
     const int gS = div_up(S + 1, T);
-    const int gPersist = 148 * 8;
+    // grid-stride kernels: one CTA wave on large problems, no more CTAs than warp-sized work items on small ones
+    const int gPersist = std::min(148 * 8, std::max(1, div_up(n, 8)));
     w.sg.start = w.seg_start;
 
     mark();  // start of H2D

@@ -541,43 +541,68 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
     long long base = (long long)warp * kWindow;
     if (base >= n) return;
     int end = (int)min((long long)n, base + kWindow);
-    int pos = (int)base;
+    // group heads of the window (a group = points of one coarse row): one coalesced read of row_of, four ballots
+    unsigned hm[kWindow / 32];
+    int G = 0;
+#pragma unroll
+    for (int k = 0; k < kWindow / 32; k++) {
+        int i = (int)base + 32 * k + lane;
+        bool head = (i < end) && (i == (int)base || g.row_of[i] != g.row_of[i - 1]);
+        hm[k] = __ballot_sync(kFull, head);
+        G += __popc(hm[k]);
+    }
+    // small problems launch nslice warps per window (gridDim.y).  A window of many small groups is dealt out group by
+    // group to teams of `cs` warps (every group's dependent metadata loads then run in parallel on different warps
+    // instead of back to back on one); the warps of a team — or, for windows of few large groups, all warps — split the
+    // group's candidate stream.
+    int cs = nslice, gs = 1;
+    if (nslice > 1 && G >= nslice) {
+        cs = nslice >= 8 ? 4 : (nslice >= 4 ? 2 : 1);
+        gs = nslice / cs;
+    }
+    const bool by_group = gs > 1;
+    const int team = slice / cs, sub = slice % cs;
+    if (by_group && team >= gs) return;  // nslice not a multiple of cs: the last warps idle
     unsigned long long tests = 0;
+    int gi = 0, pos = (int)base;
     while (pos < end) {  // uniform
-        int row = g.row_of[pos];
-        // group end: first position after pos whose row differs
+        // group end: next head after pos
         int gend = end;
-#pragma unroll 1
-        for (int k = 0; k < kWindow / 32; k++) {
-            int i = pos + 1 + 32 * k + lane;
-            bool differs = (i < end) && (g.row_of[i] != row);
-            unsigned b = __ballot_sync(kFull, differs);
-            if (b) {
-                gend = pos + 1 + 32 * k + __ffs(b) - 1;
-                break;
-            }
-            if (pos + 1 + 32 * (k + 1) >= end) break;
-        }
-        int total = gend - pos;
-        int fmin = g.fcell_of[pos], fmax = g.fcell_of[gend - 1];
-        int cmin = g.fcell_cc[fmin], cmax = g.fcell_cc[fmax];
-        float r2 = sg.r2[(int)(g.fcell_key[fmin] >> kSegShift)];
-        int jb = 0, je = 0;
-        if (lane < kRuns) {
-            int c0 = g.runs9[(long long)cmin * kRuns + lane].x, c1 = g.runs9[(long long)cmax * kRuns + lane].y;
-            if (c1 > c0) {
-                jb = g.cc_pstart[c0];
-                je = g.cc_pstart[c1];
+        {
+            int rel = pos + 1 - (int)base;
+#pragma unroll
+            for (int k = kWindow / 32 - 1; k >= 0; k--) {
+                int lo = rel - 32 * k;  // first candidate bit inside word k
+                unsigned m = hm[k];
+                if (lo > 0) m = lo >= 32 ? 0u : (m & (0xffffffffu << lo));
+                if (m) gend = (int)base + 32 * k + __ffs(m) - 1;
             }
         }
-        if (n_tests && slice == 0) {
-            unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
-            tests += (unsigned long long)cand * (unsigned)total;
-        }
-        switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
-            case 1: degree_group<1>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
-            case 2: degree_group<2>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
-            default: degree_group<3>(g, pos, total, lane, r2, jb, je, deg_sorted, slice, nslice); break;
+        const bool mine = !by_group || (gi % gs) == team;
+        gi++;
+        if (mine) {
+            int total = gend - pos;
+            int fmin = g.fcell_of[pos], fmax = g.fcell_of[gend - 1];
+            int cmin = g.fcell_cc[fmin], cmax = g.fcell_cc[fmax];
+            float r2 = sg.r2[(int)(g.fcell_key[fmin] >> kSegShift)];
+            int jb = 0, je = 0;
+            if (lane < kRuns) {
+                int c0 = g.runs9[(long long)cmin * kRuns + lane].x, c1 = g.runs9[(long long)cmax * kRuns + lane].y;
+                if (c1 > c0) {
+                    jb = g.cc_pstart[c0];
+                    je = g.cc_pstart[c1];
+                }
+            }
+            if (n_tests && sub == 0) {
+                unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
+                tests += (unsigned long long)cand * (unsigned)total;
+            }
+            const int sl = sub, ns = cs;
+            switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
+                case 1: degree_group<1>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                case 2: degree_group<2>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                default: degree_group<3>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+            }
         }
         pos = gend;
     }
