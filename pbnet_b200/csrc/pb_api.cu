@@ -213,6 +213,8 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     int *d_scalars;  // [0] err [1] C [2] R [3] K [4] Q [5] L
     unsigned long long *d_counters;
     int *scan_blocks;
+    unsigned long long *scan_state;  // single-pass scan: one word per tile + the ticket counter behind them
+    size_t scan_tiles;
     void *cub_tmp;
     size_t cub_bytes;
 };
@@ -259,6 +261,8 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
     w.d_scalars = a.get<int>(16);
     w.d_counters = a.get<unsigned long long>(8);
     w.scan_blocks = a.get<int>(std::max(N, (size_t)S * pb::kCls) / pb::kScanTile + 2);
+    w.scan_tiles = std::max(N, (size_t)S * pb::kCls) / pb::kScanTile + 2;
+    w.scan_state = a.get<unsigned long long>(w.scan_tiles + 1);
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
@@ -367,8 +371,14 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5, *d_Cc = w.d_scalars + 6, *d_rows = w.d_scalars + 7;
     unsigned long long *cnt = prof ? w.d_counters : nullptr;
 
+    // single-pass scans (pb::k_scan_onepass): tile words + ticket zeroed once per chunk, epochs separate the scans
+    PB_CUDA(cudaMemsetAsync(w.scan_state, 0, sizeof(unsigned long long) * (w.scan_tiles + 1), st));
+    unsigned scan_epoch = 0;
     auto scan = [&](const int *in, int n_host, const int *n_dev, int *out, int *total) {
-        launch_scan(st, in, n_host, n_dev, out, total, w.scan_blocks, L);
+        int nb = std::max(1, div_up(n_host, pb::kScanTile));
+        pb::k_scan_onepass<<<nb, pb::kScanThreads, 0, st>>>(in, n_host, n_dev, out, total, w.scan_state,
+                                                            reinterpret_cast<int *>(w.scan_state + w.scan_tiles), ++scan_epoch);
+        L++;
     };
 
     mark();  // PREP
@@ -442,8 +452,11 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
                                                   w.cell_gid18);
     L++;
     mark();  // LABEL
-    pb::k_label<MIXED><<<div_up(n, 128), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label, w.raw_count, dsem,
-                                                       w.cell_gid18);
+    {
+        const int ppw = n >= (1 << 18) ? 32 : (n >= (1 << 16) ? 16 : 8);
+        pb::k_label<MIXED><<<div_up(div_up(n, ppw), 4), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label,
+                                                                      w.raw_count, dsem, w.cell_gid18, ppw);
+    }
     L++;
     mark();  // FILTER
     pb::k_filter<MIXED><<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, d_thresh, w.keep, dsem);

@@ -825,10 +825,12 @@ template <bool MIXED>
 __global__ void __launch_bounds__(128)
 k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp,
         const int *__restrict__ cell_gid, int *__restrict__ raw_label, int *__restrict__ raw_count,
-        const int *__restrict__ sem, const int *__restrict__ cell_gid18) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+        const int *__restrict__ sem, const int *__restrict__ cell_gid18, int ppw) {
+    // ppw = points per warp: 32 on large problems; small problems spread the points over more warps (the loop below
+    // visits the distinct cells of a warp's LPs one after the other, each with its own chain of dependent loads)
     int lane = lane_id();
-    bool valid = i < n;
+    int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ppw + lane;
+    bool valid = lane < ppw && i < n;
     float4 p = pts4[valid ? i : 0];
     int c = valid ? g.fcell_of[i] : -1;
     bool hp = valid && (__float_as_int(p.w) & kHpBit);
@@ -1390,6 +1392,101 @@ k_scan_down(const int *__restrict__ in, int n_host, const int *__restrict__ n_de
         int i = i0 + k;
         if (i < n) out[i] = ex;
         ex += v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-pass exclusive scan (decoupled look-back): ONE launch instead of three.  Tiles take their index from a ticket
+// counter (a tile only ever waits for tiles whose CTAs are already running); a tile publishes {epoch, flag, value} in
+// one 64-bit word: flag 1 = tile aggregate, 2 = inclusive prefix.  The epoch (host counter, never 0) makes stale words
+// of earlier scans invisible, so the state array is zeroed once per call, not per scan.  The last tile writes the total
+// and rearms the ticket counter.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_onepass(const int *__restrict__ in, int n_host, const int *__restrict__ n_dev, int *__restrict__ out,
+               int *__restrict__ total_out, unsigned long long *tile_state, int *ticket, unsigned epoch) {
+    __shared__ int smem[33];
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int n = n_dev ? *n_dev : n_host;
+    const int i0 = tile * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int sum = 0;
+    // thread t owns 8 consecutive items = two 16-byte vectors (the arena keeps every array 256-byte aligned)
+    const bool full = i0 + kScanItems <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (full) {
+        int4 a = __ldg(reinterpret_cast<const int4 *>(in + i0)), b = __ldg(reinterpret_cast<const int4 *>(in + i0) + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) sum += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            int i = i0 + k;
+            v[k] = i < n ? in[i] : 0;
+            sum += v[k];
+        }
+    }
+    int total;
+    int ex = block_excl_scan(sum, smem, total);
+    if (threadIdx.x < 32) {  // warp 0: publish the aggregate, look back 32 tiles at a time
+        const int lane = threadIdx.x;
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        int prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(tile_state, tag | (2ull << 32) | (unsigned)total);
+        } else {
+            if (lane == 0) st_volatile_u64(tile_state + tile, tag | (1ull << 32) | (unsigned)total);
+            int j = tile - 1;  // lane l inspects tile j - l; tiles before 0 count as a published prefix of 0
+            while (true) {
+                int idx = j - lane;
+                unsigned long long w = idx >= 0 ? ld_volatile_u64(tile_state + idx) : (tag | (2ull << 32));
+                bool ready = (w >> 34) == epoch;
+                unsigned not_ready = ~__ballot_sync(kFull, ready);
+                int usable = not_ready ? __ffs(not_ready) - 1 : 32;  // lanes [0, usable) hold published words
+                unsigned is_prefix = __ballot_sync(kFull, ready && ((w >> 32) & 3ull) == 2ull) & (usable == 32 ? kFull : ((1u << usable) - 1u));
+                int stop = is_prefix ? __ffs(is_prefix) - 1 : usable - 1;  // last lane whose value is added
+                int val = (lane <= stop) ? (int)(unsigned)w : 0;
+                prefix += __reduce_add_sync(kFull, val);
+                if (is_prefix) break;
+                j -= usable;  // all of [0, usable) were aggregates; retry from the first unpublished tile
+            }
+            if (lane == 0) st_volatile_u64(tile_state + tile, tag | (2ull << 32) | (unsigned)(prefix + total));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == (int)gridDim.x - 1) {
+                *total_out = prefix + total;
+                *ticket = 0;
+            }
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
+    if (full) {
+        int o[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) o[k] = ex, ex += v[k];
+        reinterpret_cast<int4 *>(out + i0)[0] = make_int4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<int4 *>(out + i0)[1] = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            int i = i0 + k;
+            if (i < n) out[i] = ex;
+            ex += v[k];
+        }
     }
 }
 
