@@ -202,7 +202,7 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     float4 *pts4, *lab4, *box_lo, *box_hi, *box2_lo, *box2_hi;
     float *sx, *sy, *sz;
     // per fine cell / coarse cell (upper bound N)
-    int *fcell_start, *fcell_cc, *cc_pstart, *cc_fstart, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid;
+    int *fcell_start, *fcell_cc, *cc_pstart, *cc_fstart, *parent, *cell_hp, *cell_minhp, *comp_min, *cell_gid, *cell_first;
     uint64_t *fcell_key, *cc_key;
     int2 *runs9;
     // per raw cluster (upper bound N)
@@ -254,7 +254,7 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
     w.box_lo = a.get<float4>(N / 32 + 2); w.box_hi = a.get<float4>(N / 32 + 2);
     w.box2_lo = a.get<float4>(N / 1024 + 2); w.box2_hi = a.get<float4>(N / 1024 + 2);
     w.fcell_start = a.get<int>(N + 1); w.fcell_cc = a.get<int>(N); w.cc_pstart = a.get<int>(N + 1); w.cc_fstart = a.get<int>(N + 1);
-    w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N);
+    w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N); w.cell_first = a.get<int>(N);
     w.comp_min = a.get<int>(N); w.cell_gid = a.get<int>(N); w.fcell_key = a.get<uint64_t>(N); w.cc_key = a.get<uint64_t>(N);
     w.runs9 = a.get<int2>(N * pb::kRuns);
     w.rep = a.get<int>(N); w.raw_count = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
@@ -413,7 +413,7 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     scan(w.head_r, n, nullptr, w.ex_r, d_rows);
     pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head_f, w.ex_f, w.head_c, w.ex_c, w.head_r, w.ex_r, w.fcell_of, w.row_of,
                                   w.fcell_start, w.fcell_key, w.fcell_cc, w.cc_pstart, w.cc_fstart, w.cc_key, w.parent,
-                                  w.cell_hp, w.cell_minhp, w.comp_min, d_F, d_Cc);
+                                  w.cell_hp, w.cell_minhp, w.comp_min, d_F, d_Cc, w.cell_first);
     if (MIXED) {  // per (fine cell, class) tables start at "no HP" (F <= n cells)
         PB_CUDA(cudaMemsetAsync(w.cell_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
         PB_CUDA(cudaMemsetAsync(w.comp_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
@@ -437,11 +437,11 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     L++;
     mark();  // HP
     pb::k_hp_cells<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
-                                            w.cell_minhp, cnt, dsem, d_min_pts, w.cell_min18);
+                                            w.cell_minhp, cnt, dsem, d_min_pts, w.cell_min18, w.cell_first);
     L++;
     mark();  // UNION
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0);
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1);
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0, w.cell_first);
+    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1, w.cell_first);
     L += 2;
     mark();  // COMPONENTS
     pb::k_comp_min<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min, w.cell_min18, w.comp_min18);

@@ -341,7 +341,7 @@ __global__ void k_cells(int n, const uint64_t *__restrict__ skey, const int *__r
                         int *__restrict__ fcell_cc, int *__restrict__ cc_pstart, int *__restrict__ cc_fstart,
                         uint64_t *__restrict__ cc_key, int *__restrict__ parent, int *__restrict__ cell_hp,
                         int *__restrict__ cell_minhp, int *__restrict__ comp_min, int *__restrict__ d_F,
-                        int *__restrict__ d_Cc) {
+                        int *__restrict__ d_Cc, int *__restrict__ cell_first) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int hf = head_f[i], hc = head_c[i];
@@ -357,6 +357,7 @@ __global__ void k_cells(int n, const uint64_t *__restrict__ skey, const int *__r
         cell_hp[f] = 0;
         cell_minhp[f] = 0x7fffffff;
         comp_min[f] = 0x7fffffff;
+        cell_first[f] = 0x7fffffff;
     }
     if (hc) {
         cc_pstart[c] = i;
@@ -615,7 +616,7 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
                            const uint64_t *__restrict__ fcell_key, const int *__restrict__ deg_sorted,
                            int *__restrict__ degree_out, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
                            unsigned long long *__restrict__ counters, const int *__restrict__ sem,
-                           const int *__restrict__ min_pts_tab, int *__restrict__ cell_min18) {
+                           const int *__restrict__ min_pts_tab, int *__restrict__ cell_min18, int *__restrict__ cell_first) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     unsigned act = __ballot_sync(kFull, valid);
@@ -638,9 +639,11 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     unsigned grp = __match_any_sync(act, c);
     unsigned hpm = __ballot_sync(act, hp) & grp;
     int mn = __reduce_min_sync(grp, hp ? orig : 0x7fffffff);
+    int first = __reduce_min_sync(grp, hp ? i : 0x7fffffff);
     if (hpm && lane_id() == __ffs(grp) - 1) {
         atomicAdd(cell_hp + c, __popc(hpm));
         atomicMin(cell_minhp + c, mn);
+        atomicMin(cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
     }
     if (counters) {  // profiling only: [1] sum of degrees, [2] HP count
         unsigned long long dsum = 0, hsum = 0;
@@ -690,7 +693,8 @@ __device__ __forceinline__ bool hp_pair_exists(const float4 *__restrict__ pts4, 
 //      Launched twice: touching cells first, then the cells at fine distance 2.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp, int *parent, int far_pass) {
+k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__restrict__ cell_hp, int *parent, int far_pass,
+        const int *__restrict__ cell_first) {
     int F = *g.d_F;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
@@ -709,6 +713,7 @@ k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__rest
             }
         }
         int rootA = uf_find(parent, A);
+        const float4 pA = __ldg(pts4 + cell_first[A]);  // representative: the cell's first HP
         for (int k = 0; k < kRuns; k++) {
             int b = __shfl_sync(kFull, f0, k), e = __shfl_sync(kFull, f1, k);
             for (int fb = max(b, A + 1); fb < e; fb += 32) {
@@ -720,6 +725,18 @@ k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__rest
                     int d = fine_dist(kA, g.fcell_key[B]);
                     if (far_pass ? d == 2 : d <= 1) cand = uf_find(parent, B) != rootA;
                 }
+                // representative shortcut: every lane tests ONE exact pair (first HP of A, first HP of its cell B); a hit
+                // joins the two cells right away (lock-free, lane-parallel), only the misses pay the cooperative search
+                bool quick = false;
+                if (cand) {
+                    float4 q = __ldg(pts4 + cell_first[B]);
+                    quick = sqd(pA.x, pA.y, pA.z, q.x, q.y, q.z) <= r2;
+                    if (quick) {
+                        uf_union(parent, A, B);
+                        cand = false;
+                    }
+                }
+                if (__any_sync(kFull, quick)) rootA = uf_find(parent, A);
                 unsigned m = __ballot_sync(kFull, cand);
                 while (m) {
                     int l = __ffs(m) - 1;
