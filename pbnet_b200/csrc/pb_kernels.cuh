@@ -1322,7 +1322,7 @@ k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt
 // exclusive scan of int32 (three kernels: block sums, spine, down-sweep).  n may live on the device.
 // ------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ int block_excl_scan(int v, int *smem, int &total) {
@@ -1440,11 +1440,14 @@ k_scan_onepass(const int *__restrict__ in, int n_host, const int *__restrict__ n
     const int i0 = tile * kScanTile + threadIdx.x * kScanItems;
     int v[kScanItems];
     int sum = 0;
-    // thread t owns 8 consecutive items = two 16-byte vectors (the arena keeps every array 256-byte aligned)
+    // thread t owns kScanItems consecutive items = 16-byte vectors (the arena keeps every array 256-byte aligned)
     const bool full = i0 + kScanItems <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (full) {
-        int4 a = __ldg(reinterpret_cast<const int4 *>(in + i0)), b = __ldg(reinterpret_cast<const int4 *>(in + i0) + 1);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; q++) {
+            int4 a = __ldg(reinterpret_cast<const int4 *>(in + i0) + q);
+            v[4 * q] = a.x, v[4 * q + 1] = a.y, v[4 * q + 2] = a.z, v[4 * q + 3] = a.w;
+        }
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) sum += v[k];
     } else {
@@ -1495,8 +1498,9 @@ k_scan_onepass(const int *__restrict__ in, int n_host, const int *__restrict__ n
         int o[kScanItems];
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) o[k] = ex, ex += v[k];
-        reinterpret_cast<int4 *>(out + i0)[0] = make_int4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<int4 *>(out + i0)[1] = make_int4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; q++)
+            reinterpret_cast<int4 *>(out + i0)[q] = make_int4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; k++) {
