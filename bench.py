@@ -482,9 +482,13 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
+            "stage_ms_note": "CUDA-event intervals summed over the chunks of a step; the chunks run on two concurrent streams, so an "
+                             "interval also contains the time its kernels share the GPU with the other chunk (k_degree runs alone on "
+                             "the SMs, its interval is the kernel time; profiles/launches_*_summary.txt has the serialised per-kernel times)",
             "roofline": {"bound": "hbm", "kernel": "k_degree", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "launches_per_step": chunks, "avg_launch_ms": deg_ms, "algorithmic_bytes_per_launch": deg_bytes,
+                         "launches_per_step": chunks, "avg_launch_ms": deg_ms, "share_of_step": deg_ms_total / ms_step,
+                         "algorithmic_bytes_per_launch": deg_bytes,
                          "note": "k_degree is fp32-issue bound, not HBM bound: see roofline_alu"},
             "roofline_alu": {"kernel": "k_degree", "pair_tests_per_step": counters["pair_tests"],
                              "achieved": tests_per_s, "peak": alu_peak, "unit": "pair tests/s",
