@@ -1116,26 +1116,40 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
     int Q = *d_Q;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Q; qi += warps) {
-        int p = qlist[qi];
-        int s = seg_of[p];
-        int l0, l1;
-        if (!MIXED) {
-            l0 = sg.lab_start[s], l1 = sg.lab_start[s + 1];
-            if (l1 <= l0) continue;
-        } else {  // candidates = labelled points of the query's class (binary_cuda_functions.cu:275)
-            long long e = (long long)s * kCls + (sem[p] - 2);
-            l0 = lab_start18[e], l1 = lab_start18[e + 1];
-            if (l1 <= l0) {  // no labelled point of this class: the label of the LAST labelled point (:287-300)
-                int last = seg_lastlab[s];
+    // a warp takes 32 consecutive queries at a time: lane l fetches the header of query 32*qb + l (list entry, segment,
+    // labelled range, coordinates, own rank — a chain of three dependent loads) for all 32 at once; the queries are then
+    // processed one after the other with the header broadcast by shuffles
+    for (int qb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qb * 32 < Q; qb += warps) {
+      int hp_ = -1, hl0 = 0, hl1 = 0, hrank = 0, hlast = -1;
+      float hx = 0.f, hy = 0.f, hz = 0.f;
+      if (qb * 32 + lane < Q) {
+          hp_ = qlist[qb * 32 + lane];
+          int s = seg_of[hp_];
+          if (!MIXED) {
+              hl0 = sg.lab_start[s], hl1 = sg.lab_start[s + 1];
+          } else {  // candidates = labelled points of the query's class (binary_cuda_functions.cu:275)
+              long long e = (long long)s * kCls + (sem[hp_] - 2);
+              hl0 = lab_start18[e], hl1 = lab_start18[e + 1];
+              hlast = seg_lastlab[s];
+          }
+          hx = xo[hp_], hy = yo[hp_], hz = zo[hp_];
+          hrank = lpos[inv2[hp_]];
+      }
+      const int nq = min(32, Q - qb * 32);
+      for (int j = 0; j < nq; j++) {
+        const int p = __shfl_sync(kFull, hp_, j);
+        const int l0 = __shfl_sync(kFull, hl0, j), l1 = __shfl_sync(kFull, hl1, j);
+        if (l1 <= l0) {
+            if (MIXED) {  // no labelled point of this class: the label of the LAST labelled point (:287-300)
+                int last = __shfl_sync(kFull, hlast, j);
                 if (lane == 0 && last >= 0) cluster_id[p] = cluster_id[last];
-                continue;
             }
+            continue;
         }
-        float px = xo[p], py = yo[p], pz = zo[p];
+        const float px = __shfl_sync(kFull, hx, j), py = __shfl_sync(kFull, hy, j), pz = __shfl_sync(kFull, hz, j);
         int g0 = l0 >> 5, g1 = (l1 - 1) >> 5;
         // first guess: the group where the query itself would sit in the sorted labelled list
-        int gq = min(max(lpos[inv2[p]], l0), l1 - 1) >> 5;
+        int gq = min(max(__shfl_sync(kFull, hrank, j), l0), l1 - 1) >> 5;
         float bestD = __int_as_float(0x7f800000);
         int bestI = -1;
         nn_scan_group(gq, l0, l1, lane, px, py, pz, lab4, bestD, bestI);
@@ -1165,6 +1179,7 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
             }
         }
         if (lane == 0 && bestI >= 0) cluster_id[p] = cluster_id[bestI];
+      }
     }
 }
 
