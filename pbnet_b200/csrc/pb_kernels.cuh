@@ -856,15 +856,25 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
     if (MIXED && valid) myc = sem[__float_as_int(p.w) & ~kHpBit] - 2;
     if (hp) label = MIXED ? cell_gid18[(long long)c * kCls + myc] : cell_gid[c];
     unsigned todo = __ballot_sync(kFull, valid && !hp);
+    // every LP lane fetches the header of its OWN cell up front (key, radius, coarse cell: a chain of dependent loads,
+    // now paid once per warp); the loop below broadcasts the leader's copy
+    uint64_t kMine = 0;
+    float r2Mine = 0.f;
+    int ccMine = 0;
+    if (valid && !hp) {
+        kMine = g.fcell_key[c];
+        r2Mine = sg.r2[(int)(kMine >> kSegShift)];
+        ccMine = g.fcell_cc[c];
+    }
     while (todo) {
         int leader = __ffs(todo) - 1;
         int cL = __shfl_sync(kFull, c, leader);
         bool mine = (c == cL) && valid && !hp;
         unsigned mask = __ballot_sync(kFull, mine);
         todo &= ~mask;
-        uint64_t kL = g.fcell_key[cL];
-        float r2 = sg.r2[(int)(kL >> kSegShift)];
-        int cc = g.fcell_cc[cL];
+        uint64_t kL = __shfl_sync(kFull, kMine, leader);
+        float r2 = __shfl_sync(kFull, r2Mine, leader);
+        int cc = __shfl_sync(kFull, ccMine, leader);
         int f0 = 0, f1 = 0;
         if (lane < kRuns) {
             int2 rr = g.runs9[(long long)cc * kRuns + lane];
