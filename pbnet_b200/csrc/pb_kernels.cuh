@@ -641,9 +641,18 @@ __global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const
     int mn = __reduce_min_sync(grp, hp ? orig : 0x7fffffff);
     int first = __reduce_min_sync(grp, hp ? i : 0x7fffffff);
     if (hpm && lane_id() == __ffs(grp) - 1) {
-        atomicAdd(cell_hp + c, __popc(hpm));
-        atomicMin(cell_minhp + c, mn);
-        atomicMin(cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
+        // a cell whose points all sit inside this warp is written with plain stores (k_cells initialised the tables);
+        // only the runs that touch the first / last active lane may continue in a neighbouring warp and need atomics
+        const bool interior = !(grp & 1u) && !(grp & (1u << (31 - __clz(act))));
+        if (interior) {
+            cell_hp[c] = __popc(hpm);
+            cell_minhp[c] = mn;
+            cell_first[c] = first;
+        } else {
+            atomicAdd(cell_hp + c, __popc(hpm));
+            atomicMin(cell_minhp + c, mn);
+            atomicMin(cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
+        }
     }
     if (counters) {  // profiling only: [1] sum of degrees, [2] HP count
         unsigned long long dsum = 0, hsum = 0;
