@@ -384,13 +384,15 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     mark();  // PREP
     pb::k_prep_points<<<gN, T, 0, st>>>(n, S, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, d_err);
     pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, d_radius, d_min_pts);
+    int seg_bits = 1;
+    while ((1 << seg_bits) < S) seg_bits++;
+    // LP-assignment order on 32-bit keys when the segment id leaves at least 15 Morton bits (see k_keys)
+    const int key2_mbits = (!MIXED && 32 - seg_bits >= 15) ? std::min(32 - seg_bits, 3 * pb::kMortonBits) : 0;
     pb::k_keys<MIXED><<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err,
-                                        d_radius, w.cnt18);
+                                        d_radius, w.cnt18, key2_mbits);
     L += 3;
 
     mark();  // SORT
-    int seg_bits = 1;
-    while ((1 << seg_bits) < S) seg_bits++;
     int end_bit = pb::kSegShift + seg_bits;
     {
         size_t bytes = w.cub_bytes;
@@ -398,7 +400,13 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         if (assign_lp) {
             bytes = w.cub_bytes;
             int end_bit2 = pb::kKey2SegShift + seg_bits + (MIXED ? 5 : 0);
-            PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit2, st));
+            if (key2_mbits > 0) {
+                end_bit2 = key2_mbits + seg_bits;
+                uint32_t *k32 = reinterpret_cast<uint32_t *>(w.key2);
+                PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, k32, k32 + n, w.val, w.order2, n, 0, end_bit2, st));
+            } else {
+                PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit2, st));
+            }
             L += 2 + (end_bit2 + 7) / 8;
         }
         L += 2 + (end_bit + 7) / 8;  // histogram + exclusive sum + onesweep passes

@@ -273,7 +273,7 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
                        const int *__restrict__ sem, const int *__restrict__ seg_of,
                        uint64_t *__restrict__ key1, uint64_t *__restrict__ key2,
                        uint32_t *__restrict__ val, int *err, const float *__restrict__ radius_tab,
-                       int *__restrict__ cnt18) {
+                       int *__restrict__ cnt18, int key2_mbits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = seg_of[i];
@@ -307,9 +307,14 @@ __global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const f
     uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kMortonMax);
     uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kMortonMax);
     uint64_t mort = spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
-    if (!MIXED)
-        key2[i] = ((uint64_t)s << kKey2SegShift) | mort;
-    else
+    if (!MIXED) {
+        // key2 only ORDERS the labelled points (never a correctness filter): when segment id + the top key2_mbits of the
+        // Morton code fit 32 bits the sort runs on 32-bit keys (4 passes of 8 B instead of 5 passes of 12 B per point)
+        if (key2_mbits > 0)
+            reinterpret_cast<uint32_t *>(key2)[i] = ((uint32_t)s << key2_mbits) | (uint32_t)(mort >> (3 * kMortonBits - key2_mbits));
+        else
+            key2[i] = ((uint64_t)s << kKey2SegShift) | mort;
+    } else
         key2[i] = ((uint64_t)s << (kKey2SegShift + 5)) | ((uint64_t)(myc - 2) << kKey2SegShift) | mort;
     val[i] = (uint32_t)i;
 }
