@@ -155,7 +155,7 @@ def run_reference_arm(args):
     sample_scenes = list(range(min(args.ref_scenes, args.scenes)))
     w = workload.build(sample_scenes, sizes, args.copies)
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C1 sample: first {len(sample_scenes)} of {args.scenes} synthetic ScanNet-val-shaped "
                                    f"scenes, per-class calls as network/PBNet.py:151-179, copies={args.copies}, "
@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=312)
     ap.add_argument("--copies", type=int, default=1)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --scenes scenes PER GPU (a set of scenes x N_gpus scenes sharded by scene); strong: the same --scenes scenes sharded over the GPUs")
     ap.add_argument("--ref-scenes", type=int, default=8, help="scenes per step of the reference arm (bounded sample)")
     ap.add_argument("--cpu-sample-points", type=int, default=10_000_000, help="bounded CPU-baseline sample (~10-20 s on 16 cores)")
     ap.add_argument("--dropin-calls", type=int, default=256)
@@ -236,7 +238,11 @@ def main():
 
     rank, local_rank, world = dist_env()
     from pbnet_b200 import scenes, workload
-    sizes = scenes.scene_sizes(args.scenes)
+    # scenes are independent units: they are partitioned over the ranks (LPT by point count), no data-path collective.
+    # weak scaling (default): the set grows with the GPU count (args.scenes per GPU; the first args.scenes scenes are the
+    # N=1 set); strong scaling: BASELINE.json configs[2] taken literally (the same args.scenes scenes over all GPUs)
+    n_scenes_total = args.scenes * (world if args.scaling == "weak" else 1)
+    sizes = scenes.scene_sizes(n_scenes_total)
     shards = workload.shard_scenes(sizes, world)
     # build the workload BEFORE touching CUDA (uses forked worker processes)
     w = workload.build(shards[rank], sizes, args.copies, workers=max(1, (os.cpu_count() or 1) // max(1, world)))
@@ -465,9 +471,10 @@ def main():
         value = total_points / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"C1: {args.scenes} synthetic ScanNet-val-shaped scenes (50k-250k points, seed 22+s), "
+            "config": {"workload": f"C1: {n_scenes_total} synthetic ScanNet-val-shaped scenes "
+                                   f"({args.scenes} per GPU, {args.scaling} scaling; 50k-250k points, seed 22+s), "
                                    f"per-class calls as network/PBNet.py:151-179, copies={args.copies}, r=0.04, min_pts=31, "
                                    "sharded by scene (LPT) over ranks",
                        "points_total": total_points, "points_rank0": n, "calls_rank0": int(len(csc)), "segments_rank0": S,
