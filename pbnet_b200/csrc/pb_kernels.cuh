@@ -1140,14 +1140,17 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
     int Q = *d_Q;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
-    // a warp takes 32 consecutive queries at a time: lane l fetches the header of query 32*qb + l (list entry, segment,
+    // a warp takes bs <= 32 consecutive queries at a time: lane l fetches the header of query bs*qb + l (list entry, segment,
     // labelled range, coordinates, own rank — a chain of three dependent loads) for all 32 at once; the queries are then
     // processed one after the other with the header broadcast by shuffles
-    for (int qb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qb * 32 < Q; qb += warps) {
+    // (bs = queries per warp and trip: 32 when there are enough queries to keep every warp busy that way, fewer on small
+    // problems, where spreading the queries over the warps matters more than batching the header loads)
+    const int bs = max(1, min(32, Q / warps));
+    for (int qb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qb * bs < Q; qb += warps) {
       int hp_ = -1, hl0 = 0, hl1 = 0, hrank = 0, hlast = -1;
       float hx = 0.f, hy = 0.f, hz = 0.f;
-      if (qb * 32 + lane < Q) {
-          hp_ = qlist[qb * 32 + lane];
+      if (lane < bs && qb * bs + lane < Q) {
+          hp_ = qlist[qb * bs + lane];
           int s = seg_of[hp_];
           if (!MIXED) {
               hl0 = sg.lab_start[s], hl1 = sg.lab_start[s + 1];
@@ -1159,7 +1162,7 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
           hx = xo[hp_], hy = yo[hp_], hz = zo[hp_];
           hrank = lpos[inv2[hp_]];
       }
-      const int nq = min(32, Q - qb * 32);
+      const int nq = min(bs, Q - qb * bs);
       for (int j = 0; j < nq; j++) {
         const int p = __shfl_sync(kFull, hp_, j);
         const int l0 = __shfl_sync(kFull, hl0, j), l1 = __shfl_sync(kFull, hl1, j);
