@@ -414,12 +414,8 @@ __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const 
                 else hi = mid;
             }
             int first = lo;
-            hi = e;
-            while (lo < hi) {  // first cell with key > khi
-                int mid = (lo + hi) >> 1;
-                if (__ldg(cc_key + mid) <= khi) lo = mid + 1;
-                else hi = mid;
-            }
+            // at most three cells (x'-1, x', x'+1) of that row follow: a short linear walk instead of a second search
+            while (lo < e && __ldg(cc_key + lo) <= khi) lo++;
             out = make_int2(first, lo);
         }
         runs9[t] = out;
