@@ -226,6 +226,18 @@ int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, int64_t n_ent
                         float score_thresh, int32_t npoint_thresh, float nms_thresh, int32_t *label, float *cluster_scores,
                         int64_t *cluster_sem, int32_t *cluster_proposal, int64_t cap, int64_t *n_clusters_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mesh vertex normals — the fourth op of the reference's extension module.  Replaces
+ *   void cal_normal_line(at::Tensor xyz, at::Tensor f_abc, at::Tensor n_xyz, int num_vtx, int num_face)
+ *        lib/PB_lib/src/normal/cal_normal.h:10, cal_normal.cu:114-160, bound at lib/PB_lib/src/PB_lib_api.cpp:10,
+ *        called from lib/PB_lib/torch_io/pbnet_ops.py:163 (offline preprocessing, datasets/scannetv2/decode_scannet.py)
+ * xyz f32[num_vtx][3], face i32[>=num_face][3] (only the first num_face faces take part), normal_xyz f32[num_vtx][3] (out):
+ * area-weighted mean of the normals of the faces listing the vertex, summed in ascending face order with the reference's
+ * fp32 arithmetic; vertices without faces get (0,0,1).  Host or device pointers; synchronous.
+ */
+int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *face, float *normal_xyz, int32_t num_vtx, int32_t num_face,
+                       int mem_kind, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

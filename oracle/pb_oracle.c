@@ -676,3 +676,56 @@ int pb_oracle_grid(const float *x, const float *y, const float *z, const float *
     return run(1, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, radius, min_pts, para_f, nv_flag,
                cluster_id, cluster_num, den_queue, center, clt_sem, n_clusters_out, st);
 }
+
+/* =================================================================================================
+ * Mesh vertex normals — restatement of lib/PB_lib/src/normal/cal_normal.cu (the fourth op of the PB_lib
+ * module, bound at PB_lib_api.cpp:10, called from lib/PB_lib/torch_io/pbnet_ops.py:163).
+ *
+ *   surface_normal_area (:43-76)   n = (B-A) x (C-A); "area" = |n|^2 / 2 (sic); n /= |n|
+ *   vertex_normal       (:78-112)  per vertex, over the faces 0..num_face-1 IN ORDER that list it (once per face):
+ *                                  s += n_f * area_f, a += area_f; a == 0 -> (0,0,1), else (s/a) / |s/a|
+ *
+ * Arithmetic as nvcc 12.9 contracts it for sm_100a (SASS of oracle/_ref): cross component = fma(u, v, -(w*t));
+ * dot(n,n) = fma(z,z, fma(y,y, x*x)) but linalg_two_norm = sqrt(fma(z,z, fma(x,x, y*y))) (the middle product is the
+ * plain multiply, as in the grouping predicate); accumulation s = fma(n, area, s); IEEE sqrt and division.
+ * ================================================================================================= */
+static inline float norm3(float x, float y, float z) { return sqrtf(fmaf(z, z, fmaf(x, x, y * y))); }
+
+int pb_oracle_normals(const float *xyz, const int *face, int num_vtx, int num_face, float *out) {
+    float *fn = (float *)malloc(sizeof(float) * 3 * (size_t)(num_face > 0 ? num_face : 1));
+    float *fa = (float *)malloc(sizeof(float) * (size_t)(num_face > 0 ? num_face : 1));
+    float *acc = (float *)calloc(4 * (size_t)(num_vtx > 0 ? num_vtx : 1), sizeof(float));
+    if (!fn || !fa || !acc) return -1;
+    for (int f = 0; f < num_face; f++) {
+        int ia = face[3 * f], ib = face[3 * f + 1], ic = face[3 * f + 2];
+        if (ia < 0 || ib < 0 || ic < 0 || ia >= num_vtx || ib >= num_vtx || ic >= num_vtx) { free(fn); free(fa); free(acc); return -2; }
+        float ax = xyz[3 * ib] - xyz[3 * ia], ay = xyz[3 * ib + 1] - xyz[3 * ia + 1], az = xyz[3 * ib + 2] - xyz[3 * ia + 2];
+        float bx = xyz[3 * ic] - xyz[3 * ia], by = xyz[3 * ic + 1] - xyz[3 * ia + 1], bz = xyz[3 * ic + 2] - xyz[3 * ia + 2];
+        float nx = fmaf(ay, bz, -(az * by)), ny = fmaf(az, bx, -(ax * bz)), nz = fmaf(ax, by, -(ay * bx));
+        fa[f] = fmaf(nz, nz, fmaf(ny, ny, nx * nx)) * 0.5f;
+        float l = norm3(nx, ny, nz);
+        fn[3 * f] = nx / l, fn[3 * f + 1] = ny / l, fn[3 * f + 2] = nz / l;
+        /* faces are visited in ascending order, so per-vertex sums see them in the reference's loop order */
+        int v[3] = {ia, ib, ic};
+        for (int j = 0; j < 3; j++) {
+            if ((j == 1 && v[1] == v[0]) || (j == 2 && (v[2] == v[0] || v[2] == v[1]))) continue; /* once per face */
+            float *s = acc + 4 * (size_t)v[j];
+            s[0] = fmaf(fn[3 * f], fa[f], s[0]);
+            s[1] = fmaf(fn[3 * f + 1], fa[f], s[1]);
+            s[2] = fmaf(fn[3 * f + 2], fa[f], s[2]);
+            s[3] = s[3] + fa[f];
+        }
+    }
+    for (int u = 0; u < num_vtx; u++) {
+        const float *s = acc + 4 * (size_t)u;
+        if (s[3] == 0.0f) {
+            out[3 * u] = 0.f, out[3 * u + 1] = 0.f, out[3 * u + 2] = 1.f;
+        } else {
+            float x = s[0] / s[3], y = s[1] / s[3], z = s[2] / s[3];
+            float l = norm3(x, y, z);
+            out[3 * u] = x / l, out[3 * u + 1] = y / l, out[3 * u + 2] = z / l;
+        }
+    }
+    free(fn); free(fa); free(acc);
+    return 0;
+}

@@ -115,3 +115,22 @@ def oracle_cluster(ins_offseted, ins_orig, sem, ins_bp, radius, min_pts, batch_s
     m18 = (np.ones(18) * min_pts).astype(np.int32)
     o = oracle_binary_cluster(ins_offseted, ins_orig, sem, ins_bp, r18, m18, 0.05, True, mode)
     return o["cluster_id"], o["cluster_num"], o["den_queue"] + 1, o["center"]
+
+
+def oracle_normals(xyz, face, num_face=None):
+    """Vertex normals as lib/PB_lib/src/normal/cal_normal.cu computes them (pb_oracle_normals in pb_oracle.c).
+    xyz f32[V,3], face i32[F,3]; ``num_face`` = how many leading faces take part (the reference wrapper passes V,
+    lib/PB_lib/torch_io/pbnet_ops.py:163)."""
+    L = _load()
+    L.pb_oracle_normals.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_float)]
+    L.pb_oracle_normals.restype = ctypes.c_int
+    xyz = _f32(xyz).reshape(-1, 3)
+    face = _i32(face).reshape(-1, 3)
+    nf = face.shape[0] if num_face is None else int(num_face)
+    assert 0 <= nf <= face.shape[0]
+    out = np.empty_like(xyz)
+    rc = L.pb_oracle_normals(_fp(xyz), _ip(face), xyz.shape[0], nf, _fp(out))
+    if rc != 0:
+        raise ValueError(f"pb_oracle_normals failed ({rc}): vertex index out of range")
+    return out

@@ -1400,3 +1400,71 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     *n_clusters_out = ctx->h_scalars[3];
     return PB_OK;
 }
+
+// =================================================================================================
+// mesh vertex normals (lib/PB_lib/src/normal/cal_normal.cu, PB_lib_api.cpp:10) — see pb_normals.cuh
+// =================================================================================================
+#include "pb_normals.cuh"
+
+extern "C" int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *face, float *normal_xyz, int32_t num_vtx,
+                                  int32_t num_face, int mem_kind, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (num_vtx < 0 || num_face < 0 || (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE)) return fail(ctx, PB_ERR_ARG, "bad argument");
+    if (num_vtx == 0) return PB_OK;
+    if (!xyz || !normal_xyz || (num_face > 0 && !face)) return fail(ctx, PB_ERR_ARG, "null pointer");
+    if ((long long)num_face * 3 >= (1LL << 31)) return fail(ctx, PB_ERR_ARG, "num_face too large");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    const bool host_io = mem_kind == PB_MEM_HOST;
+    const size_t V = (size_t)num_vtx, F = (size_t)num_face, NK = 3 * F;
+    float *d_xyz = nullptr, *d_out = nullptr, *fnormal = nullptr, *farea = nullptr;
+    int *d_face = nullptr, *d_err = nullptr;
+    uint64_t *key = nullptr, *key_alt = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        d_xyz = host_io ? a.get<float>(3 * V) : nullptr;
+        d_out = host_io ? a.get<float>(3 * V) : nullptr;
+        d_face = host_io ? a.get<int>(std::max<size_t>(NK, 1)) : nullptr;
+        fnormal = a.get<float>(std::max<size_t>(NK, 1)), farea = a.get<float>(std::max<size_t>(F, 1));
+        key = a.get<uint64_t>(std::max<size_t>(NK, 1)), key_alt = a.get<uint64_t>(std::max<size_t>(NK, 1));
+        d_err = a.get<int>(4);
+        cub_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)std::max<size_t>(NK, 1), 0, 64);
+        cub_tmp = a.get<char>(cub_bytes);
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+        }
+    }
+    const float *x_in = xyz;
+    const int *f_in = face;
+    float *o = normal_xyz;
+    if (host_io) {
+        PB_CUDA(cudaMemcpyAsync(d_xyz, xyz, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, st));
+        if (NK) PB_CUDA(cudaMemcpyAsync(d_face, face, sizeof(int) * NK, cudaMemcpyHostToDevice, st));
+        x_in = d_xyz, f_in = d_face, o = d_out;
+    }
+    PB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int) * 4, st));
+    const int T = 256;
+    const uint64_t *skey = key_alt;
+    if (num_face > 0) {
+        pbn::k_face_normals<<<div_up(num_face, T), T, 0, st>>>(x_in, f_in, num_face, num_vtx, fnormal, farea, key, d_err);
+        size_t cb = cub_bytes;
+        PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, (int)NK, 0, 64, st));
+        ctx->launches += 1 + 10;
+    }
+    pbn::k_vertex_normals<<<div_up(num_vtx, T), T, 0, st>>>(num_vtx, (long long)NK, skey, fnormal, farea, o);
+    ctx->launches++;
+    PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (host_io) PB_CUDA(cudaMemcpyAsync(normal_xyz, d_out, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_scalars[0]) return fail(ctx, PB_ERR_ARG, "face lists a vertex index outside [0, num_vtx)");
+    return PB_OK;
+}

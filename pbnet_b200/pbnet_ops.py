@@ -100,3 +100,25 @@ class CalIoUAndMasklabel(Function):
 
 
 cal_iou_and_masklabel = CalIoUAndMasklabel.apply
+
+
+class Get_normal_line(Function):
+    """Mirror of lib/PB_lib/torch_io/pbnet_ops.py:143-173: numpy ``xyz[V,3]``, ``face[F,3]`` -> float32 tensor ``[V,3]``.
+    Like the reference wrapper it passes ``num_face = V`` (:163 uses ``normal_line.shape[0]``), i.e. only the first V faces
+    take part; with fewer than V faces the reference reads out of bounds — here that is a ValueError."""
+
+    @staticmethod
+    def forward(ctx, xyz, face):
+        from .shim import PB_lib
+        xyz = torch.from_numpy(xyz).type(torch.float32).contiguous()
+        face = torch.from_numpy(face).type(torch.int32).contiguous()
+        normal_line = torch.zeros_like(xyz).type(torch.float32).contiguous()
+        PB_lib.cal_normal_line(xyz, face, normal_line, xyz.shape[0], normal_line.shape[0])
+        return normal_line
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None
+
+
+get_normal_line = Get_normal_line.apply

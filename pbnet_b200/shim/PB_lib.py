@@ -77,4 +77,18 @@ def cal_iou_and_masklabel(proposals_idx, proposals_offset, instance_labels, inst
          mask_scores_sigmoid, mask_label, mode)
 
 
-cal_normal_line = _not_on_path("cal_normal_line", "lib/PB_lib/src/normal/cal_normal.cu")
+def cal_normal_line(xyz, face, normal_line, num_vtx, num_face):
+    """lib/PB_lib/src/normal/cal_normal.h:10 — CPU (or CUDA) float32 ``xyz[V,3]``, int32 ``face[F,3]``, in-place
+    ``normal_line[V,3]``; ``num_face`` faces take part (the reference wrapper passes V, pbnet_ops.py:163)."""
+    from pbnet_b200._lib import PBError
+    ctx = default_context(xyz.device.index if xyz.is_cuda else (torch.cuda.current_device() if torch.cuda.is_available() else 0))
+    if int(num_face) > face.shape[0]:
+        raise ValueError(f"num_face={num_face} exceeds the {face.shape[0]} faces given (the reference would read out of bounds)")
+    for t, dt in ((xyz, torch.float32), (face, torch.int32), (normal_line, torch.float32)):
+        if t.dtype != dt or not t.is_contiguous() or t.is_cuda != xyz.is_cuda:
+            raise TypeError("cal_normal_line: contiguous float32 xyz / normal_line and int32 face on one device")
+    rc = ctx._lib.pb_cal_normal_line(ctx._h, xyz.data_ptr(), face.data_ptr(), normal_line.data_ptr(), int(num_vtx), int(num_face),
+                                     1 if xyz.is_cuda else 0, None)
+    if rc != 0:
+        raise PBError(rc, ctx._lib.pb_last_error(ctx._h).decode())
+    return None

@@ -98,8 +98,8 @@ def test_dropin_surfaces_match_reference():
     assert len(inspect.signature(PB_lib.binary_cluster).parameters) == 20
     assert list(inspect.signature(pbnet_ops.Cluster.forward).parameters)[1:] == [
         "ins_offseted", "ins_orig", "sem", "ins_bp", "radius", "min_pts", "batch_size"]
-    with pytest.raises(NotImplementedError):
-        PB_lib.cal_normal_line()  # dead code in the reference (both call sites commented out)
+    assert len(inspect.signature(PB_lib.cal_normal_line).parameters) == 5  # lib/PB_lib/src/normal/cal_normal.h:10
+    assert callable(pbnet_ops.get_normal_line)
     assert len(inspect.signature(PB_lib.get_iou).parameters) == 7
     assert len(inspect.signature(PB_lib.cal_iou_and_masklabel).parameters) == 10
     ref_ops = "/root/reference/lib/PB_lib/torch_io/pbnet_ops.py"

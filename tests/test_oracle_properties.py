@@ -102,3 +102,22 @@ def test_literal_equals_grid_random(seed, n, radius, min_pts):
     b = po.oracle_binary_cluster(p, po_, sem, seg, r18, m18, mode="literal")
     assert H.diff_report(a, b) == []
     check_invariants(a, sem, seg)
+
+
+def test_normals_oracle_geometry():
+    """oracle/pb_oracle.c::pb_oracle_normals (restatement of lib/PB_lib/src/normal/cal_normal.cu): a planar fan has the plane's
+    normal at every vertex, unreferenced vertices get (0,0,1), flipping the winding flips the normal, and only the first
+    num_face faces take part."""
+    import numpy as np
+    from oracle import pb_oracle as po
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.3, 0.2, 5.0]], np.float32)
+    face = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    n = po.oracle_normals(xyz, face)
+    assert np.array_equal(n, np.tile(np.array([0, 0, 1], np.float32), (5, 1)))
+    n = po.oracle_normals(xyz, face[:, ::-1].copy())
+    assert np.array_equal(n[:4], np.tile(np.array([0, 0, -1], np.float32), (4, 1))) and np.array_equal(n[4], [0, 0, 1])
+    tilted = np.array([[0, 0, 0], [1, 0, 1], [0, 1, 0]], np.float32)          # plane z = x, normal (-1,0,1)/sqrt2
+    n = po.oracle_normals(tilted, np.array([[0, 1, 2]], np.int32))
+    assert np.allclose(n, np.array([-1, 0, 1]) / np.sqrt(2), atol=1e-7)
+    n1 = po.oracle_normals(xyz, face, num_face=1)                             # vertex 3 is only in face 1 -> default
+    assert np.array_equal(n1[3], [0, 0, 1]) and np.array_equal(n1[1], [0, 0, 1])
