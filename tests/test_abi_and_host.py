@@ -110,3 +110,29 @@ def test_dropin_surfaces_match_reference():
         spec.loader.exec_module(m)
         assert m.PB_lib is PB_lib and callable(m.cluster)
     sys.modules.pop("PB_lib", None)
+
+
+def test_weak_scaling_set_extends_the_single_gpu_set():
+    """bench.py --scaling weak: the 312*N-scene set starts with the N=1 set (same sizes, same seeds), and the LPT
+    partition covers every scene exactly once with balanced point counts."""
+    from pbnet_b200 import scenes, workload
+    s1, s8 = scenes.scene_sizes(312), scenes.scene_sizes(312 * 8)
+    assert np.array_equal(s8[:312], s1)
+    shards = workload.shard_scenes(s8, 8)
+    flat = sorted(i for sh in shards for i in sh)
+    assert flat == list(range(312 * 8))
+    loads = np.array([int(s8[sh].sum()) for sh in shards], np.float64)
+    assert loads.max() / loads.min() < 1.01
+
+
+def test_local_scene_threshold_and_mask_helpers():
+    import torch
+    from pbnet_b200 import evalpost, grouping
+    from pbnet_b200.scenes import COUNT_MEAN
+    thr = grouping._big_thresholds(COUNT_MEAN)
+    want = (torch.tensor(COUNT_MEAN) * 0.2).numpy()      # network/PBNet.py:210: an fp32 tensor product
+    assert thr.dtype == np.float32 and np.array_equal(thr, want)
+    assert thr[2] == np.float32(783.4000244140625)        # 3917 * 0.2 in fp32
+    lab = torch.tensor([0, -100, 1, 1, 0], dtype=torch.int32)
+    m = evalpost.dense_masks(lab, 2)
+    assert m.tolist() == [[1, 0, 0, 0, 1], [0, 0, 1, 1, 0]]
