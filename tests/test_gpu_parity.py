@@ -208,3 +208,17 @@ def test_fused_class_loop_equals_reference_loop(ctx):
         assert torch.equal(f["clt_ctr"].reshape(-1).view(torch.int32), ctr.view(torch.int32))
         seen += 1
     assert seen == len(fused) and seen > 5
+
+
+def test_launch_count_of_a_dropin_call_stays_lean():
+    """Regression guard for the per-call latency of the drop-in path: one per-class call is ONE fixed sequence of
+    launches (single-pass scans, 32-bit LP keys) — 46 when this was written; the reference issues ~90 blocking CUDA
+    calls per segment plus one host round trip per BFS level (lib/PB_lib/src/pbnet/binary.cu)."""
+    from pbnet_b200 import scenes
+    from pbnet_b200.cluster import Context
+    ctx = Context(0)
+    sc = scenes.make_scene(5, 20000)
+    c = scenes.class_calls(sc, 3)[0]
+    H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=True)
+    assert 30 <= ctx.last_launch_count <= 50, ctx.last_launch_count
+    ctx.close()
