@@ -72,8 +72,11 @@ int64_t pb_last_launch_count(const pb_ctx *ctx);
  *      n_clusters_out  total clusters — host pointer
  * mem_kind  PB_MEM_HOST: data pointers are host memory (pinned memory makes the copies asynchronous);
  *           PB_MEM_DEVICE: device pointers on the context's device, results stay on the device.
- * stream    cudaStream_t or NULL for the context's own stream.  The call returns after the stream
- *           has been synchronised (n_clusters_out is valid on return).
+ * stream    cudaStream_t, or NULL: with PB_MEM_HOST the context's own (non-blocking) stream, with PB_MEM_DEVICE the
+ *           legacy default stream (so the call is ordered after the producers of the caller's buffers).  The call
+ *           returns after the stream has been synchronised (n_clusters_out is valid on return).
+ *           A context owns ONE scratch arena: a call on a different stream than the previous call first waits for
+ *           that stream (the asynchronous device-only entry points below may still be running on it).
  */
 int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo,
                       const float *yo, const float *zo, const int32_t *sem, const int32_t *seg_counts,

@@ -14,8 +14,9 @@
  *                        test is the exact predicate, so outputs are bit-identical to _literal.
  *
  * Pinning status: cross-checked against the compiled reference (oracle/_ref, built from
- * /root/reference by oracle/build_ref.py) on the GPU box — see tests/test_ref_crosscheck.py and
- * the committed fixtures under tests/golden/.
+ * /root/reference by oracle/build_ref.py) on the GPU box by tests/golden/make_golden.py (147/147 cases bit for
+ * bit, tests/golden/crosscheck_report_r01.json); the committed fixtures under tests/golden/ are re-checked on CPU by
+ * tests/test_oracle_golden.py and live against oracle/_ref by tests/test_gpu_shim.py.
  *
  * Reference map (file:line under /root/reference/lib/PB_lib/src/pbnet/):
  *   predicate            binary_cuda_functions.cu:305-308 (+ SASS FMA contraction), :85, :160-161

@@ -2,12 +2,14 @@
 GPU box with the gpurun snapshot."""
 from __future__ import annotations
 
+import glob
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "pb_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "pb_kernels.cuh"), os.path.join(HERE, "csrc", "pb_voxel.cuh"), os.path.join(HERE, "csrc", "pb_iou.cuh"), os.path.join(HERE, "..", "include", "pbnet_b200.h")]
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
+    os.path.join(HERE, "..", "include", "pbnet_b200.h")]
 SO = os.environ.get("PBNET_B200_SO", os.path.join(HERE, "libpbnet_b200.so"))  # override: kernel-variant experiments
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -157,6 +157,20 @@ class Context:
             center = new(3 * cap, torch.float32, np.float32, pinned)
         if clt_sem is None:
             clt_sem = new(cap, torch.int32, np.int32, pinned)
+        # caller-supplied outputs go to C as raw pointers: check them like the inputs
+        for name, a, dt, need in (("cluster_id", cluster_id, "int32", n), ("cluster_num", cluster_num, "int32", S),
+                                  ("degree", degree, "int32", n), ("center", center, "float32", 0), ("clt_sem", clt_sem, "int32", 0)):
+            if isinstance(a, torch.Tensor) != is_torch:
+                raise TypeError(f"{name}: outputs must be of the same kind (torch / numpy) as the inputs")
+            if is_torch:
+                ok = a.is_cuda == on_device and a.is_contiguous() and str(a.dtype) == "torch." + dt and a.dim() == 1 and (
+                    not on_device or a.device.index == self.device)
+            else:
+                ok = a.dtype == np.dtype(dt) and a.flags["C_CONTIGUOUS"] and a.ndim == 1 and a.flags["WRITEABLE"]
+            if not ok:
+                raise TypeError(f"{name}: need a contiguous 1-D {dt} output next to the inputs")
+            if a.shape[0] < need:
+                raise ValueError(f"{name}: length {a.shape[0]} < {need}")
         nclt = ctypes.c_int64(0)
         kind = PB_MEM_DEVICE if on_device else PB_MEM_HOST
         sptr = stream_handle(stream) if stream is not None else (stream_handle(torch.cuda.current_stream(x.device))

@@ -52,6 +52,7 @@ struct pb_ctx {
     Arena arena;
     std::string err;
     int64_t launches = 0;
+    cudaStream_t last_stream = nullptr;  // stream of the last call that used the arena
     bool profiling = false;
     cudaEvent_t ev[ST_COUNT + 1] = {};
     float stage_ms[ST_COUNT] = {};
@@ -85,6 +86,14 @@ int fail(pb_ctx *ctx, int code, const std::string &msg) {
     } while (0)
 
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// Stream of a call.  A NULL stream means "the context's own (non-blocking) stream" for host data; for DEVICE data it
+// means the legacy default stream, so that the call is ordered after whatever produced the caller's buffers (the
+// context stream is created with cudaStreamNonBlocking and would not wait for them).
+inline cudaStream_t pick_stream(pb_ctx *ctx, void *stream_v, bool device_data) {
+    if (stream_v) return (cudaStream_t)stream_v;
+    return device_data ? cudaStreamLegacy : ctx->stream;
+}
 
 struct Scan {  // exclusive scan of int32, n known on host or (upper bound on host, exact on device)
     int *block_sums = nullptr;
@@ -277,6 +286,10 @@ static void invalidate_scene_state();  // the arena is about to be reused (pb_lo
 namespace {
 int ensure_arena(pb_ctx *ctx, size_t need, cudaStream_t st) {
     invalidate_scene_state();
+    // The arena is one scratch area reset per call: work still pending on ANOTHER stream (an earlier asynchronous call)
+    // must finish before this call overwrites it.  Calls that stay on one stream are ordered by the stream itself.
+    if (ctx->last_stream && ctx->last_stream != st) PB_CUDA(cudaStreamSynchronize(ctx->last_stream));
+    ctx->last_stream = st;
     if (need > ctx->arena.cap) {
         PB_CUDA(cudaStreamSynchronize(st));
         if (ctx->arena.base) PB_CUDA(cudaFree(ctx->arena.base));
@@ -555,7 +568,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     if (S > 0 && !cluster_num) return fail(ctx, PB_ERR_ARG, "null cluster_num");
     const bool host_io = mem_kind == PB_MEM_HOST;
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, !host_io);
     if (n == 0) {
         if (S > 0) {
             if (host_io) std::memset(cluster_num, 0, sizeof(int) * S);
@@ -804,7 +817,7 @@ extern "C" int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int s
     if (n == 0) return PB_OK;
     if (!coords || !vcoords || !index || !inverse || !order || !vox_start || cap < 1) return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, mem_kind == PB_MEM_DEVICE);
     const bool host_io = mem_kind == PB_MEM_HOST;
     const size_t N = (size_t)n, esz = coord_f64 ? 8 : 4;
     int64_t &L = ctx->launches;
@@ -896,7 +909,7 @@ extern "C" int pb_voxel_rows(pb_ctx *ctx, const float *rows, int64_t n_rows, int
     if (V == 0) return PB_OK;
     if (!rows || !order || !vox_start || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, mem_kind == PB_MEM_DEVICE);
     const bool host_io = mem_kind == PB_MEM_HOST;
     const float *d_rows = rows;
     const int *d_order = order, *d_vs = vox_start;
@@ -939,7 +952,7 @@ extern "C" int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, 
     if (n == 0) return PB_OK;
     if (!vfeat || !inverse || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, mem_kind == PB_MEM_DEVICE);
     const bool host_io = mem_kind == PB_MEM_HOST;
     const float *d_v = vfeat;
     const long long *d_inv = reinterpret_cast<const long long *>(inverse);
@@ -992,7 +1005,7 @@ extern "C" int pb_cal_iou_and_masklabel(pb_ctx *ctx, const int32_t *proposals_id
         (mode == 1 && !mask_scores_sigmoid))
         return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     int rc = ensure_arena(ctx, sizeof(int) * (size_t)nProposal + 4096, st);
     if (rc) return rc;
     int *ptotal = ctx->arena.get<int>((size_t)nProposal);
@@ -1086,7 +1099,7 @@ extern "C" int pb_local_scenes_plan(pb_ctx *ctx, const int32_t *cluster_id, cons
     }
     if (!cluster_id || !center) return fail(ctx, PB_ERR_ARG, "null data pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     const bool train = ins_label != nullptr;
     const size_t N = (size_t)n;
     int64_t &L = ctx->launches;
@@ -1179,7 +1192,7 @@ extern "C" int pb_local_scenes_fill(pb_ctx *ctx, const int64_t *point_map, int64
     if (!s.ready || s.owner != ctx) return fail(ctx, PB_ERR_ARG, "pb_local_scenes_fill must directly follow a successful pb_local_scenes_plan on this thread");
     if (!prop_offsets) return fail(ctx, PB_ERR_ARG, "null prop_offsets");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     if (s.P == 0) {
         PB_CUDA(cudaMemsetAsync(prop_offsets, 0, sizeof(int64_t), st));
         return PB_OK;
@@ -1212,7 +1225,7 @@ extern "C" int pb_get_proposal(pb_ctx *ctx, const int64_t *prop_offsets, int64_t
     *n_kept_out = 0, *n_nonempty_out = 0;
     if (!proposals_offset) return fail(ctx, PB_ERR_ARG, "null proposals_offset");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     if (n_proposals == 0 || n_entries == 0) {
         PB_CUDA(cudaMemsetAsync(proposals_offset, 0, sizeof(int64_t), st));
         return PB_OK;
@@ -1256,7 +1269,7 @@ extern "C" int pb_scene_features(pb_ctx *ctx, const float *point_feat, int32_t C
     if (n_entries == 0) return PB_OK;
     if (!point_feat || !sem_score || !index || !prop_id || !prop_sem || !dpn || !out) return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     const int T = 256;
     int grid = (int)std::min<int64_t>((n_entries * 32 + T - 1) / T, 148 * 32);
     pbs::k_scene_feat<<<grid, T, 0, st>>>(n_entries, C, n_cls, point_feat, sem_score, (const long long *)index, prop_id, prop_sem, dpn, out);
@@ -1295,7 +1308,7 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     if (n3 == 0) return PB_OK;
     if (!label || !superpoint || !sem_table) return fail(ctx, PB_ERR_ARG, "null pointer");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
     const int T = 256;
     int64_t &L = ctx->launches;
     if (P == 0 || M == 0) {
@@ -1416,7 +1429,7 @@ extern "C" int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *
     if (!xyz || !normal_xyz || (num_face > 0 && !face)) return fail(ctx, PB_ERR_ARG, "null pointer");
     if ((long long)num_face * 3 >= (1LL << 31)) return fail(ctx, PB_ERR_ARG, "num_face too large");
     PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t st = pick_stream(ctx, stream_v, mem_kind == PB_MEM_DEVICE);
     const bool host_io = mem_kind == PB_MEM_HOST;
     const size_t V = (size_t)num_vtx, F = (size_t)num_face, NK = 3 * F;
     float *d_xyz = nullptr, *d_out = nullptr, *fnormal = nullptr, *farea = nullptr;

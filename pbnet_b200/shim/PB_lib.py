@@ -41,13 +41,6 @@ def binary_cluster(x, y, z, l1_norm, index_mapper, xo, yo, zo, sem, ins_bp, radi
     return None
 
 
-def _not_on_path(name, where):
-    def f(*a, **k):
-        raise NotImplementedError(f"PB_lib.{name} ({where}) is outside the grouping hot path; see DESIGN.md 'next'")
-    f.__name__ = name
-    return f
-
-
 def _iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, n_inst, n_prop,
          mask_scores, mask_label, mode):
     from pbnet_b200._lib import PBError
@@ -87,8 +80,10 @@ def cal_normal_line(xyz, face, normal_line, num_vtx, num_face):
     for t, dt in ((xyz, torch.float32), (face, torch.int32), (normal_line, torch.float32)):
         if t.dtype != dt or not t.is_contiguous() or t.is_cuda != xyz.is_cuda:
             raise TypeError("cal_normal_line: contiguous float32 xyz / normal_line and int32 face on one device")
+    from pbnet_b200.cluster import stream_handle
+    st = stream_handle(torch.cuda.current_stream(xyz.device)) if xyz.is_cuda else None  # ordered after xyz / face's producers
     rc = ctx._lib.pb_cal_normal_line(ctx._h, xyz.data_ptr(), face.data_ptr(), normal_line.data_ptr(), int(num_vtx), int(num_face),
-                                     1 if xyz.is_cuda else 0, None)
+                                     1 if xyz.is_cuda else 0, st)
     if rc != 0:
         raise PBError(rc, ctx._lib.pb_last_error(ctx._h).decode())
     return None

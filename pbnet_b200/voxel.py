@@ -95,14 +95,22 @@ def voxel_map(coordinates, quantization_size=None, batch=None) -> VoxelMap:
     return vm
 
 
-def voxel_rows(rows: torch.Tensor, vm: VoxelMap, mode: str = "pick") -> torch.Tensor:
+def _out_like(out, shape, device):
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or out.device != device or not out.is_contiguous():
+        raise TypeError(f"out: need a contiguous float32 tensor of shape {tuple(shape)} on {device}")
+    return out
+
+
+def voxel_rows(rows: torch.Tensor, vm: VoxelMap, mode: str = "pick", out: torch.Tensor | None = None) -> torch.Tensor:
     """Per-voxel reduction of point rows: 'pick' (representative), 'mean', 'sum' (ascending point order)."""
     L = _bind()
     rows = rows.to(torch.float32).contiguous()
     n, C = int(rows.shape[0]), int(rows.shape[1])
     ctx = _ctx_for(rows)
     V = vm.n_voxels
-    out = torch.empty((V, C), dtype=torch.float32, device=rows.device)
+    out = _out_like(out, (V, C), rows.device)
     kind = PB_MEM_DEVICE if rows.is_cuda else PB_MEM_HOST
     sptr = stream_handle(torch.cuda.current_stream(rows.device)) if rows.is_cuda else None
     order, vstart = vm.order.to(rows.device), vm.vox_start.to(rows.device)
@@ -112,14 +120,14 @@ def voxel_rows(rows: torch.Tensor, vm: VoxelMap, mode: str = "pick") -> torch.Te
     return out
 
 
-def devoxelize_raw(vfeat: torch.Tensor, inverse: torch.Tensor) -> torch.Tensor:
+def devoxelize_raw(vfeat: torch.Tensor, inverse: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     L = _bind()
     vfeat = vfeat.to(torch.float32).contiguous()
     inverse = inverse.to(device=vfeat.device, dtype=torch.int64).contiguous()
     V, C = int(vfeat.shape[0]), int(vfeat.shape[1])
     n = int(inverse.shape[0])
     ctx = _ctx_for(vfeat)
-    out = torch.empty((n, C), dtype=torch.float32, device=vfeat.device)
+    out = _out_like(out, (n, C), vfeat.device)
     kind = PB_MEM_DEVICE if vfeat.is_cuda else PB_MEM_HOST
     sptr = stream_handle(torch.cuda.current_stream(vfeat.device)) if vfeat.is_cuda else None
     rc = L.pb_devoxelize(ctx._h, vfeat.data_ptr(), V, C, inverse.data_ptr(), n, out.data_ptr(), kind, sptr)
