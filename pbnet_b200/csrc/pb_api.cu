@@ -4,7 +4,8 @@
 // (lib/PB_lib/src/pbnet/cluster.cu:57-110) and BINARY::Solver's ~90 synchronous
 // cudaMalloc/cudaMemcpy/cudaFree calls per segment plus one host round trip per BFS level
 // (lib/PB_lib/src/pbnet/binary.cu).  Here ALL segments of ALL calls go through one fixed sequence
-// of ~35 launches on one stream with a single host synchronisation at the end.
+// of ~25 launches per chunk (two chunk streams for large batches); the host reads three integers (the cell extents that
+// size the sort keys) in between and synchronises once at the end.
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
@@ -17,6 +18,7 @@
 
 #include "../../include/pbnet_b200.h"
 #include "pb_kernels.cuh"
+#include "pb_fused.cuh"
 
 namespace {
 
@@ -69,6 +71,7 @@ struct pb_ctx {
     unsigned long long *h_chunk_counters = nullptr;
     size_t h_chunk_cap = 0;
     std::vector<cudaEvent_t> chunk_ev;
+    std::vector<cudaEvent_t> front_ev, deg_ev;  // per chunk: extents delivered / the always-on pair around k_degree
 };
 
 namespace {
@@ -149,6 +152,8 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->front_ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->deg_ev) cudaEventDestroy(ev);
     if (ctx->h_chunk_scalars) cudaFreeHost(ctx->h_chunk_scalars);
     if (ctx->h_chunk_counters) cudaFreeHost(ctx->h_chunk_counters);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -189,25 +194,55 @@ extern "C" float pb_stage_ms(const pb_ctx *ctx, int i) { return (ctx && i >= 0 &
 extern "C" int64_t pb_counter(const pb_ctx *ctx, int i) { return (ctx && i >= 0 && i < 16) ? ctx->counters[i] : 0; }
 
 // ------------------------------------------------------------------------------------------------
+// ====================================================================================================
+// grouping path: workspace, launch sequence
+// ====================================================================================================
 namespace {
 
-struct Work {  // all device buffers of one call; laid out by plan() on the arena
-    // inputs (device copies when the caller's data is on the host)
+constexpr int kTileItems = 16;                     // items per thread of the tile kernels (large path)
+constexpr int kTile = pb::kTB * kTileItems;        // 4096 points per tile
+
+// Host-built, segment-aligned tile table of one chunk (pb::TileTab): [begin | count | seg | first | hslot | srow] x T
+struct TileHost {
+    std::vector<int> buf;
+    int T = 0, slots = 0, rows = 0;
+};
+
+void build_tiles(const int *start, int S, int tile, TileHost &th) {
+    int T = 0;
+    for (int s = 0; s < S; s++) T += (start[s + 1] - start[s] + tile - 1) / tile;
+    th.T = T, th.slots = 0, th.rows = 0;
+    th.buf.assign((size_t)6 * std::max(T, 1), 0);
+    int *begin = th.buf.data(), *count = begin + T, *seg = count + T, *first = seg + T, *hslot = first + T, *srow = hslot + T;
+    int t = 0;
+    for (int s = 0; s < S; s++) {
+        int n = start[s + 1] - start[s];
+        int nt = (n + tile - 1) / tile;
+        int slot = nt >= 2 ? th.slots++ : -1;
+        for (int k = 0; k < nt; k++, t++) {
+            begin[t] = start[s] + k * tile;
+            count[t] = std::min(tile, n - k * tile);
+            seg[t] = s;
+            first[t] = t - k;
+            hslot[t] = slot;
+            srow[t] = nt >= 2 ? th.rows++ : -1;
+        }
+    }
+}
+
+struct Work {  // all device buffers of one chunk; laid out by plan() on the arena
+    // inputs / outputs (device copies when the caller's data is on the host)
     float *x, *y, *z, *xo, *yo, *zo;
     int *sem;
-    // outputs
-    int *cluster_id, *cluster_num, *degree, *clt_sem;
-    float *center;
-    // tables
-    float *radius, *thresh;
-    int *min_pts;
-    int *seg_start, *seg_call_first;
+    int *cluster_id, *cluster_num, *degree;
+    // header block (one H2D copy): seg_start[S+1] | call_first[S] | tile table 6T | radius 18 | thresh 18 | min_pts 18
+    int *hdr;
+    size_t hdr_cap;
     pb::SegArrays sg;
     // per point
-    int *seg_of, *fcell_of, *row_of, *deg_sorted, *head_f, *head_c, *head_r, *ex_f, *ex_c, *ex_r, *raw_label, *flag, *gid_at,
-        *qflag, *qpos, *labflag, *lpos, *qlist, *inv2;
-    uint64_t *key1, *key1_alt, *key2, *key2_alt;
-    uint32_t *val, *order1, *order2;
+    int *seg_of, *fcell_of, *row_of, *deg_sorted, *raw_label, *flag, *gid_at, *lpos, *qlist, *inv2;
+    uint64_t *key1[2];
+    uint32_t *key2[2], *v1[2], *v2[2];
     float4 *pts4, *lab4, *box_lo, *box_hi, *box2_lo, *box2_hi;
     float *sx, *sy, *sz;
     // per fine cell / coarse cell (upper bound N)
@@ -218,22 +253,26 @@ struct Work {  // all device buffers of one call; laid out by plan() on the aren
     int *rep, *raw_count, *keep, *kscan, *clt_seg;
     // mixed-class mode only: per (fine cell, class) and per (segment, class) tables
     int *cell_min18, *comp_min18, *cell_gid18, *cnt18, *pos18, *lab_start18, *seg_lastlab;
-    // scalars
-    int *d_scalars;  // [0] err [1] C [2] R [3] K [4] Q [5] L
+    // scalars: [0] err [1] F [2] R [3] K [4] Q [5] L [6] Cc [7] rows [8] mixed scan total [9] centre ticket [10..12] extents
+    int *d_scalars;
     unsigned long long *d_counters;
-    int *scan_blocks;
-    unsigned long long *scan_state;  // single-pass scan: one word per tile + the ticket counter behind them
+    unsigned long long *scan_state;  // k_scan_onepass: one word per tile + the ticket counter behind them
     size_t scan_tiles;
-    void *cub_tmp;
-    size_t cub_bytes;
+    unsigned long long *gridA, *gridB, *rel_state;  // look-back words of k_grid_build / k_relabel_scan [T]
+    int *tickets;                    // [16] tile tickets: 0..9 sort passes (sort*5 + pass), 10 grid build, 11 relabel
+    unsigned *sort_state;            // [(P1+P2)][rows][kBins]
+    unsigned *hist;                  // [slots][(P1+P2)*kBins]
+    // zero-initialised region A (before the front kernels) and B (sort state + histograms, sized after the key layout is known)
+    char *zeroA_begin, *zeroA_end, *ffA_begin, *ffA_end, *zeroB_begin;
+    size_t zeroB_cap;
 };
 
-void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
+// T_max / rows_max / slots_max: bounds of the tile table of any chunk planned on this slot
+void plan(Arena &a, Work &w, long long n, int S, int T_max, int rows_max, int slots_max, bool host_io, bool mixed) {
     size_t N = (size_t)n;
     if (mixed) {
         w.cell_min18 = a.get<int>(N * pb::kCls); w.comp_min18 = a.get<int>(N * pb::kCls); w.cell_gid18 = a.get<int>(N * pb::kCls);
-        w.cnt18 = a.get<int>((size_t)S * pb::kCls + 1); w.pos18 = a.get<int>((size_t)S * pb::kCls + 1);
-        w.lab_start18 = a.get<int>((size_t)S * pb::kCls + 1); w.seg_lastlab = a.get<int>(S);
+        w.pos18 = a.get<int>((size_t)S * pb::kCls + 1); w.lab_start18 = a.get<int>((size_t)S * pb::kCls + 1);
     }
     if (host_io) {
         w.x = a.get<float>(N); w.y = a.get<float>(N); w.z = a.get<float>(N);
@@ -243,21 +282,19 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
         w.cluster_num = a.get<int>(S);
         w.degree = a.get<int>(N);
     }
+    w.hdr_cap = (size_t)2 * S + 1 + (size_t)6 * std::max(T_max, 1) + 54;
+    w.hdr = a.get<int>(w.hdr_cap);
     w.clt_seg = a.get<int>(N);
-    w.seg_start = a.get<int>(S + 1); w.seg_call_first = a.get<int>(S);
-    w.sg.enc_min_s = a.get<unsigned>(3 * S); w.sg.enc_min_o = a.get<unsigned>(3 * S); w.sg.enc_max_o = a.get<unsigned>(3 * S);
     w.sg.cls = a.get<int>(S); w.sg.min_pts = a.get<int>(S); w.sg.r2 = a.get<float>(S); w.sg.inv_h = a.get<float>(S);
     w.sg.min_s = a.get<float>(3 * S); w.sg.min_o = a.get<float>(3 * S); w.sg.inv_g = a.get<float>(S);
-    w.sg.cc_start = a.get<int>(S + 1); w.sg.lab_start = a.get<int>(S + 1); w.sg.id_base = a.get<int>(S);
+    w.sg.cc_start = a.get<int>(S + 1); w.sg.cc_end = a.get<int>(S + 1); w.sg.id_base = a.get<int>(S);
     w.sg.k_base = a.get<int>(S); w.sg.cluster_num = a.get<int>(S);
     w.seg_of = a.get<int>(N); w.fcell_of = a.get<int>(N); w.row_of = a.get<int>(N); w.deg_sorted = a.get<int>(N);
-    w.head_f = a.get<int>(N); w.head_c = a.get<int>(N); w.head_r = a.get<int>(N);
-    w.ex_f = a.get<int>(N); w.ex_c = a.get<int>(N); w.ex_r = a.get<int>(N);
-    w.raw_label = a.get<int>(N); w.flag = a.get<int>(N); w.gid_at = a.get<int>(N);
-    w.qflag = a.get<int>(N); w.qpos = a.get<int>(N); w.labflag = a.get<int>(N); w.lpos = a.get<int>(N); w.qlist = a.get<int>(N);
-    w.inv2 = a.get<int>(N);
-    w.key1 = a.get<uint64_t>(N); w.key1_alt = a.get<uint64_t>(N); w.key2 = a.get<uint64_t>(N); w.key2_alt = a.get<uint64_t>(N);
-    w.val = a.get<uint32_t>(N); w.order1 = a.get<uint32_t>(N); w.order2 = a.get<uint32_t>(N);
+    w.raw_label = a.get<int>(N); w.gid_at = a.get<int>(N);
+    w.lpos = a.get<int>(N); w.qlist = a.get<int>(N); w.inv2 = a.get<int>(N);
+    for (int k = 0; k < 2; k++) {
+        w.key1[k] = a.get<uint64_t>(N); w.key2[k] = a.get<uint32_t>(N); w.v1[k] = a.get<uint32_t>(N); w.v2[k] = a.get<uint32_t>(N);
+    }
     w.pts4 = a.get<float4>(N); w.lab4 = a.get<float4>(N);
     w.sx = a.get<float>(N + 2); w.sy = a.get<float>(N + 2); w.sz = a.get<float>(N + 2);
     w.box_lo = a.get<float4>(N / 32 + 2); w.box_hi = a.get<float4>(N / 32 + 2);
@@ -266,17 +303,29 @@ void plan(Arena &a, Work &w, long long n, int S, bool host_io, bool mixed) {
     w.parent = a.get<int>(N); w.cell_hp = a.get<int>(N); w.cell_minhp = a.get<int>(N); w.cell_first = a.get<int>(N);
     w.comp_min = a.get<int>(N); w.cell_gid = a.get<int>(N); w.fcell_key = a.get<uint64_t>(N); w.cc_key = a.get<uint64_t>(N);
     w.runs9 = a.get<int2>(N * pb::kRuns);
-    w.rep = a.get<int>(N); w.raw_count = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
-    w.d_scalars = a.get<int>(16);
+    w.rep = a.get<int>(N); w.keep = a.get<int>(N); w.kscan = a.get<int>(N);
+    // ---- 0xff-initialised region: encoded minima (+ mixed: last labelled point per segment)
+    w.ffA_begin = reinterpret_cast<char *>(a.get<char>(0));
+    w.sg.enc_min_s = a.get<unsigned>(3 * S); w.sg.enc_min_o = a.get<unsigned>(3 * S);
+    w.seg_lastlab = a.get<int>(mixed ? S : 1);
+    w.ffA_end = reinterpret_cast<char *>(a.get<char>(0));
+    // ---- zero-initialised region A
+    w.zeroA_begin = reinterpret_cast<char *>(a.get<char>(0));
+    w.d_scalars = a.get<int>(32);
     w.d_counters = a.get<unsigned long long>(8);
-    w.scan_blocks = a.get<int>(std::max(N, (size_t)S * pb::kCls) / pb::kScanTile + 2);
+    w.tickets = a.get<int>(16);
+    w.sg.enc_max_s = a.get<unsigned>(3 * S); w.sg.enc_max_o = a.get<unsigned>(3 * S);
+    w.flag = a.get<int>(N); w.raw_count = a.get<int>(N);
     w.scan_tiles = std::max(N, (size_t)S * pb::kCls) / pb::kScanTile + 2;
     w.scan_state = a.get<unsigned long long>(w.scan_tiles + 1);
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
-    w.cub_bytes = bytes;
-    w.cub_tmp = a.get<char>(bytes);
+    w.gridA = a.get<unsigned long long>(std::max(T_max, 1)); w.gridB = a.get<unsigned long long>(std::max(T_max, 1));
+    w.rel_state = a.get<unsigned long long>(std::max(T_max, 1));
+    w.cnt18 = a.get<int>(mixed ? (size_t)S * pb::kCls + 1 : 1);
+    w.zeroA_end = reinterpret_cast<char *>(a.get<char>(0));
+    // ---- zero-initialised region B: sort look-back state + digit histograms for up to 2*kMaxPasses passes
+    w.zeroB_begin = reinterpret_cast<char *>(a.get<char>(0));
+    w.zeroB_cap = ((size_t)std::max(rows_max, 1) + (size_t)std::max(slots_max, 1)) * 2 * pb::kMaxPasses * pb::kBins * sizeof(unsigned);
+    a.get<char>(w.zeroB_cap);
 }
 
 }  // namespace
@@ -316,6 +365,7 @@ void launch_scan(cudaStream_t st, const int *in, int n_host, const int *n_dev, i
 }
 }  // namespace
 
+
 namespace {
 
 struct ChunkIO {          // one chunk = a run of consecutive calls; all pointers already offset to the chunk
@@ -325,35 +375,43 @@ struct ChunkIO {          // one chunk = a run of consecutive calls; all pointer
     int n, S;
     const int *start;       // host [S+1], local to the chunk
     const int *call_first;  // host [S], local to the chunk
+    const TileHost *tiles;
     float *center_out;      // device, capacity 3*n floats (chunk-private region)
     int *clt_sem_out;       // device, capacity n
     int *h_scalars;         // pinned [16]
     unsigned long long *h_counters;  // pinned [8]
     cudaEvent_t *ev;        // ST_COUNT+1 events or nullptr
+    cudaEvent_t ev_front;   // recorded after the extents are on their way to the host
+    cudaEvent_t ev_deg[2];  // always-on pair around k_degree
 };
 
-// Enqueues the whole launch sequence of one chunk on `st`.  No host synchronisation.
-template <bool MIXED>
-int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assign_lp, const float *d_radius,
-                  const int *d_min_pts, const float *d_thresh, cudaStream_t st, int64_t &L) {
-    const int n = io.n, S = io.S;
-    const bool prof = io.ev != nullptr;
-    int stage_ev = 0;
-    auto mark = [&]() {
-        if (prof) cudaEventRecord(io.ev[stage_ev], st);
-        stage_ev++;
-    };
-    const int T = 256;
-    const int gN = div_up(n, T);
-    const int gS = div_up(S + 1, T);
-    // grid-stride kernels: one CTA wave on large problems, no more CTAs than warp-sized work items on small ones
-    const int gPersist = std::min(148 * 8, std::max(1, div_up(n, 8)));
-    w.sg.start = w.seg_start;
+struct ChunkDev {  // device views of the header block, valid after enqueue_front
+    int *seg_start, *call_first;
+    pb::TileTab tt;
+    float *radius, *thresh;
+    int *min_pts;
+};
 
-    mark();  // start of H2D
-    const float *dx = io.x, *dy = io.y, *dz = io.z, *dxo = io.xo, *dyo = io.yo, *dzo = io.zo;
-    const int *dsem = io.sem;
-    int *d_cluster_id = io.cluster_id, *d_cluster_num = io.cluster_num, *d_degree = io.degree;
+ChunkDev header_views(const Work &w, int S, int T) {
+    ChunkDev d;
+    int *p = w.hdr;
+    d.seg_start = p, p += S + 1;
+    d.call_first = p, p += S;
+    const int Tz = std::max(T, 1);
+    d.tt.begin = p, d.tt.count = p + Tz, d.tt.seg = p + 2 * Tz, d.tt.first = p + 3 * Tz, d.tt.hslot = p + 4 * Tz, d.tt.srow = p + 5 * Tz;
+    d.tt.T = T;
+    p += 6 * Tz;
+    d.radius = reinterpret_cast<float *>(p), p += 18;
+    d.thresh = reinterpret_cast<float *>(p), p += 18;
+    d.min_pts = p;
+    return d;
+}
+
+// Front of a chunk: copies, initialisation, validation + bounding boxes, per-segment parameters, cell extents -> host.
+int enqueue_front(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, bool mixed, const float *radius, const int *min_pts,
+                  const float *thresh, cudaStream_t st, int64_t &L, std::vector<int> &hdr_host) {
+    const int n = io.n, S = io.S, T = io.tiles->T;
+    if (io.ev) cudaEventRecord(io.ev[ST_H2D], st);
     if (host_io) {
         size_t fb = sizeof(float) * (size_t)n;
         PB_CUDA(cudaMemcpyAsync(w.x, io.x, fb, cudaMemcpyHostToDevice, st));
@@ -363,29 +421,180 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
         PB_CUDA(cudaMemcpyAsync(w.yo, io.yo, fb, cudaMemcpyHostToDevice, st));
         PB_CUDA(cudaMemcpyAsync(w.zo, io.zo, fb, cudaMemcpyHostToDevice, st));
         PB_CUDA(cudaMemcpyAsync(w.sem, io.sem, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
-        dx = w.x, dy = w.y, dz = w.z, dxo = w.xo, dyo = w.yo, dzo = w.zo, dsem = w.sem;
-        d_cluster_id = w.cluster_id, d_cluster_num = w.cluster_num, d_degree = w.degree;
     }
-    // segment tables: pageable host memory -> staged synchronously by the driver, safe to reuse after return
-    PB_CUDA(cudaMemcpyAsync(w.seg_start, io.start, sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(w.seg_call_first, io.call_first, sizeof(int) * S, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemsetAsync(w.sg.enc_min_s, 0xff, sizeof(unsigned) * 3 * S, st));
-    PB_CUDA(cudaMemsetAsync(w.sg.enc_min_o, 0xff, sizeof(unsigned) * 3 * S, st));
-    PB_CUDA(cudaMemsetAsync(w.sg.enc_max_o, 0x00, sizeof(unsigned) * 3 * S, st));
-    PB_CUDA(cudaMemsetAsync(w.d_scalars, 0, sizeof(int) * 16, st));
-    PB_CUDA(cudaMemsetAsync(w.d_counters, 0, sizeof(unsigned long long) * 8, st));
-    PB_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int) * (size_t)n, st));
-    PB_CUDA(cudaMemsetAsync(w.raw_count, 0, sizeof(int) * (size_t)n, st));
-    if (MIXED) {
-        PB_CUDA(cudaMemsetAsync(w.cnt18, 0, sizeof(int) * ((size_t)S * pb::kCls + 1), st));
-        PB_CUDA(cudaMemsetAsync(w.seg_lastlab, 0xff, sizeof(int) * S, st));
+    // header block: pageable host memory -> staged synchronously by the driver, safe to reuse after return
+    const int Tz = std::max(T, 1);
+    hdr_host.assign((size_t)2 * S + 1 + (size_t)6 * Tz + 54, 0);
+    {
+        int *p = hdr_host.data();
+        std::memcpy(p, io.start, sizeof(int) * (S + 1)), p += S + 1;
+        std::memcpy(p, io.call_first, sizeof(int) * S), p += S;
+        if (T > 0) std::memcpy(p, io.tiles->buf.data(), sizeof(int) * (size_t)6 * T);
+        p += 6 * Tz;
+        std::memcpy(p, radius, 18 * sizeof(float)), p += 18;
+        std::memcpy(p, thresh, 18 * sizeof(float)), p += 18;
+        std::memcpy(p, min_pts, 18 * sizeof(int));
     }
+    PB_CUDA(cudaMemcpyAsync(w.hdr, hdr_host.data(), sizeof(int) * hdr_host.size(), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(w.ffA_begin, 0xff, w.ffA_end - w.ffA_begin, st));
+    PB_CUDA(cudaMemsetAsync(w.zeroA_begin, 0, w.zeroA_end - w.zeroA_begin, st));
+    if (mixed) {  // per (fine cell, class) tables start at "no HP"
+        PB_CUDA(cudaMemsetAsync(w.cell_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
+        PB_CUDA(cudaMemsetAsync(w.comp_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
+    }
+    ChunkDev d = header_views(w, S, T);
+    w.sg.start = d.seg_start;
+    const float *dx = host_io ? w.x : io.x, *dy = host_io ? w.y : io.y, *dz = host_io ? w.z : io.z;
+    const float *dxo = host_io ? w.xo : io.xo, *dyo = host_io ? w.yo : io.yo, *dzo = host_io ? w.zo : io.zo;
+    const int *dsem = host_io ? w.sem : io.sem;
+    if (io.ev) cudaEventRecord(io.ev[ST_PREP], st);
+    pb::k_prep<kTileItems><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.d_scalars);
+    pb::k_seg_params<<<div_up(std::max(S, 1), 256), 256, 0, st>>>(S, w.sg, dsem, d.radius, d.min_pts, w.d_scalars + 10, w.d_scalars);
+    L += 2;
+    PB_CUDA(cudaMemcpyAsync(io.h_scalars + 10, w.d_scalars + 10, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaEventRecord(io.ev_front, st));
+    return PB_OK;
+}
+
+template <typename KeyT>
+void launch_sort_passes(Work &w, const pb::TileTab &tt, const int *seg_start, const pb::PassPlan &p1, const pb::PassPlan &p2,
+                        int rows, cudaStream_t st, int64_t &L, int which) {
+    // which: 0 = sort 1 only (KeyT = its key type), 1 = sort 2 only, 2 = both (same key type)
+    const int stride = (p1.npass + p2.npass) * pb::kBins;
+    const size_t state_pass = (size_t)std::max(rows, 1) * pb::kBins;
+    const int np = which == 0 ? p1.npass : (which == 1 ? p2.npass : std::max(p1.npass, p2.npass));
+    const size_t smem = sizeof(pb::SortSmem<KeyT, kTileItems>);
+    for (int p = 0; p < np; p++) {
+        pb::SortArgs<KeyT> a[2];
+        int na = 0;
+        if (which != 1 && p < p1.npass) {
+            pb::SortArgs<KeyT> &q = a[na++];
+            q.keys_in = reinterpret_cast<const KeyT *>(w.key1[p & 1]), q.keys_out = reinterpret_cast<KeyT *>(w.key1[(p + 1) & 1]);
+            q.vals_in = p ? w.v1[p & 1] : nullptr, q.vals_out = w.v1[(p + 1) & 1];
+            q.hist = w.hist, q.hist_stride = stride, q.hist_off = p * pb::kBins;
+            q.state = w.sort_state + (size_t)p * state_pass, q.ticket = w.tickets + p;
+            q.shift = p1.shift[p], q.width = p1.width[p];
+        }
+        if (which != 0 && p < p2.npass) {
+            pb::SortArgs<KeyT> &q = a[na++];
+            q.keys_in = reinterpret_cast<const KeyT *>(w.key2[p & 1]), q.keys_out = reinterpret_cast<KeyT *>(w.key2[(p + 1) & 1]);
+            q.vals_in = p ? w.v2[p & 1] : nullptr, q.vals_out = w.v2[(p + 1) & 1];
+            q.hist = w.hist, q.hist_stride = stride, q.hist_off = (p1.npass + p) * pb::kBins;
+            q.state = w.sort_state + (size_t)(p1.npass + p) * state_pass, q.ticket = w.tickets + 5 + p;
+            q.shift = p2.shift[p], q.width = p2.width[p];
+        }
+        if (na == 0) continue;
+        if (na == 1) a[1] = a[0];
+        pb::k_sort_pass<KeyT, kTileItems><<<dim3(tt.T, na), pb::kTB, smem, st>>>(a[0], a[1], tt, seg_start);
+        L++;
+    }
+}
+
+// Everything after the key layout is known.  No host synchronisation.
+template <bool MIXED>
+int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assign_lp, cudaStream_t st, int64_t &L) {
+    const int n = io.n, S = io.S, T = io.tiles->T;
+    const bool prof = io.ev != nullptr;
+    int stage_ev = ST_SORT;
+    auto mark = [&]() {
+        if (prof) cudaEventRecord(io.ev[stage_ev], st);
+        stage_ev++;
+    };
+    const int T256 = 256;
+    const int gS = div_up(S + 1, T256);
+    // grid-stride kernels: one CTA wave on large problems, no more CTAs than warp-sized work items on small ones
+    const int gPersist = std::min(148 * 8, std::max(1, div_up(n, 8)));
+    ChunkDev d = header_views(w, S, T);
+    const float *dx = host_io ? w.x : io.x, *dy = host_io ? w.y : io.y, *dz = host_io ? w.z : io.z;
+    const float *dxo = host_io ? w.xo : io.xo, *dyo = host_io ? w.yo : io.yo, *dzo = host_io ? w.zo : io.zo;
+    const int *dsem = host_io ? w.sem : io.sem;
+    int *d_cluster_id = host_io ? w.cluster_id : io.cluster_id, *d_cluster_num = host_io ? w.cluster_num : io.cluster_num;
+    int *d_degree = host_io ? w.degree : io.degree;
     int *d_err = w.d_scalars, *d_F = w.d_scalars + 1, *d_R = w.d_scalars + 2, *d_K = w.d_scalars + 3,
         *d_Q = w.d_scalars + 4, *d_L = w.d_scalars + 5, *d_Cc = w.d_scalars + 6, *d_rows = w.d_scalars + 7;
     unsigned long long *cnt = prof ? w.d_counters : nullptr;
 
-    // single-pass scans (pb::k_scan_onepass): tile words + ticket zeroed once per chunk, epochs separate the scans
-    PB_CUDA(cudaMemsetAsync(w.scan_state, 0, sizeof(unsigned long long) * (w.scan_tiles + 1), st));
+    // ---- key layout from the extents the front delivered
+    pb::KeysArgs ka;
+    ka.lay = pb::make_key_layout(io.h_scalars[10], io.h_scalars[11], io.h_scalars[12]);
+    ka.key64 = ka.lay.bits > 32;
+    ka.plan1 = pb::make_pass_plan(ka.lay.bits);
+    ka.plan2 = pb::make_pass_plan(assign_lp ? (MIXED ? 32 : 3 * pb::kMortonBits) : 1);
+    if (!assign_lp) ka.plan2.npass = 0;
+    const int npass_all = ka.plan1.npass + ka.plan2.npass;
+    ka.hist_stride = npass_all * pb::kBins;
+    const int rows = io.tiles->rows, slots = io.tiles->slots;
+    const size_t state_words = (size_t)npass_all * std::max(rows, 1) * pb::kBins;
+    w.sort_state = reinterpret_cast<unsigned *>(w.zeroB_begin);
+    w.hist = w.sort_state + state_words;
+    ka.hist = w.hist;
+    const size_t zeroB = (state_words + (size_t)std::max(slots, 1) * ka.hist_stride) * sizeof(unsigned);
+    if (zeroB > w.zeroB_cap) return fail(ctx, PB_ERR_ARG, "internal: sort state exceeds its plan");
+    if (rows > 0 || slots > 0) PB_CUDA(cudaMemsetAsync(w.zeroB_begin, 0, zeroB, st));
+
+    const int Tz = std::max(T, 1);
+    pb::k_keys<MIXED, kTileItems><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, ka, dx, dy, dz, dxo, dyo, dzo, dsem, w.key1[0],
+                                                                             w.key2[0], d_err, d.radius, w.cnt18);
+    L++;
+    mark();  // SORT
+    if (ka.key64) {
+        launch_sort_passes<uint64_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 0);
+        if (assign_lp) launch_sort_passes<uint32_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 1);
+    } else {
+        launch_sort_passes<uint32_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, assign_lp ? 2 : 0);
+    }
+    const void *skey = w.key1[ka.plan1.npass & 1];
+    const uint32_t *order1 = w.v1[ka.plan1.npass & 1];
+    const uint32_t *order2 = w.v2[ka.plan2.npass & 1];
+
+    mark();  // GRID
+    pb::GridOut go;
+    go.pts4 = w.pts4, go.sx = w.sx, go.sy = w.sy, go.sz = w.sz, go.fcell_of = w.fcell_of, go.row_of = w.row_of;
+    go.fcell_start = w.fcell_start, go.fcell_cc = w.fcell_cc, go.cc_pstart = w.cc_pstart, go.cc_fstart = w.cc_fstart;
+    go.parent = w.parent, go.cell_hp = w.cell_hp, go.cell_minhp = w.cell_minhp, go.comp_min = w.comp_min, go.cell_first = w.cell_first;
+    go.fcell_key = w.fcell_key, go.cc_key = w.cc_key, go.d_F = d_F, go.d_Cc = d_Cc, go.d_rows = d_rows;
+    go.stateA = w.gridA, go.stateB = w.gridB, go.ticket = w.tickets + 10;
+    if (ka.key64)
+        pb::k_grid_build<uint64_t, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint64_t *>(skey), order1, dx, dy, dz, go);
+    else
+        pb::k_grid_build<uint32_t, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint32_t *>(skey), order1, dx, dy, dz, go);
+    pb::k_runs<<<gPersist, T256, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
+    L += 2;
+    pb::Grid grid;
+    grid.pts4 = w.pts4; grid.sx = w.sx; grid.sy = w.sy; grid.sz = w.sz; grid.fcell_of = w.fcell_of; grid.row_of = w.row_of; grid.fcell_start = w.fcell_start;
+    grid.fcell_key = w.fcell_key; grid.fcell_cc = w.fcell_cc; grid.cc_pstart = w.cc_pstart; grid.cc_fstart = w.cc_fstart;
+    grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
+
+    mark();  // DEGREE
+    PB_CUDA(cudaEventRecord(io.ev_deg[0], st));
+    {
+        // small problems: several warps share one 128-point window and split its candidate stream
+        const int windows = div_up(n, pb::kWindow);
+        const int nslice = std::max(1, std::min(32, (148 * 16) / windows));
+        pb::HpOut hp;
+        hp.pts4_w = reinterpret_cast<int *>(w.pts4), hp.degree_out = d_degree, hp.cell_hp = w.cell_hp, hp.cell_minhp = w.cell_minhp;
+        hp.cell_first = w.cell_first, hp.counters = cnt;
+        const dim3 g(div_up(n, pb::kWindow * 4), nslice);
+        if (nslice == 1 && !MIXED) {  // one warp owns a window's whole candidate stream: HP rule + cell statistics fused in
+            pb::k_degree<true><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
+            PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
+            mark();  // HP
+        } else {
+            if (nslice > 1) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
+            pb::k_degree<false><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
+            PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
+            mark();  // HP
+            pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
+                                                                   w.cell_minhp, cnt, dsem, d.min_pts, w.cell_min18, w.cell_first);
+            L++;
+        }
+    }
+    L++;
+    mark();  // UNION
+    pb::k_union<<<gPersist, T256, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0, w.cell_first);
+    pb::k_union<<<gPersist, T256, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1, w.cell_first);
+    L += 2;
+    mark();  // COMPONENTS
     unsigned scan_epoch = 0;
     auto scan = [&](const int *in, int n_host, const int *n_dev, int *out, int *total) {
         int nb = std::max(1, div_up(n_host, pb::kScanTile));
@@ -393,84 +602,12 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
                                                             reinterpret_cast<int *>(w.scan_state + w.scan_tiles), ++scan_epoch);
         L++;
     };
-
-    mark();  // PREP
-    pb::k_prep_points<<<gN, T, 0, st>>>(n, S, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, d_err);
-    pb::k_seg_params<<<gS, T, 0, st>>>(n, S, w.sg, dsem, d_radius, d_min_pts);
-    int seg_bits = 1;
-    while ((1 << seg_bits) < S) seg_bits++;
-    // LP-assignment order on 32-bit keys when the segment id leaves at least 15 Morton bits (see k_keys)
-    const int key2_mbits = (!MIXED && 32 - seg_bits >= 15) ? std::min(32 - seg_bits, 3 * pb::kMortonBits) : 0;
-    pb::k_keys<MIXED><<<gN, T, 0, st>>>(n, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.key1, w.key2, w.val, d_err,
-                                        d_radius, w.cnt18, key2_mbits);
-    L += 3;
-
-    mark();  // SORT
-    int end_bit = pb::kSegShift + seg_bits;
-    {
-        size_t bytes = w.cub_bytes;
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key1, w.key1_alt, w.val, w.order1, n, 0, end_bit, st));
-        if (assign_lp) {
-            bytes = w.cub_bytes;
-            int end_bit2 = pb::kKey2SegShift + seg_bits + (MIXED ? 5 : 0);
-            if (key2_mbits > 0) {
-                end_bit2 = key2_mbits + seg_bits;
-                uint32_t *k32 = reinterpret_cast<uint32_t *>(w.key2);
-                PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, k32, k32 + n, w.val, w.order2, n, 0, end_bit2, st));
-            } else {
-                PB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.key2, w.key2_alt, w.val, w.order2, n, 0, end_bit2, st));
-            }
-            L += 2 + (end_bit2 + 7) / 8;
-        }
-        L += 2 + (end_bit + 7) / 8;  // histogram + exclusive sum + onesweep passes
-    }
-    const uint64_t *skey = w.key1_alt;
-
-    mark();  // GRID
-    pb::k_gather_heads<<<gN, T, 0, st>>>(n, skey, w.order1, dx, dy, dz, w.pts4, w.sx, w.sy, w.sz, w.head_f, w.head_c, w.head_r);
-    L++;
-    scan(w.head_f, n, nullptr, w.ex_f, d_F);  // d_F / d_Cc are rewritten by k_cells with the same values
-    scan(w.head_c, n, nullptr, w.ex_c, d_Cc);
-    scan(w.head_r, n, nullptr, w.ex_r, d_rows);
-    pb::k_cells<<<gN, T, 0, st>>>(n, skey, w.head_f, w.ex_f, w.head_c, w.ex_c, w.head_r, w.ex_r, w.fcell_of, w.row_of,
-                                  w.fcell_start, w.fcell_key, w.fcell_cc, w.cc_pstart, w.cc_fstart, w.cc_key, w.parent,
-                                  w.cell_hp, w.cell_minhp, w.comp_min, d_F, d_Cc, w.cell_first);
-    if (MIXED) {  // per (fine cell, class) tables start at "no HP" (F <= n cells)
-        PB_CUDA(cudaMemsetAsync(w.cell_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
-        PB_CUDA(cudaMemsetAsync(w.comp_min18, 0x7f, sizeof(int) * (size_t)n * pb::kCls, st));
-    }
-    pb::k_seg_cells<<<gS, T, 0, st>>>(n, S, w.sg, w.fcell_of, w.fcell_cc, d_Cc);
-    pb::k_runs<<<gPersist, T, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
-    L += 3;
-    pb::Grid grid;
-    grid.pts4 = w.pts4; grid.sx = w.sx; grid.sy = w.sy; grid.sz = w.sz; grid.fcell_of = w.fcell_of; grid.row_of = w.row_of; grid.fcell_start = w.fcell_start;
-    grid.fcell_key = w.fcell_key; grid.fcell_cc = w.fcell_cc; grid.cc_pstart = w.cc_pstart; grid.cc_fstart = w.cc_fstart;
-    grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
-
-    mark();  // DEGREE
-    {
-        // small problems: several warps share one 128-point window and split its candidate stream
-        const int windows = div_up(n, pb::kWindow);
-        const int nslice = std::max(1, std::min(32, (148 * 16) / windows));
-        if (nslice > 1) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
-        pb::k_degree<<<dim3(div_up(n, pb::kWindow * 4), nslice), 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
-    }
-    L++;
-    mark();  // HP
-    pb::k_hp_cells<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
-                                            w.cell_minhp, cnt, dsem, d_min_pts, w.cell_min18, w.cell_first);
-    L++;
-    mark();  // UNION
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 0, w.cell_first);
-    pb::k_union<<<gPersist, T, 0, st>>>(w.sg, grid, w.pts4, w.cell_hp, w.parent, 1, w.cell_first);
-    L += 2;
-    mark();  // COMPONENTS
-    pb::k_comp_min<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min, w.cell_min18, w.comp_min18);
-    pb::k_flag_roots<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag, w.comp_min18);
+    pb::k_comp_min<MIXED><<<gPersist, T256, 0, st>>>(d_F, w.cell_hp, w.parent, w.cell_minhp, w.comp_min, w.cell_min18, w.comp_min18);
+    pb::k_flag_roots<MIXED><<<gPersist, T256, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.flag, w.comp_min18);
     L += 2;
     scan(w.flag, n, nullptr, w.gid_at, d_R);
-    pb::k_cell_gid<MIXED><<<gPersist, T, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep, w.comp_min18,
-                                                  w.cell_gid18);
+    pb::k_cell_gid<MIXED><<<gPersist, T256, 0, st>>>(d_F, w.cell_hp, w.parent, w.comp_min, w.gid_at, w.cell_gid, w.rep, w.comp_min18,
+                                                    w.cell_gid18);
     L++;
     mark();  // LABEL
     {
@@ -480,34 +617,32 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
     }
     L++;
     mark();  // FILTER
-    pb::k_filter<MIXED><<<gPersist, T, 0, st>>>(d_R, w.sg, w.rep, w.seg_of, w.raw_count, d_thresh, w.keep, dsem);
+    pb::k_filter_scan<MIXED><<<1, 1024, 0, st>>>(n, S, w.sg, d_R, w.rep, w.seg_of, w.raw_count, d.thresh, w.keep, w.kscan, d_K, dsem,
+                                                d.call_first, w.gid_at, d_cluster_num);
     L++;
-    scan(w.keep, n, d_R, w.kscan, d_K);
-    pb::k_seg_clusters<<<gS, T, 0, st>>>(n, S, w.sg, w.seg_call_first, w.gid_at, d_R, w.kscan, d_K, d_cluster_num);
-    pb::k_relabel<MIXED><<<gN, T, 0, st>>>(n, w.sg, w.seg_of, w.raw_label, w.keep, w.kscan, assign_lp, d_cluster_id, w.qflag,
-                                           io.clt_sem_out, w.clt_seg, w.rep, dsem, w.seg_lastlab);
-    L += 2;
     mark();  // LP_BUILD
-    if (assign_lp) {
-        pb::k_lab_flags<<<gN, T, 0, st>>>(n, w.order2, d_cluster_id, w.labflag, w.inv2);
+    {
+        pb::RelabelOut ro;
+        ro.cluster_id = d_cluster_id, ro.clt_sem = io.clt_sem_out, ro.clt_seg = w.clt_seg, ro.qlist = w.qlist, ro.inv2 = w.inv2;
+        ro.lpos = w.lpos, ro.seg_lastlab = w.seg_lastlab, ro.lab4 = w.lab4, ro.d_Q = d_Q, ro.d_L = d_L, ro.state = w.rel_state;
+        ro.ticket = w.tickets + 11;
+        pb::k_relabel_scan<MIXED, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, w.raw_label, w.keep, w.kscan, assign_lp, w.rep, dsem,
+                                                                     order2, dxo, dyo, dzo, ro);
         L++;
-        scan(w.qflag, n, nullptr, w.qpos, d_Q);
-        scan(w.labflag, n, nullptr, w.lpos, d_L);
-        pb::k_compact<<<gN, T, 0, st>>>(n, w.qflag, w.qpos, w.qlist, w.order2, w.labflag, w.lpos, dxo, dyo, dzo, w.lab4);
-        pb::k_seg_lab<<<gS, T, 0, st>>>(n, S, w.sg, w.lpos, d_L);
+    }
+    if (assign_lp) {
         if (MIXED) {
             scan(w.cnt18, S * pb::kCls, nullptr, w.pos18, w.d_scalars + 8);
-            pb::k_seg_lab18<<<div_up((long long)S * pb::kCls + 1, T), T, 0, st>>>(n, S, w.pos18, w.lpos, d_L, w.lab_start18);
+            pb::k_seg_lab18<<<div_up((long long)S * pb::kCls + 1, T256), T256, 0, st>>>(n, S, w.pos18, w.lpos, d_L, w.lab_start18);
             L++;
         }
-        pb::k_lab_boxes<<<gPersist, T, 0, st>>>(d_L, w.lab4, w.box_lo, w.box_hi);
-        pb::k_lab_boxes2<<<gPersist, T, 0, st>>>(d_L, w.box_lo, w.box_hi, w.box2_lo, w.box2_hi);
-        L += 4;
+        pb::k_lab_boxes<<<std::min(148 * 8, std::max(1, div_up(n, 1024))), pb::kTB, 0, st>>>(d_L, w.lab4, w.box_lo, w.box_hi, w.box2_lo, w.box2_hi);
+        L++;
     }
     mark();  // LP_NN
     if (assign_lp) {
-        pb::k_nn<MIXED><<<gPersist, T, 0, st>>>(d_Q, w.sg, w.qlist, w.seg_of, w.inv2, w.lpos, dxo, dyo, dzo, w.lab4, w.box_lo,
-                                                w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id, dsem, w.lab_start18, w.seg_lastlab);
+        pb::k_nn<MIXED><<<gPersist, T256, 0, st>>>(n, d_Q, d_L, w.sg, w.qlist, w.seg_of, w.inv2, w.lpos, dxo, dyo, dzo, w.lab4, w.box_lo,
+                                                   w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id, dsem, w.lab_start18, w.seg_lastlab);
         L++;
     }
     mark();  // CENTRES
@@ -515,7 +650,7 @@ int enqueue_chunk(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int ass
                                                             w.d_scalars + 9);
     L++;
     mark();  // D2H
-    PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 10, cudaMemcpyDeviceToHost, st));
     if (prof) PB_CUDA(cudaMemcpyAsync(io.h_counters, w.d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     if (host_io) {
         PB_CUDA(cudaMemcpyAsync(io.cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -540,7 +675,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     ctx->launches = 0;
     if (n_seg < 0 || n_pts < 0 || n_calls < 0 || (n_seg > 0 && !seg_counts) || !radius || !min_pts || !n_clusters_out)
         return fail(ctx, PB_ERR_ARG, "null / negative argument");
-    if (n_pts >= (int64_t)1 << 31) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^31");
+    if (n_pts >= (int64_t)1 << 30) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^30");
     if (n_seg >= (1 << 22)) return fail(ctx, PB_ERR_ARG, "n_seg must be below 2^22");
     if (mem_kind != PB_MEM_HOST && mem_kind != PB_MEM_DEVICE) return fail(ctx, PB_ERR_ARG, "bad mem_kind");
     const int S = n_seg;
@@ -576,6 +711,14 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             PB_CUDA(cudaStreamSynchronize(st));
         }
         return PB_OK;
+    }
+    static bool smem_attr_done = false;
+    if (!smem_attr_done) {  // the 64-bit-key sort tile needs more than the default 48 KB of dynamic shared memory
+        cudaFuncSetAttribute(pb::k_sort_pass<uint64_t, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<uint64_t, kTileItems>));
+        cudaFuncSetAttribute(pb::k_sort_pass<uint32_t, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<uint32_t, kTileItems>));
+        smem_attr_done = true;
     }
 
     // ---- chunking: runs of consecutive calls of ~chunk_points points, alternating over two streams so
@@ -615,9 +758,23 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     const int G = (int)chunks.size();
     const bool multi = G > 1;
-    int n_max = 0, S_max = 0;
-    for (auto &ch : chunks) n_max = std::max(n_max, ch.p1 - ch.p0), S_max = std::max(S_max, ch.s1 - ch.s0);
     const int slots = multi ? 2 : 1;
+    // per-chunk host tables: local segment starts, first segment of every segment's call, tile table
+    std::vector<std::vector<int>> lstart(G), lcall(G);
+    std::vector<TileHost> tiles(G);
+    int n_max = 0, S_max = 0, T_max = 0, rows_max = 0, hslots_max = 0;
+    for (int gi = 0; gi < G; gi++) {
+        const Chunk &ch = chunks[gi];
+        const int cn = ch.p1 - ch.p0, cS = ch.s1 - ch.s0;
+        lstart[gi].assign(cS + 1, 0);
+        lcall[gi].assign(std::max(cS, 1), 0);
+        for (int s = 0; s <= cS; s++) lstart[gi][s] = start[ch.s0 + s] - ch.p0;
+        for (int c = ch.c0; c < ch.c1; c++)
+            for (int s = call_seg0[c]; s < call_seg0[c + 1]; s++) lcall[gi][s - ch.s0] = call_seg0[c] - ch.s0;
+        build_tiles(lstart[gi].data(), cS, kTile, tiles[gi]);
+        n_max = std::max(n_max, cn), S_max = std::max(S_max, cS), T_max = std::max(T_max, tiles[gi].T);
+        rows_max = std::max(rows_max, tiles[gi].rows), hslots_max = std::max(hslots_max, tiles[gi].slots);
+    }
 
     // Segments that mix classes (never produced by PBNet) are detected on the device by the first attempt;
     // the call is then repeated with the per-(cell, class) tables of the mixed-class kernels.
@@ -626,8 +783,8 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     ctx->launches = 0;
     // ---- workspace: `slots` private work areas + call-wide cluster metadata ------------------------------
     Work w[2];
-    float *center_all = nullptr, *d_radius = nullptr, *d_thresh = nullptr;
-    int *clt_sem_all = nullptr, *d_min_pts = nullptr;
+    float *center_all = nullptr;
+    int *clt_sem_all = nullptr;
     for (int pass = 0; pass < 2; pass++) {
         Arena dry;
         dry.dry = true;
@@ -635,12 +792,9 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         if (pass == 1) ctx->arena.off = 0, ctx->arena.dry = false;
         center_all = a.get<float>(3 * (size_t)n);
         clt_sem_all = a.get<int>((size_t)n);
-        d_radius = a.get<float>(18);
-        d_thresh = a.get<float>(18);
-        d_min_pts = a.get<int>(18);
         for (int k = 0; k < slots; k++) {
             std::memset(&w[k], 0, sizeof(Work));
-            plan(a, w[k], n_max, S_max, host_io, mixed);
+            plan(a, w[k], n_max, S_max, T_max, rows_max, hslots_max, host_io, mixed);
         }
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
@@ -662,11 +816,18 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         ctx->chunk_ev.resize((size_t)G * (ST_COUNT + 1));
         for (size_t i = old; i < ctx->chunk_ev.size(); i++) cudaEventCreate(&ctx->chunk_ev[i]);
     }
+    if ((int)ctx->front_ev.size() < G) {
+        size_t old = ctx->front_ev.size();
+        ctx->front_ev.resize(G);
+        ctx->deg_ev.resize((size_t)2 * G);
+        for (size_t i = old; i < (size_t)G; i++) {
+            cudaEventCreateWithFlags(&ctx->front_ev[i], cudaEventDisableTiming);
+            cudaEventCreate(&ctx->deg_ev[2 * i]);
+            cudaEventCreate(&ctx->deg_ev[2 * i + 1]);
+        }
+    }
     float thresh[18];
     for (int i = 0; i < 18; i++) thresh[i] = kMeanCount[i] * para_f;  // fp32 multiply, binary.cu:256
-    PB_CUDA(cudaMemcpyAsync(d_radius, radius, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(d_min_pts, min_pts, sizeof(int) * 18, cudaMemcpyHostToDevice, st));
-    PB_CUDA(cudaMemcpyAsync(d_thresh, thresh, sizeof(float) * 18, cudaMemcpyHostToDevice, st));
 
     cudaStream_t cs[2] = {st, st};
     if (multi) {
@@ -676,27 +837,43 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         PB_CUDA(cudaStreamWaitEvent(cs[0], ctx->ev_fork, 0));
         PB_CUDA(cudaStreamWaitEvent(cs[1], ctx->ev_fork, 0));
     }
-    std::vector<int> lstart, lcall;
-    for (int gi = 0; gi < G; gi++) {
+    std::vector<ChunkIO> ios(G);
+    std::vector<int> hdr_host;
+    auto make_io = [&](int gi) {
         const Chunk &ch = chunks[gi];
-        ChunkIO io;
-        io.n = ch.p1 - ch.p0;
-        io.S = ch.s1 - ch.s0;
-        lstart.assign(io.S + 1, 0);
-        lcall.assign(std::max(io.S, 1), 0);
-        for (int s = 0; s <= io.S; s++) lstart[s] = start[ch.s0 + s] - ch.p0;
-        for (int c = ch.c0; c < ch.c1; c++)
-            for (int s = call_seg0[c]; s < call_seg0[c + 1]; s++) lcall[s - ch.s0] = call_seg0[c] - ch.s0;
+        ChunkIO &io = ios[gi];
+        io.n = ch.p1 - ch.p0, io.S = ch.s1 - ch.s0;
         io.x = x + ch.p0, io.y = y + ch.p0, io.z = z + ch.p0, io.xo = xo + ch.p0, io.yo = yo + ch.p0, io.zo = zo + ch.p0;
         io.sem = sem + ch.p0;
         io.cluster_id = cluster_id + ch.p0, io.degree = degree + ch.p0, io.cluster_num = cluster_num + ch.s0;
-        io.start = lstart.data(), io.call_first = lcall.data();
+        io.start = lstart[gi].data(), io.call_first = lcall[gi].data(), io.tiles = &tiles[gi];
         io.center_out = center_all + 3 * (size_t)ch.p0, io.clt_sem_out = clt_sem_all + ch.p0;
         io.h_scalars = ctx->h_chunk_scalars + 16 * gi, io.h_counters = ctx->h_chunk_counters + 8 * gi;
         io.ev = prof ? &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)] : nullptr;
-        int rc = mixed ? enqueue_chunk<true>(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches)
-                       : enqueue_chunk<false>(ctx, w[gi % slots], io, host_io, assign_lp, d_radius, d_min_pts, d_thresh, cs[gi % 2], ctx->launches);
+        io.ev_front = ctx->front_ev[gi];
+        io.ev_deg[0] = ctx->deg_ev[2 * gi], io.ev_deg[1] = ctx->deg_ev[2 * gi + 1];
+    };
+    // Fronts run ahead by at most one chunk per stream slot: chunk gi+2 reuses the work area of chunk gi, so its front is
+    // enqueued behind the rest of chunk gi (same stream).  The host waits for a front only to read three integers (the cell
+    // extents that size the sort keys); the other stream keeps the GPU busy meanwhile.
+    int fronts = 0;
+    auto front = [&](int gi) -> int {
+        make_io(gi);
+        return enqueue_front(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host);
+    };
+    for (; fronts < std::min(G, slots); fronts++) {
+        int rc = front(fronts);
         if (rc) return rc;
+    }
+    for (int gi = 0; gi < G; gi++) {
+        PB_CUDA(cudaEventSynchronize(ios[gi].ev_front));
+        int rc = mixed ? enqueue_rest<true>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
+                       : enqueue_rest<false>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
+        if (rc) return rc;
+        if (fronts < G) {  // the next chunk of this slot
+            rc = front(fronts++);
+            if (rc) return rc;
+        }
     }
     if (multi) {
         PB_CUDA(cudaEventRecord(ctx->ev_join[0], cs[0]));
@@ -743,9 +920,18 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             call_clusters[c] = t;
         }
     }
+    {   // always-on: time of k_degree (one event pair per chunk); with profiling every stage
+        for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+        for (int gi = 0; gi < G; gi++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ios[gi].ev_deg[0], ios[gi].ev_deg[1]);
+            ctx->stage_ms[ST_DEGREE] += ms;
+        }
+        ctx->counters[6] = G;
+    }
     if (prof) {
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
-        for (int i = 0; i < 7; i++) ctx->counters[i] = 0;
+        for (int i = 0; i < 6; i++) ctx->counters[i] = 0;
         ctx->counters[8] = 0;
         for (int gi = 0; gi < G; gi++) {
             cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
@@ -764,7 +950,6 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ctx->counters[5] += hs[2];
             ctx->counters[8] += hs[6];
         }
-        ctx->counters[6] = G;
     }
     ctx->counters[7] = mixed;
     return PB_OK;

@@ -62,6 +62,7 @@ __device__ __forceinline__ float dec_f(unsigned e) {
 struct SegArrays {
     const int *start;     // [S+1] first point of each segment (host-computed prefix sum)
     unsigned *enc_min_s;  // [3S] encoded min of shifted coords
+    unsigned *enc_max_s;  // [3S]
     unsigned *enc_min_o;  // [3S] encoded min of original coords
     unsigned *enc_max_o;  // [3S]
     int *cls;             // [S] class of the segment (class of its first point)
@@ -71,8 +72,8 @@ struct SegArrays {
     float *min_s;         // [3S]
     float *min_o;         // [3S]
     float *inv_g;         // [S]
-    int *cc_start;        // [S+1] first coarse-cell ordinal of each segment
-    int *lab_start;       // [S+1] first labelled-list position of each segment
+    int *cc_start;        // [S] first coarse-cell ordinal of each non-empty segment
+    int *cc_end;          // [S] one past its last coarse-cell ordinal
     int *id_base;         // [S] global kept-cluster index at which this segment's CALL starts
     int *k_base;          // [S] global kept-cluster index of this segment's first cluster
     int *cluster_num;     // [S]
@@ -142,251 +143,6 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1  per point: segment id, validation, per-segment bounding boxes
-// ------------------------------------------------------------------------------------------------
-__global__ void k_prep_points(int n, int S, SegArrays sg, const float *__restrict__ x,
-                              const float *__restrict__ y, const float *__restrict__ z,
-                              const float *__restrict__ xo, const float *__restrict__ yo,
-                              const float *__restrict__ zo, const int *__restrict__ sem,
-                              int *__restrict__ seg_of, int *err) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < n;
-    int s = 0;
-    float vx = 0, vy = 0, vz = 0, ox = 0, oy = 0, oz = 0;
-    if (valid) {
-        int lo = 0, hi = S - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (__ldg(sg.start + mid) <= i) lo = mid;
-            else hi = mid - 1;
-        }
-        s = lo;
-        seg_of[i] = s;
-        vx = x[i], vy = y[i], vz = z[i], ox = xo[i], oy = yo[i], oz = zo[i];
-        int c = sem[i];
-        int e = 0;
-        if (c < 2 || c > 19) e |= kErrSem;
-        if (!(isfinite(vx) && isfinite(vy) && isfinite(vz) && isfinite(ox) && isfinite(oy) && isfinite(oz)))
-            e |= kErrNonFinite;
-        if (e) atomicOr(err, e);
-    }
-    // bounding boxes: reduce in the warp, then in the block when the whole block lies in one segment (the usual
-    // case: 9 atomics per 256 points instead of per 32 — the kernel is bound by same-address atomics otherwise)
-    __shared__ unsigned sh[9][8];
-    __shared__ int sh_seg[8];
-    const int lane = lane_id(), wid = threadIdx.x >> 5;
-    unsigned act = __ballot_sync(kFull, valid);
-    unsigned e[9];
-    e[0] = enc_f(vx), e[1] = enc_f(vy), e[2] = enc_f(vz), e[3] = enc_f(ox), e[4] = enc_f(oy), e[5] = enc_f(oz);
-    e[6] = e[3], e[7] = e[4], e[8] = e[5];
-    bool uniform = false;
-    int s0 = 0;
-    if (valid) {  // only the lanes named in `act` may take part in the *_sync calls
-        s0 = __shfl_sync(act, s, __ffs(act) - 1);
-        uniform = __all_sync(act, s == s0);
-    }
-    if (valid && uniform) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) e[k] = __reduce_min_sync(act, e[k]);
-#pragma unroll
-        for (int k = 6; k < 9; k++) e[k] = __reduce_max_sync(act, e[k]);
-    }
-    int first = act ? __ffs(act) - 1 : 0;
-    if (lane == first) {
-        sh_seg[wid] = (valid && uniform) ? s0 : -1 - wid;  // distinct negative tags never compare equal
-        if (valid && uniform)
-            for (int k = 0; k < 9; k++) sh[k][wid] = e[k];
-    }
-    __syncthreads();
-    bool block_uniform = true;
-    for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) block_uniform &= sh_seg[w2] == sh_seg[0];
-    block_uniform &= sh_seg[0] >= 0;
-    if (block_uniform) {
-        if (threadIdx.x < 9) {
-            int k = threadIdx.x;
-            unsigned v = sh[k][0];
-            for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) v = k < 6 ? min(v, sh[k][w2]) : max(v, sh[k][w2]);
-            int sb = sh_seg[0];
-            if (k < 3) atomicMin(sg.enc_min_s + 3 * sb + k, v);
-            else if (k < 6) atomicMin(sg.enc_min_o + 3 * sb + (k - 3), v);
-            else atomicMax(sg.enc_max_o + 3 * sb + (k - 6), v);
-        }
-        return;
-    }
-    if (!valid) return;
-    if (uniform) {
-        if (lane == first) {
-            for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_s + 3 * s + k, e[k]);
-            for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_o + 3 * s + k, e[3 + k]);
-            for (int k = 0; k < 3; k++) atomicMax(sg.enc_max_o + 3 * s + k, e[6 + k]);
-        }
-    } else {
-        for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_s + 3 * s + k, e[k]);
-        for (int k = 0; k < 3; k++) atomicMin(sg.enc_min_o + 3 * s + k, e[3 + k]);
-        for (int k = 0; k < 3; k++) atomicMax(sg.enc_max_o + 3 * s + k, e[6 + k]);
-    }
-}
-
-// K2  per segment: radius / cell edge / origin
-__global__ void k_seg_params(int n, int S, SegArrays sg, const int *__restrict__ sem,
-                             const float *__restrict__ radius_tab, const int *__restrict__ min_pts_tab) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    int b = sg.start[s], e = sg.start[s + 1];
-    int c = 2;
-    if (e > b) c = sem[b];
-    if (c < 2 || c > 19) c = 2;  // flagged by k_prep_points
-    sg.cls[s] = c;
-    sg.min_pts[s] = min_pts_tab[c - 2];
-    float r = radius_tab[c - 2];
-    sg.r2[s] = __fmul_rn(r, r);  // binary_cuda_functions.cu:85  cur_radius * cur_radius
-    // fine cell edge h = r/2 * (1 + 2^-7): h*sqrt(3) < r (one fine cell = clique) and the coarse cell
-    // (2h >= r) makes the 3^3 coarse stencil a superset of the r-ball, with margins far above the
-    // fp32 rounding of the cell coordinate
-    float h = r * 0.5f * (1.0f + 1.0f / 128.0f);
-    if (!(h > 0.f)) h = 1e-6f;
-    sg.inv_h[s] = 1.0f / h;
-    float ext = 0.f;
-    for (int k = 0; k < 3; k++) {
-        float mn = e > b ? dec_f(sg.enc_min_s[3 * s + k]) : 0.f;
-        sg.min_s[3 * s + k] = mn;
-        float mo = e > b ? dec_f(sg.enc_min_o[3 * s + k]) : 0.f;
-        float Mo = e > b ? dec_f(sg.enc_max_o[3 * s + k]) : 0.f;
-        sg.min_o[3 * s + k] = mo;
-        ext = fmaxf(ext, Mo - mo);
-    }
-    // LP-assignment sort grid (ordering only, never a correctness filter): 512 cells along the longest
-    // axis of the segment's box -> 27 Morton bits, a 5-pass instead of a 7-pass radix sort
-    float g = fmaxf(ext / (float)kMortonMax, 1e-6f);
-    sg.inv_g[s] = 1.0f / g;
-}
-
-// K3  per point: 64-bit sort keys.  key1 = seg | coarse z,y,x | fine z,y,x bit (shifted space);
-//     key2 = seg | morton(original space, cell edge g) for the LP-assignment ordering
-//     MIXED (segments that mix classes — the API allows it, PBNet never does): key2 additionally groups
-//     by class so that every (segment, class) owns one contiguous labelled range
-template <bool MIXED>
-__global__ void k_keys(int n, SegArrays sg, const float *__restrict__ x, const float *__restrict__ y,
-                       const float *__restrict__ z, const float *__restrict__ xo,
-                       const float *__restrict__ yo, const float *__restrict__ zo,
-                       const int *__restrict__ sem, const int *__restrict__ seg_of,
-                       uint64_t *__restrict__ key1, uint64_t *__restrict__ key2,
-                       uint32_t *__restrict__ val, int *err, const float *__restrict__ radius_tab,
-                       int *__restrict__ cnt18, int key2_mbits) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int s = seg_of[i];
-    int myc = min(max(sem[i], 2), 19);
-    if (!MIXED) {
-        if (sem[i] != sg.cls[s]) atomicOr(err, kErrMixed);
-    } else {
-        // the reference looks the radius up with a sorted-position index (binary_cuda_functions.cu:35,110):
-        // only well defined when all classes of a segment share one radius
-        if (radius_tab[myc - 2] != radius_tab[sg.cls[s] - 2]) atomicOr(err, kErrRadius);
-        atomicAdd(cnt18 + (long long)s * kCls + (myc - 2), 1);
-    }
-    float ih = sg.inv_h[s];
-    float fx = __fmul_rn(__fsub_rn(x[i], sg.min_s[3 * s]), ih);
-    float fy = __fmul_rn(__fsub_rn(y[i], sg.min_s[3 * s + 1]), ih);
-    float fz = __fmul_rn(__fsub_rn(z[i], sg.min_s[3 * s + 2]), ih);
-    int cx = (fx >= 0.f && fx < 1e9f) ? (int)fx : 0;
-    int cy = (fy >= 0.f && fy < 1e9f) ? (int)fy : 0;
-    int cz = (fz >= 0.f && fz < 1e9f) ? (int)fz : 0;
-    if (cx > kCellMax || cy > kCellMax || cz > kCellMax) {
-        atomicOr(err, kErrRange);
-        cx = min(cx, kCellMax), cy = min(cy, kCellMax), cz = min(cz, kCellMax);
-    }
-    key1[i] = ((uint64_t)s << kSegShift) | ((uint64_t)(cz >> 1) << (3 + 2 * kCoarseBits)) |
-              ((uint64_t)(cy >> 1) << (3 + kCoarseBits)) | ((uint64_t)(cx >> 1) << 3) |
-              (uint64_t)(((cz & 1) << 2) | ((cy & 1) << 1) | (cx & 1));
-    float ig = sg.inv_g[s];
-    float gx = (xo[i] - sg.min_o[3 * s]) * ig, gy = (yo[i] - sg.min_o[3 * s + 1]) * ig,
-          gz = (zo[i] - sg.min_o[3 * s + 2]) * ig;
-    uint32_t mx = (uint32_t)min((gx >= 0.f && gx < 1e9f) ? (int)gx : 0, kMortonMax);
-    uint32_t my = (uint32_t)min((gy >= 0.f && gy < 1e9f) ? (int)gy : 0, kMortonMax);
-    uint32_t mz = (uint32_t)min((gz >= 0.f && gz < 1e9f) ? (int)gz : 0, kMortonMax);
-    uint64_t mort = spread3(mx) | (spread3(my) << 1) | (spread3(mz) << 2);
-    if (!MIXED) {
-        // key2 only ORDERS the labelled points (never a correctness filter): when segment id + the top key2_mbits of the
-        // Morton code fit 32 bits the sort runs on 32-bit keys (4 passes of 8 B instead of 5 passes of 12 B per point)
-        if (key2_mbits > 0)
-            reinterpret_cast<uint32_t *>(key2)[i] = ((uint32_t)s << key2_mbits) | (uint32_t)(mort >> (3 * kMortonBits - key2_mbits));
-        else
-            key2[i] = ((uint64_t)s << kKey2SegShift) | mort;
-    } else
-        key2[i] = ((uint64_t)s << (kKey2SegShift + 5)) | ((uint64_t)(myc - 2) << kKey2SegShift) | mort;
-    val[i] = (uint32_t)i;
-}
-
-// K4  after sort 1: gather coordinates into cell order, flag fine-cell / coarse-cell / row heads
-__global__ void k_gather_heads(int n, const uint64_t *__restrict__ skey, const uint32_t *__restrict__ order,
-                               const float *__restrict__ x, const float *__restrict__ y,
-                               const float *__restrict__ z, float4 *__restrict__ pts4, float *__restrict__ sx,
-                               float *__restrict__ sy, float *__restrict__ sz, int *__restrict__ head_f,
-                               int *__restrict__ head_c, int *__restrict__ head_r) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t o = order[i];
-    float vx = x[o], vy = y[o], vz = z[o];
-    pts4[i] = make_float4(vx, vy, vz, __int_as_float((int)o));
-    sx[i] = vx, sy[i] = vy, sz[i] = vz;
-    if (i == n - 1) sx[n] = sx[n + 1] = sy[n] = sy[n + 1] = sz[n] = sz[n + 1] = 0.f;  // pad for 64-bit pair loads
-    uint64_t k = skey[i], p = i ? skey[i - 1] : ~k;
-    head_f[i] = (k != p) ? 1 : 0;
-    head_c[i] = ((k >> 3) != (p >> 3)) ? 1 : 0;
-    head_r[i] = ((k >> kRowShift) != (p >> kRowShift)) ? 1 : 0;
-}
-
-// K5  cell tables from the scanned head flags
-__global__ void k_cells(int n, const uint64_t *__restrict__ skey, const int *__restrict__ head_f,
-                        const int *__restrict__ ex_f, const int *__restrict__ head_c, const int *__restrict__ ex_c,
-                        const int *__restrict__ head_r, const int *__restrict__ ex_r, int *__restrict__ fcell_of,
-                        int *__restrict__ row_of, int *__restrict__ fcell_start, uint64_t *__restrict__ fcell_key,
-                        int *__restrict__ fcell_cc, int *__restrict__ cc_pstart, int *__restrict__ cc_fstart,
-                        uint64_t *__restrict__ cc_key, int *__restrict__ parent, int *__restrict__ cell_hp,
-                        int *__restrict__ cell_minhp, int *__restrict__ comp_min, int *__restrict__ d_F,
-                        int *__restrict__ d_Cc, int *__restrict__ cell_first) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int hf = head_f[i], hc = head_c[i];
-    int f = ex_f[i] + hf - 1, c = ex_c[i] + hc - 1;
-    fcell_of[i] = f;
-    row_of[i] = ex_r[i] + head_r[i] - 1;
-    uint64_t key = skey[i];
-    if (hf) {
-        fcell_start[f] = i;
-        fcell_key[f] = key;
-        fcell_cc[f] = c;
-        parent[f] = f;
-        cell_hp[f] = 0;
-        cell_minhp[f] = 0x7fffffff;
-        comp_min[f] = 0x7fffffff;
-        cell_first[f] = 0x7fffffff;
-    }
-    if (hc) {
-        cc_pstart[c] = i;
-        cc_fstart[c] = f;
-        cc_key[c] = key >> 3;
-    }
-    if (i == n - 1) {
-        fcell_start[f + 1] = n;
-        cc_pstart[c + 1] = n;
-        cc_fstart[c + 1] = f + 1;
-        *d_F = f + 1;
-        *d_Cc = c + 1;
-    }
-}
-
-// K6  first coarse-cell ordinal of every segment
-__global__ void k_seg_cells(int n, int S, SegArrays sg, const int *__restrict__ fcell_of,
-                            const int *__restrict__ fcell_cc, const int *__restrict__ d_Cc) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > S) return;
-    int b = sg.start[s];
-    sg.cc_start[s] = (b < n) ? fcell_cc[fcell_of[b]] : *d_Cc;
-}
-
 // K7  coarse stencil rows: runs9[c*9 + (dz+1)*3 + (dy+1)] = [first coarse cell, last+1) with
 //     cx'-1 <= x' <= cx'+1 in coarse row (cy'+dy, cz'+dz) — contiguous because cells sort x-fastest
 __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const int *__restrict__ d_Cc,
@@ -406,7 +162,7 @@ __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const 
                             ((uint64_t)ny << kCoarseBits);
             uint64_t klo = base | (uint64_t)max(cx - 1, 0);
             uint64_t khi = base | (uint64_t)min(cx + 1, kCoarseMax);  // inclusive
-            int b = sg.cc_start[s], e = sg.cc_start[s + 1];
+            int b = sg.cc_start[s], e = sg.cc_end[s];
             int lo = b, hi = e;
             while (lo < hi) {  // first cell with key >= klo
                 int mid = (lo + hi) >> 1;
@@ -493,9 +249,20 @@ __device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-b
 // One group of up to 128 query points [g0, g0+total).  Lane l of pair p owns the two ADJACENT sorted points
 // base + 64p + 2l and +1 (base = g0 rounded down to even), fetched with one 64-bit load per coordinate: the
 // loaded register pair is directly the packed operand of FADD2 (no re-packing moves).
-template <int P>
+// HP epilogue of a degree group (FUSE_HP, large problems where one warp owns the whole candidate stream of its window):
+// degree scatter to input order, HP rule (binary_cuda_functions.cu:175-186), HP bit in pts4.w, per-cell HP count /
+// minimum HP index / first HP position — what round 1 did in a separate pass over the points (k_hp_cells).
+struct HpOut {
+    int *pts4_w;          // pts4 viewed as int[4N]: word 4i+3 = orig index | HP bit
+    int *degree_out;      // [N] input order
+    int *cell_hp, *cell_minhp, *cell_first;
+    unsigned long long *counters;  // profiling: [1] sum of degrees, [2] HP count (or nullptr)
+};
+
+template <int P, bool FUSE_HP>
 __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
-                                             int *__restrict__ deg_sorted, int slice, int nslice) {
+                                             int *__restrict__ deg_sorted, int slice, int nslice, int min_pts,
+                                             const HpOut &hp, unsigned &dsum, unsigned &hsum) {
     const float4 *__restrict__ pts4 = g.pts4;
     const int base = g0 & ~1;
     unsigned long long qx[P], qy[P], qz[P];
@@ -528,20 +295,48 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
 #pragma unroll
     for (int s = 0; s < 2 * P; s++) {
         int i = base + 64 * (s >> 1) + 2 * lane + (s & 1);
-        if (i >= g0 && i < g0 + total) {  // binary_cuda_functions.cu:88  ans - 1 (self)
-            if (nslice == 1) deg_sorted[i] = cnt[s] - 1;
-            else atomicAdd(deg_sorted + i, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
+        const bool in = i >= g0 && i < g0 + total;
+        if (!FUSE_HP) {
+            if (in) {  // binary_cuda_functions.cu:88  ans - 1 (self)
+                if (nslice == 1) deg_sorted[i] = cnt[s] - 1;
+                else atomicAdd(deg_sorted + i, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
+            }
+        } else {
+            const unsigned act = __ballot_sync(kFull, in);
+            if (in) {
+                const int d = cnt[s] - 1;
+                const int orig = hp.pts4_w[4 * (long long)i + 3];
+                const bool is_hp = d >= min_pts;
+                hp.degree_out[orig] = d;
+                if (is_hp) hp.pts4_w[4 * (long long)i + 3] = orig | kHpBit;
+                const int c = g.fcell_of[i];
+                const unsigned grp = __match_any_sync(act, c);
+                const unsigned hpm = __ballot_sync(act, is_hp) & grp;
+                const int mn = __reduce_min_sync(grp, is_hp ? orig : 0x7fffffff);
+                const int first = __reduce_min_sync(grp, is_hp ? i : 0x7fffffff);
+                if (hpm && lane == __ffs(grp) - 1) {
+                    atomicAdd(hp.cell_hp + c, __popc(hpm));
+                    atomicMin(hp.cell_minhp + c, mn);
+                    atomicMin(hp.cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
+                }
+            }
+            if (hp.counters) {  // profiling only (every lane accumulates the warp totals)
+                dsum += __reduce_add_sync(kFull, in ? (unsigned)(cnt[s] - 1) : 0u);
+                hsum += __popc(__ballot_sync(kFull, in && cnt[s] - 1 >= min_pts));
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(128, PB_DEG_MINB)
-k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
-    const int slice = blockIdx.y, nslice = gridDim.y;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// one 128-point window; `warp` = window index, (slice, nslice) = this warp's share of the window (small problems)
+template <bool FUSE_HP>
+__device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const Grid &g, int *__restrict__ deg_sorted,
+                                              unsigned long long *__restrict__ n_tests, const HpOut &hp, int warp, int slice,
+                                              int nslice) {
     int lane = lane_id();
     long long base = (long long)warp * kWindow;
     if (base >= n) return;
+    unsigned dsum = 0, hsum = 0;
     int end = (int)min((long long)n, base + kWindow);
     // group heads of the window (a group = points of one coarse row): one coalesced read of row_of, four ballots
     unsigned hm[kWindow / 32];
@@ -586,7 +381,9 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
             int total = gend - pos;
             int fmin = g.fcell_of[pos], fmax = g.fcell_of[gend - 1];
             int cmin = g.fcell_cc[fmin], cmax = g.fcell_cc[fmax];
-            float r2 = sg.r2[(int)(g.fcell_key[fmin] >> kSegShift)];
+            const int seg = (int)(g.fcell_key[fmin] >> kSegShift);
+            float r2 = sg.r2[seg];
+            const int min_pts = FUSE_HP ? sg.min_pts[seg] : 0;
             int jb = 0, je = 0;
             if (lane < kRuns) {
                 int c0 = g.runs9[(long long)cmin * kRuns + lane].x, c1 = g.runs9[(long long)cmax * kRuns + lane].y;
@@ -601,14 +398,26 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
             }
             const int sl = sub, ns = cs;
             switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
-                case 1: degree_group<1>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
-                case 2: degree_group<2>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
-                default: degree_group<3>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                case 1: degree_group<1, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
+                case 2: degree_group<2, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
+                default: degree_group<3, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
             }
         }
         pos = gend;
     }
-    if (n_tests && lane == 0) atomicAdd(n_tests, tests);
+    if (n_tests && lane == 0) {
+        atomicAdd(n_tests, tests);
+        if (FUSE_HP && hp.counters) {
+            atomicAdd(hp.counters + 1, (unsigned long long)dsum);
+            atomicAdd(hp.counters + 2, (unsigned long long)hsum);
+        }
+    }
+}
+
+template <bool FUSE_HP>
+__global__ void __launch_bounds__(128, PB_DEG_MINB)
+k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests, HpOut hp) {
+    degree_window<FUSE_HP>(n, sg, g, deg_sorted, n_tests, hp, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y);
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order
@@ -935,101 +744,6 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
     }
 }
 
-// K15  fragment filter (binary.cu:219-268): drop raw cluster g iff float(size) < mean_count*para_f
-template <bool MIXED>
-__global__ void k_filter(const int *__restrict__ d_R, SegArrays sg, const int *__restrict__ rep,
-                         const int *__restrict__ seg_of, const int *__restrict__ raw_count,
-                         const float *__restrict__ thresh18, int *__restrict__ keep, const int *__restrict__ sem) {
-    int R = *d_R;
-    for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < R; gi += gridDim.x * blockDim.x) {
-        int s = seg_of[rep[gi]];
-        // class of a cluster = class of its highest-index member (binary.cu:245); all members share it
-        float t = thresh18[(MIXED ? sem[rep[gi]] : sg.cls[s]) - 2];
-        keep[gi] = ((float)raw_count[gi] < t) ? 0 : 1;
-    }
-}
-
-__device__ __forceinline__ int kept_before(const int *kscan, const int *d_K, int gi, int R) {
-    return gi < R ? kscan[gi] : *d_K;
-}
-
-// K16  per segment: cluster count, first kept-cluster index, id base of the segment's call
-__global__ void k_seg_clusters(int n, int S, SegArrays sg, const int *__restrict__ seg_call_first,
-                               const int *__restrict__ gid_at, const int *__restrict__ d_R,
-                               const int *__restrict__ kscan, const int *__restrict__ d_K,
-                               int *__restrict__ cluster_num_out) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    int R = *d_R;
-    int b = sg.start[s], e = sg.start[s + 1];
-    int g0 = b < n ? gid_at[b] : R, g1 = e < n ? gid_at[e] : R;
-    int k0 = kept_before(kscan, d_K, g0, R), k1 = kept_before(kscan, d_K, g1, R);
-    sg.k_base[s] = k0;
-    sg.cluster_num[s] = k1 - k0;
-    cluster_num_out[s] = k1 - k0;
-    int f = sg.start[seg_call_first[s]];
-    int gf = f < n ? gid_at[f] : R;
-    sg.id_base[s] = kept_before(kscan, d_K, gf, R);
-}
-
-// K17  final ids of HP-stage labels; query flags for LP assignment; per-cluster metadata
-template <bool MIXED>
-__global__ void k_relabel(int n, SegArrays sg, const int *__restrict__ seg_of, const int *__restrict__ raw_label,
-                          const int *__restrict__ keep, const int *__restrict__ kscan, int assign_lp,
-                          int *__restrict__ cluster_id, int *__restrict__ qflag, int *__restrict__ clt_sem,
-                          int *__restrict__ clt_seg, const int *__restrict__ rep, const int *__restrict__ sem,
-                          int *__restrict__ seg_lastlab) {
-    int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n) return;
-    int gi = raw_label[u];
-    int s = seg_of[u];
-    int id = -1;
-    if (gi >= 0 && keep[gi]) {
-        int kk = kscan[gi];
-        id = kk - sg.id_base[s];
-        if (rep[gi] == u) {
-            clt_sem[kk] = MIXED ? sem[u] : sg.cls[s];
-            clt_seg[kk] = s;
-        }
-        if (MIXED) atomicMax(seg_lastlab + s, u);  // fallback target of binary_cuda_functions.cu:287-300
-    }
-    cluster_id[u] = id;
-    qflag[u] = (id < 0 && assign_lp && sg.cluster_num[s] > 0) ? 1 : 0;
-}
-
-// K18a  labelled flags in LP-assignment order (order2 = points sorted by segment | morton(original));
-//       inv2 = rank of every point in that order
-__global__ void k_lab_flags(int n, const uint32_t *__restrict__ order2, const int *__restrict__ cluster_id,
-                            int *__restrict__ labflag, int *__restrict__ inv2) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t o = order2[i];
-    labflag[i] = cluster_id[o] >= 0 ? 1 : 0;
-    inv2[o] = i;
-}
-
-// K18b  compaction: query list (input order) and labelled list (order2) as float4 {xo,yo,zo,index}
-__global__ void k_compact(int n, const int *__restrict__ qflag, const int *__restrict__ qpos,
-                          int *__restrict__ qlist, const uint32_t *__restrict__ order2,
-                          const int *__restrict__ labflag, const int *__restrict__ lpos,
-                          const float *__restrict__ xo, const float *__restrict__ yo,
-                          const float *__restrict__ zo, float4 *__restrict__ lab4) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (qflag[i]) qlist[qpos[i]] = i;
-    if (labflag[i]) {
-        uint32_t o = order2[i];
-        lab4[lpos[i]] = make_float4(xo[o], yo[o], zo[o], __int_as_float((int)o));
-    }
-}
-
-__global__ void k_seg_lab(int n, int S, SegArrays sg, const int *__restrict__ lpos, const int *__restrict__ d_L) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > S) return;
-    int b = sg.start[s];
-    sg.lab_start[s] = b < n ? lpos[b] : *d_L;
-}
-
 // MIXED: first labelled-list position of every (segment, class) block of order2
 __global__ void k_seg_lab18(int n, int S, const int *__restrict__ pos18, const int *__restrict__ lpos,
                             const int *__restrict__ d_L, int *__restrict__ lab_start18) {
@@ -1037,56 +751,6 @@ __global__ void k_seg_lab18(int n, int S, const int *__restrict__ pos18, const i
     if (e > S * kCls) return;
     int pos = e < S * kCls ? pos18[e] : n;
     lab_start18[e] = pos < n ? lpos[pos] : *d_L;
-}
-
-// K19  bounding boxes of the labelled list: level 1 = 32 points, level 2 = 32 level-1 boxes
-__global__ void k_lab_boxes(const int *__restrict__ d_L, const float4 *__restrict__ lab4,
-                            float4 *__restrict__ box_lo, float4 *__restrict__ box_hi) {
-    int L = *d_L;
-    int G = (L + 31) >> 5;
-    int lane = lane_id();
-    int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gi < G; gi += warps) {
-        int j = gi * 32 + lane;
-        float4 q = lab4[min(j, L - 1)];
-        float lx = q.x, ly = q.y, lz = q.z, hx = q.x, hy = q.y, hz = q.z;
-        for (int o = 16; o; o >>= 1) {
-            lx = fminf(lx, __shfl_xor_sync(kFull, lx, o));
-            ly = fminf(ly, __shfl_xor_sync(kFull, ly, o));
-            lz = fminf(lz, __shfl_xor_sync(kFull, lz, o));
-            hx = fmaxf(hx, __shfl_xor_sync(kFull, hx, o));
-            hy = fmaxf(hy, __shfl_xor_sync(kFull, hy, o));
-            hz = fmaxf(hz, __shfl_xor_sync(kFull, hz, o));
-        }
-        if (lane == 0) {
-            box_lo[gi] = make_float4(lx, ly, lz, 0.f);
-            box_hi[gi] = make_float4(hx, hy, hz, 0.f);
-        }
-    }
-}
-__global__ void k_lab_boxes2(const int *__restrict__ d_L, const float4 *__restrict__ box_lo,
-                             const float4 *__restrict__ box_hi, float4 *__restrict__ box2_lo,
-                             float4 *__restrict__ box2_hi) {
-    int L = *d_L;
-    int G = (L + 31) >> 5, G2 = (G + 31) >> 5;
-    int lane = lane_id();
-    int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g2 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g2 < G2; g2 += warps) {
-        int gi = min(g2 * 32 + lane, G - 1);
-        float4 lo = box_lo[gi], hi = box_hi[gi];
-        for (int o = 16; o; o >>= 1) {
-            lo.x = fminf(lo.x, __shfl_xor_sync(kFull, lo.x, o));
-            lo.y = fminf(lo.y, __shfl_xor_sync(kFull, lo.y, o));
-            lo.z = fminf(lo.z, __shfl_xor_sync(kFull, lo.z, o));
-            hi.x = fmaxf(hi.x, __shfl_xor_sync(kFull, hi.x, o));
-            hi.y = fmaxf(hi.y, __shfl_xor_sync(kFull, hi.y, o));
-            hi.z = fmaxf(hi.z, __shfl_xor_sync(kFull, hi.z, o));
-        }
-        if (lane == 0) {
-            box2_lo[g2] = lo;
-            box2_hi[g2] = hi;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1127,13 +791,14 @@ __device__ __forceinline__ void nn_scan_group(int gi, int l0, int l1, int lane, 
 
 template <bool MIXED>
 __global__ void __launch_bounds__(256)
-k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, const int *__restrict__ seg_of,
+k_nn(int n, const int *__restrict__ d_Q, const int *__restrict__ d_L, SegArrays sg, const int *__restrict__ qlist, const int *__restrict__ seg_of,
      const int *__restrict__ inv2, const int *__restrict__ lpos, const float *__restrict__ xo,
      const float *__restrict__ yo, const float *__restrict__ zo, const float4 *__restrict__ lab4,
      const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, const float4 *__restrict__ box2_lo,
      const float4 *__restrict__ box2_hi, int *cluster_id, const int *__restrict__ sem,
      const int *__restrict__ lab_start18, const int *__restrict__ seg_lastlab) {
     int Q = *d_Q;
+    const int L = *d_L;
     int lane = lane_id();
     int warps = (gridDim.x * blockDim.x) >> 5;
     // a warp takes bs <= 32 consecutive queries at a time: lane l fetches the header of query bs*qb + l (list entry, segment,
@@ -1149,7 +814,9 @@ k_nn(const int *__restrict__ d_Q, SegArrays sg, const int *__restrict__ qlist, c
           hp_ = qlist[qb * bs + lane];
           int s = seg_of[hp_];
           if (!MIXED) {
-              hl0 = sg.lab_start[s], hl1 = sg.lab_start[s + 1];
+              // labelled range of the segment: lpos (exclusive count of labelled points per sorted position) at its borders
+              int b0 = sg.start[s], b1 = sg.start[s + 1];
+              hl0 = lpos[b0], hl1 = b1 < n ? lpos[b1] : L;
           } else {  // candidates = labelled points of the query's class (binary_cuda_functions.cu:275)
               long long e = (long long)s * kCls + (sem[hp_] - 2);
               hl0 = lab_start18[e], hl1 = lab_start18[e + 1];

@@ -211,14 +211,15 @@ def test_fused_class_loop_equals_reference_loop(ctx):
 
 
 def test_launch_count_of_a_dropin_call_stays_lean():
-    """Regression guard for the per-call latency of the drop-in path: one per-class call is ONE fixed sequence of
-    launches (single-pass scans, 32-bit LP keys) — 46 when this was written; the reference issues ~90 blocking CUDA
-    calls per segment plus one host round trip per BFS level (lib/PB_lib/src/pbnet/binary.cu)."""
+    """Regression guard for the per-call latency of the drop-in path: one per-class call is ONE fixed sequence of launches
+    (round 1: 46; round 2: the small-problem path is one cooperative launch + the front kernels, the large path ~25 fat
+    kernels); the reference issues ~90 blocking CUDA calls per segment plus one host round trip per BFS level
+    (lib/PB_lib/src/pbnet/binary.cu)."""
     from pbnet_b200 import scenes
     from pbnet_b200.cluster import Context
     ctx = Context(0)
     sc = scenes.make_scene(5, 20000)
     c = scenes.class_calls(sc, 3)[0]
     H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=True)
-    assert 30 <= ctx.last_launch_count <= 50, ctx.last_launch_count
+    assert 1 <= ctx.last_launch_count <= 30, ctx.last_launch_count
     ctx.close()
