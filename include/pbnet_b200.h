@@ -106,6 +106,11 @@ int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const
  * Results do not depend on the chunking. */
 void pb_set_chunk_points(pb_ctx *ctx, int64_t points);
 
+/* Calls of ONE reference call with at most 32 segments whose adjacency bitmaps fit 16 MB (a segment of up to ~11 k points:
+ * the per-class calls of pbnet_ops.cluster) run as ONE cooperative launch of the small-call kernel (pb_small.cuh) instead of
+ * the cell-grid pipeline.  mode 0 = never, 1 / -1 = whenever eligible (default).  Results are identical either way. */
+void pb_set_small_calls(pb_ctx *ctx, int mode);
+
 /* Device self-test of the centre kernel's division (k_centres replays the reference's running mean
  * M += (x - M) / n, lib/PB_lib/src/pbnet/binary_cuda_functions.cu:237-239, with a reciprocal-based
  * correctly rounded quotient): compares it bit for bit with div.rn.f32 on n_samples pseudo-random and
@@ -170,6 +175,21 @@ int pb_cal_iou_and_masklabel(pb_ctx *ctx, const int32_t *proposals_idx, const in
                              const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
                              int32_t nInstance, int32_t nProposal, const float *mask_scores_sigmoid,
                              float *mask_label, int mode, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side front end of the fused class loop (device pointers only).  Replaces, for ALL classes at once, the Python of
+ *   network/PBNet.py:151-165   per class: nonzero + sort of the class's points, the `count < count_mean[c]*0.05` skip,
+ *                              gathers of xyz / offset / class, the fp32 add `ins_orig + ins_offset`
+ *   network/PBNet.py:282-287   get_batch_offset: points per scene copy
+ * xyz / offset f32[n_pts][3], sem i64[n_pts] (argmax class, 0..19), batch i32 or i64 [n_pts] (scene copy, 0..copies-1),
+ * skip_thresh20 = fp32(count_mean[c]*0.05) (HOST, entries 0/1 unused).  Outputs (device, capacity n_pts): SoA shifted /
+ * original coordinates, class and original point index of the kept points in class-major, copy-major, ascending-index
+ * order — the layout pb_binary_cluster_batched consumes (one call per kept class, `copies` segments each).  Host outputs:
+ * class_keep20[c], seg_counts[(kept classes) x copies], n_kept.  One host synchronisation. */
+int pb_group_front(pb_ctx *ctx, const float *xyz, const float *offset, const int64_t *sem, const void *batch, int batch_is64,
+                   int64_t n_pts, int32_t copies, const float *skip_thresh20, float *x, float *y, float *z, float *xo, float *yo,
+                   float *zo, int32_t *sem32, int64_t *point_index, int32_t *class_keep20, int32_t *seg_counts,
+                   int64_t *n_kept_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * "local scene" proposal lists and get_proposal (device pointers only; the device-resident continuation of

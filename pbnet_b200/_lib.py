@@ -15,8 +15,8 @@ ERR_NAMES = {1: "PB_ERR_ARG", 2: "PB_ERR_CUDA", 3: "PB_ERR_SEM_RANGE", 4: "PB_ER
 # every symbol include/pbnet_b200.h declares
 SYMBOLS = ["pb_create", "pb_destroy", "pb_last_error", "pb_last_launch_count", "pb_binary_cluster",
            "pb_binary_cluster_batched", "pb_set_profiling", "pb_stage_count", "pb_stage_name", "pb_stage_ms",
-           "pb_counter", "pb_set_chunk_points", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize", "pb_get_iou", "pb_cal_iou_and_masklabel",
-           "pb_local_scenes_plan", "pb_local_scenes_fill", "pb_get_proposal", "pb_scene_features", "pb_eval_postprocess", "pb_cal_normal_line"]
+           "pb_counter", "pb_set_chunk_points", "pb_set_small_calls", "pb_selftest_division", "pb_voxelize", "pb_voxel_rows", "pb_devoxelize", "pb_get_iou", "pb_cal_iou_and_masklabel",
+           "pb_group_front", "pb_local_scenes_plan", "pb_local_scenes_fill", "pb_get_proposal", "pb_scene_features", "pb_eval_postprocess", "pb_cal_normal_line"]
 
 
 class PBError(RuntimeError):
@@ -55,6 +55,8 @@ def lib():
     L.pb_set_profiling.restype = None
     L.pb_set_chunk_points.argtypes = [vp, ctypes.c_int64]
     L.pb_set_chunk_points.restype = None
+    L.pb_set_small_calls.argtypes = [vp, ctypes.c_int]
+    L.pb_set_small_calls.restype = None
     L.pb_selftest_division.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     L.pb_selftest_division.restype = ctypes.c_int
     L.pb_get_iou.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
@@ -77,6 +79,9 @@ def lib():
     L.pb_eval_postprocess.restype = ctypes.c_int
     L.pb_cal_normal_line.argtypes = [vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int, vp]
     L.pb_cal_normal_line.restype = ctypes.c_int
+    L.pb_group_front.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                 i64p, vp]
+    L.pb_group_front.restype = ctypes.c_int
     L.pb_stage_count.argtypes = []
     L.pb_stage_count.restype = ctypes.c_int
     L.pb_stage_name.argtypes = [ctypes.c_int]

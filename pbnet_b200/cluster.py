@@ -49,6 +49,26 @@ def _as_host_f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+_T_DTYPES = (torch.float32, torch.int32)
+_N_DTYPES = (np.dtype("float32"), np.dtype("int32"))
+
+
+def _check_arrays(items, is_torch, on_device, device, n, exact):
+    """items: (name, array, 0 = float32 | 1 = int32).  Contiguous 1-D arrays of the right dtype, all in one place."""
+    for name, a, k in items:
+        if isinstance(a, torch.Tensor) != is_torch:
+            raise TypeError(f"{name}: mixing torch and numpy arrays")
+        if is_torch:
+            ok = a.dtype == _T_DTYPES[k] and a.dim() == 1 and a.is_contiguous() and a.is_cuda == on_device and (
+                not on_device or a.device.index == device)
+        else:
+            ok = a.dtype == _N_DTYPES[k] and a.ndim == 1 and a.flags["C_CONTIGUOUS"] and (exact or a.flags["WRITEABLE"])
+        if not ok:
+            raise TypeError(f"{name}: need a contiguous 1-D {'int32' if k else 'float32'} array next to x (same device)")
+        if (a.shape[0] != n) if exact else (a.shape[0] < n):
+            raise ValueError(f"{name}: length {a.shape[0]} does not fit {n}")
+
+
 class Context:
     """Owns a pb_ctx (stream + device workspace).  Not thread-safe: one Context per thread."""
 
@@ -83,6 +103,10 @@ class Context:
         """Chunk size (points) of the two-stream pipelining of large batched calls; 0 = automatic."""
         self._lib.pb_set_chunk_points(self._h, int(points))
 
+    def set_small_calls(self, mode: int):
+        """Small-call kernel (one cooperative launch for a per-class call): 0 = never, 1 / -1 = whenever eligible (default)."""
+        self._lib.pb_set_small_calls(self._h, int(mode))
+
     def selftest_division(self, n_samples: int = 1 << 28, seed: int = 0) -> int:
         """Mismatches between k_centres' reciprocal-based quotient and div.rn.f32 (expected 0)."""
         bad = ctypes.c_int64(-1)
@@ -100,7 +124,8 @@ class Context:
         return {self._lib.pb_stage_name(i).decode(): float(self._lib.pb_stage_ms(self._h, i)) for i in range(n)}
 
     def counters(self) -> dict:
-        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode", "coarse_cells"]
+        names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode", "coarse_cells",
+                 "small_path"]
         return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------------------------------------
@@ -123,20 +148,8 @@ class Context:
         m18 = _as_host_i32(min_pts18)
         if r18.shape != (18,) or m18.shape != (18,):
             raise ValueError("radius / min_pts tables must have 18 entries")
-        for name, a, dt in (("x", x, "float32"), ("y", y, "float32"), ("z", z, "float32"), ("xo", xo, "float32"),
-                            ("yo", yo, "float32"), ("zo", zo, "float32"), ("sem", sem, "int32")):
-            if isinstance(a, torch.Tensor) != is_torch:
-                raise TypeError("mixing torch and numpy inputs")
-            if is_torch:
-                if a.is_cuda != on_device or not a.is_contiguous() or str(a.dtype) != "torch." + dt or a.dim() != 1:
-                    raise TypeError(f"{name}: need a contiguous 1-D {dt} tensor on the same device as x")
-                if on_device and a.device.index != self.device:
-                    raise TypeError(f"{name}: tensor is on cuda:{a.device.index}, context on cuda:{self.device}")
-            else:
-                if a.dtype != np.dtype(dt) or not a.flags["C_CONTIGUOUS"] or a.ndim != 1:
-                    raise TypeError(f"{name}: need a contiguous 1-D {dt} array")
-            if a.shape[0] != n:
-                raise ValueError(f"{name}: length {a.shape[0]} != {n}")
+        _check_arrays((("x", x, 0), ("y", y, 0), ("z", z, 0), ("xo", xo, 0), ("yo", yo, 0), ("zo", zo, 0), ("sem", sem, 1)),
+                      is_torch, on_device, self.device, n, exact=True)
 
         def new(shape, dtype_t, dtype_n, like_pinned=False):
             if is_torch:
@@ -146,31 +159,31 @@ class Context:
             return np.empty(shape, dtype=dtype_n)
 
         pinned = is_torch and not on_device and x.is_pinned()
+        given = []
         if cluster_id is None:
             cluster_id = new(n, torch.int32, np.int32, pinned)
+        else:
+            given.append(("cluster_id", cluster_id, 1, n))
         if cluster_num is None:
             cluster_num = new(S, torch.int32, np.int32, pinned)
+        else:
+            given.append(("cluster_num", cluster_num, 1, S))
         if degree is None:
             degree = new(n, torch.int32, np.int32, pinned)
+        else:
+            given.append(("degree", degree, 1, n))
         cap = max(n, 1)
         if center is None:
             center = new(3 * cap, torch.float32, np.float32, pinned)
+        else:
+            given.append(("center", center, 0, 0))
         if clt_sem is None:
             clt_sem = new(cap, torch.int32, np.int32, pinned)
+        else:
+            given.append(("clt_sem", clt_sem, 1, 0))
         # caller-supplied outputs go to C as raw pointers: check them like the inputs
-        for name, a, dt, need in (("cluster_id", cluster_id, "int32", n), ("cluster_num", cluster_num, "int32", S),
-                                  ("degree", degree, "int32", n), ("center", center, "float32", 0), ("clt_sem", clt_sem, "int32", 0)):
-            if isinstance(a, torch.Tensor) != is_torch:
-                raise TypeError(f"{name}: outputs must be of the same kind (torch / numpy) as the inputs")
-            if is_torch:
-                ok = a.is_cuda == on_device and a.is_contiguous() and str(a.dtype) == "torch." + dt and a.dim() == 1 and (
-                    not on_device or a.device.index == self.device)
-            else:
-                ok = a.dtype == np.dtype(dt) and a.flags["C_CONTIGUOUS"] and a.ndim == 1 and a.flags["WRITEABLE"]
-            if not ok:
-                raise TypeError(f"{name}: need a contiguous 1-D {dt} output next to the inputs")
-            if a.shape[0] < need:
-                raise ValueError(f"{name}: length {a.shape[0]} < {need}")
+        for name, a, kind_, need in given:
+            _check_arrays(((name, a, kind_),), is_torch, on_device, self.device, need, exact=False)
         nclt = ctypes.c_int64(0)
         kind = PB_MEM_DEVICE if on_device else PB_MEM_HOST
         sptr = stream_handle(stream) if stream is not None else (stream_handle(torch.cuda.current_stream(x.device))

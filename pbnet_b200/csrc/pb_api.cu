@@ -19,6 +19,7 @@
 #include "../../include/pbnet_b200.h"
 #include "pb_kernels.cuh"
 #include "pb_fused.cuh"
+#include "pb_small.cuh"
 
 namespace {
 
@@ -66,6 +67,14 @@ struct pb_ctx {
     long long chunk_points = 0;  // 0 = automatic
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
+    bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
+    int small_mode = -1;   // PB_SMALL=0: never use the small-call kernel; 1: whenever it is eligible; -1: automatic
+    char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
+    size_t h_stage_cap = 0;
+    int coop_blocks_per_sm = 0, sm_count = 0;
+    bool fuse_hp = false;  // PB_FUSE_HP=1: HP rule + cell statistics as an epilogue of k_degree instead of a separate pass
+                           // (measured at C1: 39.9 ms fused vs 37.9 ms with k_hp_cells: the epilogue's atomics and dependent
+                           // loads sit on the fp32-bound kernel's critical path)
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int *h_chunk_scalars = nullptr;
     unsigned long long *h_chunk_counters = nullptr;
@@ -134,6 +143,12 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         cudaStreamCreateWithPriority(&ctx->auxp[1], cudaStreamNonBlocking, lo);
         const char *e = getenv("PB_STREAM_PRIO");  // experiments: 0 = never, 1 = always
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+        const char *sg = getenv("PB_STAGGER");
+        ctx->stagger = sg && sg[0] == '1';
+        const char *sm = getenv("PB_SMALL");
+        ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
+        const char *fh = getenv("PB_FUSE_HP");
+        ctx->fuse_hp = fh && fh[0] == '1';
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
@@ -149,6 +164,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
@@ -173,6 +189,9 @@ extern "C" void pb_set_profiling(pb_ctx *ctx, int on) {
 }
 extern "C" void pb_set_chunk_points(pb_ctx *ctx, int64_t points) {
     if (ctx) ctx->chunk_points = points;
+}
+extern "C" void pb_set_small_calls(pb_ctx *ctx, int mode) {
+    if (ctx) ctx->small_mode = mode < 0 ? -1 : (mode ? 1 : 0);
 }
 extern "C" int pb_selftest_division(pb_ctx *ctx, int64_t n_samples, int64_t seed, int64_t *mismatches) {
     if (!ctx || !mismatches || n_samples < 0) return PB_ERR_ARG;
@@ -383,6 +402,7 @@ struct ChunkIO {          // one chunk = a run of consecutive calls; all pointer
     cudaEvent_t *ev;        // ST_COUNT+1 events or nullptr
     cudaEvent_t ev_front;   // recorded after the extents are on their way to the host
     cudaEvent_t ev_deg[2];  // always-on pair around k_degree
+    cudaEvent_t wait_deg;   // k_degree of the previous chunk (other stream) finished, or nullptr
 };
 
 struct ChunkDev {  // device views of the header block, valid after enqueue_front
@@ -566,6 +586,9 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     grid.cc_key = w.cc_key; grid.runs9 = w.runs9; grid.d_F = d_F; grid.d_Cc = d_Cc;
 
     mark();  // DEGREE
+    // staggered pipeline: the neighbour-count kernels of consecutive chunks run one after the other, so that the
+    // latency-bound tail of chunk i overlaps k_degree of chunk i+1 instead of its own twin
+    if (io.wait_deg) PB_CUDA(cudaStreamWaitEvent(st, io.wait_deg, 0));
     PB_CUDA(cudaEventRecord(io.ev_deg[0], st));
     {
         // small problems: several warps share one 128-point window and split its candidate stream
@@ -575,7 +598,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         hp.pts4_w = reinterpret_cast<int *>(w.pts4), hp.degree_out = d_degree, hp.cell_hp = w.cell_hp, hp.cell_minhp = w.cell_minhp;
         hp.cell_first = w.cell_first, hp.counters = cnt;
         const dim3 g(div_up(n, pb::kWindow * 4), nslice);
-        if (nslice == 1 && !MIXED) {  // one warp owns a window's whole candidate stream: HP rule + cell statistics fused in
+        if (nslice == 1 && !MIXED && ctx->fuse_hp) {  // one warp owns a window's whole candidate stream: HP rule + cell statistics fused in
             pb::k_degree<true><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
             PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
             mark();  // HP
@@ -664,6 +687,157 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
 
 }  // namespace
 
+// ----------------------------------------------------------------------------------------------------------------
+// Small calls (one call, few segments, a few thousand points each): ONE cooperative launch of pbsm::k_small, one copy
+// in and one copy out through pinned staging when the data lives on the host.  Returns PB_OK, an error, or kNotSmall
+// (not eligible / mixed classes found: the caller falls through to the general path).
+// ----------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kNotSmall = -1;
+constexpr long long kSmallAdjWords = 1ll << 22;   // 16 MB of adjacency bitmap: one segment of ~11.5 k points
+constexpr int kSmallCentreHead = 256;             // clusters whose centres travel with the first read-back
+}  // namespace
+
+static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
+                     const float *zo, const int32_t *sem, const std::vector<int> &start, int S, int n, const float *radius,
+                     const int32_t *min_pts, float para_f, int assign_lp, int32_t *cluster_id, int32_t *cluster_num,
+                     int32_t *degree, float *center, int64_t center_cap, int32_t *clt_sem, int64_t clt_sem_cap,
+                     int64_t *n_clusters_out, int64_t *call_clusters, bool host_io, cudaStream_t st) {
+    if (ctx->small_mode == 0 || S < 1 || S > pbsm::kMaxSeg || n < 1) return kNotSmall;
+    pbsm::SmallArgs a;
+    std::memset(&a, 0, sizeof(a));
+    long long adj_words = 0;
+    int mask_words = 0;
+    for (int s = 0; s < S; s++) {
+        const int ns = start[s + 1] - start[s], W = (ns + 31) / 32;
+        a.start[s] = start[s], a.mask_off[s] = mask_words, a.adj_off[s] = adj_words;
+        adj_words += (long long)ns * W;
+        mask_words += W;
+    }
+    a.start[S] = n, a.mask_off[S] = mask_words, a.adj_off[S] = adj_words;
+    if (adj_words > kSmallAdjWords) return kNotSmall;
+    if (ctx->coop_blocks_per_sm == 0) {
+        int coop = 0, occ = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pbsm::k_small, pbsm::kThreads, 0);
+        ctx->sm_count = sms;
+        ctx->coop_blocks_per_sm = (coop && occ > 0 && sms > 0) ? std::min(occ, 2) : -1;
+    }
+    if (ctx->coop_blocks_per_sm < 0) return kNotSmall;
+    const size_t N = (size_t)n;
+    // ---- workspace
+    float *din = nullptr, *d_center = nullptr;
+    int *d_cltsem = nullptr, *outblk = nullptr, *d_start = nullptr, *d_callfirst = nullptr;
+    char *zero_begin = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &ar = pass == 0 ? dry : ctx->arena;
+        if (pass == 1) ctx->arena.off = 0, ctx->arena.dry = false;
+        if (host_io) din = ar.get<float>(7 * N);  // x y z xo yo zo sem, one H2D copy
+        d_center = ar.get<float>(3 * N), d_cltsem = ar.get<int>(N);
+        d_start = ar.get<int>(S + 1), d_callfirst = ar.get<int>(S);
+        a.sg.cls = ar.get<int>(S), a.sg.min_pts = ar.get<int>(S), a.sg.r2 = ar.get<float>(S), a.sg.k_base = ar.get<int>(S);
+        a.sg.cluster_num = ar.get<int>(S), a.sg.id_base = ar.get<int>(S);
+        a.seg_of = ar.get<int>(N), a.parent = ar.get<int>(N), a.gid_at = ar.get<int>(N), a.raw_label = ar.get<int>(N);
+        a.rep = ar.get<int>(N), a.keep = ar.get<int>(N), a.kscan = ar.get<int>(N), a.clt_seg = ar.get<int>(N);
+        a.adj = ar.get<unsigned>((size_t)std::max<long long>(adj_words, 1));
+        // zero-initialised region, ending with the scalars; the result block [scalars | cluster_num | cluster_id | degree]
+        // starts there (one read-back when the results go to the host)
+        zero_begin = reinterpret_cast<char *>(ar.get<char>(0));
+        a.hpmask = ar.get<unsigned>(mask_words), a.labmask = ar.get<unsigned>(mask_words);
+        a.flag = ar.get<int>(N), a.raw_count = ar.get<int>(N);
+        outblk = ar.get<int>(16 + pbsm::kMaxSeg + 2 * N);
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+        }
+    }
+    a.scal = outblk;
+    const size_t zero_bytes = reinterpret_cast<char *>(outblk + 16) - zero_begin;
+    a.n = n, a.S = S, a.assign_lp = assign_lp;
+    for (int i = 0; i < 18; i++) a.radius[i] = radius[i], a.min_pts[i] = min_pts[i], a.thresh[i] = kMeanCount[i] * para_f;
+    a.sg.start = d_start, a.call_first = d_callfirst;
+    // ---- inputs
+    const size_t in_bytes = 7 * N * sizeof(float);
+    const size_t out_ints = 16 + pbsm::kMaxSeg + 2 * N;
+    const size_t head_bytes = (size_t)kSmallCentreHead * 4 * sizeof(float);
+    if (host_io) {
+        const size_t need = std::max(in_bytes, out_ints * sizeof(int) + head_bytes);
+        if (ctx->h_stage_cap < need) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr, ctx->h_stage_cap = 0;
+            PB_CUDA(cudaMallocHost(&ctx->h_stage, need + need / 2));
+            ctx->h_stage_cap = need + need / 2;
+        }
+        float *hs = reinterpret_cast<float *>(ctx->h_stage);
+        const float *src[6] = {x, y, z, xo, yo, zo};
+        for (int k = 0; k < 6; k++) std::memcpy(hs + k * N, src[k], N * sizeof(float));
+        std::memcpy(hs + 6 * N, sem, N * sizeof(int));
+        PB_CUDA(cudaMemcpyAsync(din, hs, in_bytes, cudaMemcpyHostToDevice, st));
+        a.x = din, a.y = din + N, a.z = din + 2 * N, a.xo = din + 3 * N, a.yo = din + 4 * N, a.zo = din + 5 * N;
+        a.sem = reinterpret_cast<const int *>(din + 6 * N);
+        a.cluster_num = outblk + 16, a.cluster_id = outblk + 16 + pbsm::kMaxSeg, a.degree = outblk + 16 + pbsm::kMaxSeg + n;
+        a.center = d_center, a.clt_sem = d_cltsem;
+    } else {
+        a.x = x, a.y = y, a.z = z, a.xo = xo, a.yo = yo, a.zo = zo, a.sem = sem;
+        a.cluster_num = cluster_num, a.cluster_id = cluster_id, a.degree = degree;
+        a.center = d_center, a.clt_sem = d_cltsem;   // copied to the caller's arrays once the cluster count is known
+    }
+    PB_CUDA(cudaMemsetAsync(zero_begin, 0, zero_bytes, st));
+    const int tasks = (n + pbsm::kQB - 1) / pbsm::kQB + S;
+    const int max_blocks = ctx->sm_count * ctx->coop_blocks_per_sm;
+    const int blocks = std::max(std::min(ctx->sm_count, max_blocks), std::min(max_blocks, div_up(tasks, pbsm::kThreads / 32)));
+    void *kargs[] = {&a};
+    PB_CUDA(cudaLaunchCooperativeKernel((void *)pbsm::k_small, dim3(blocks), dim3(pbsm::kThreads), kargs, 0, st));
+    ctx->launches = 1;
+    // ---- results
+    int *hres = reinterpret_cast<int *>(ctx->h_stage);
+    int scal_local[16];
+    const int head = std::min(n, kSmallCentreHead);
+    if (host_io) {
+        PB_CUDA(cudaMemcpyAsync(hres, outblk, out_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(hres + out_ints, d_center, sizeof(float) * 3 * head, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(hres + out_ints + 3 * kSmallCentreHead, d_cltsem, sizeof(int) * head, cudaMemcpyDeviceToHost, st));
+    } else {
+        PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, outblk, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    const int *sc = host_io ? hres : ctx->h_scalars;
+    std::memcpy(scal_local, sc, sizeof(scal_local));
+    const int errbits = scal_local[0];
+    if (errbits & pb::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "class id outside [2,19]");
+    if (errbits & pb::kErrNonFinite) return fail(ctx, PB_ERR_NONFINITE, "non-finite coordinate");
+    if (errbits & pb::kErrMixed) return kNotSmall;   // segments that mix classes take the general path
+    const long long K = scal_local[3];
+    *n_clusters_out = K;
+    if (host_io) {
+        std::memcpy(cluster_num, hres + 16, sizeof(int) * S);
+        std::memcpy(cluster_id, hres + 16 + pbsm::kMaxSeg, sizeof(int) * N);
+        std::memcpy(degree, hres + 16 + pbsm::kMaxSeg + N, sizeof(int) * N);
+    }
+    if (K > 0) {
+        if (!center || !clt_sem || 3LL * K > center_cap || K > clt_sem_cap)
+            return fail(ctx, PB_ERR_CAPACITY, "center / clt_sem capacity too small for " + std::to_string(K) + " clusters");
+        if (host_io && K <= head) {
+            std::memcpy(center, hres + out_ints, sizeof(float) * 3 * (size_t)K);
+            std::memcpy(clt_sem, hres + out_ints + 3 * kSmallCentreHead, sizeof(int) * (size_t)K);
+        } else {
+            cudaMemcpyKind kind = host_io ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+            PB_CUDA(cudaMemcpyAsync(center, d_center, sizeof(float) * 3 * (size_t)K, kind, st));
+            PB_CUDA(cudaMemcpyAsync(clt_sem, d_cltsem, sizeof(int) * (size_t)K, kind, st));
+            PB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    if (call_clusters) call_clusters[0] = K;
+    for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+    for (int i = 0; i < 9; i++) ctx->counters[i] = 0;
+    ctx->counters[5] = scal_local[2], ctx->counters[6] = 1;
+    ctx->counters[9] = 1;   // small-call path taken
+    return PB_OK;
+}
+
 static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
                     const float *zo, const int32_t *sem, const int32_t *seg_counts, int32_t n_seg,
                     const int32_t *call_seg_counts, int32_t n_calls, int64_t n_pts, const float *radius,
@@ -712,6 +886,12 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         }
         return PB_OK;
     }
+    if (n_calls == 1) {
+        int rc = run_small(ctx, x, y, z, xo, yo, zo, sem, start, S, n, radius, min_pts, para_f, assign_lp, cluster_id, cluster_num,
+                           degree, center, center_cap, clt_sem, clt_sem_cap, n_clusters_out, call_clusters, host_io, st);
+        if (rc != kNotSmall) return rc;
+    }
+    ctx->counters[9] = 0;
     static bool smem_attr_done = false;
     if (!smem_attr_done) {  // the 64-bit-key sort tile needs more than the default 48 KB of dynamic shared memory
         cudaFuncSetAttribute(pb::k_sort_pass<uint64_t, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -852,6 +1032,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         io.ev = prof ? &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)] : nullptr;
         io.ev_front = ctx->front_ev[gi];
         io.ev_deg[0] = ctx->deg_ev[2 * gi], io.ev_deg[1] = ctx->deg_ev[2 * gi + 1];
+        io.wait_deg = (ctx->stagger && gi > 0) ? ctx->deg_ev[2 * (gi - 1) + 1] : nullptr;
     };
     // Fronts run ahead by at most one chunk per stream slot: chunk gi+2 reuses the work area of chunk gi, so its front is
     // enqueued behind the rest of chunk gi (same stream).  The host waits for a front only to read three integers (the cell
@@ -922,14 +1103,27 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     {   // always-on: time of k_degree (one event pair per chunk); with profiling every stage
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+        // chunks on the two streams run concurrently: report the time during which k_degree was resident at all (the
+        // union of the per-chunk intervals on the common event clock), not the sum of overlapping intervals
+        std::vector<std::pair<float, float>> iv;
         for (int gi = 0; gi < G; gi++) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ios[gi].ev_deg[0], ios[gi].ev_deg[1]);
-            ctx->stage_ms[ST_DEGREE] += ms;
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ios[0].ev_deg[0], ios[gi].ev_deg[0]);
+            cudaEventElapsedTime(&b, ios[0].ev_deg[0], ios[gi].ev_deg[1]);
+            iv.push_back({a, b});
         }
+        std::sort(iv.begin(), iv.end());
+        float covered = 0.f, cur_a = iv[0].first, cur_b = iv[0].second;
+        for (size_t i = 1; i < iv.size(); i++) {
+            if (iv[i].first > cur_b) covered += cur_b - cur_a, cur_a = iv[i].first, cur_b = iv[i].second;
+            else cur_b = std::max(cur_b, iv[i].second);
+        }
+        covered += cur_b - cur_a;
+        ctx->stage_ms[ST_DEGREE] = covered;
         ctx->counters[6] = G;
     }
     if (prof) {
+        const float deg_union = ctx->stage_ms[ST_DEGREE];
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
         for (int i = 0; i < 6; i++) ctx->counters[i] = 0;
         ctx->counters[8] = 0;
@@ -950,6 +1144,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ctx->counters[5] += hs[2];
             ctx->counters[8] += hs[6];
         }
+        ctx->stage_ms[ST_DEGREE] = deg_union;
     }
     ctx->counters[7] = mixed;
     return PB_OK;
@@ -979,6 +1174,94 @@ extern "C" int pb_binary_cluster(pb_ctx *ctx, const float *x, const float *y, co
     return run_impl(ctx, x, y, z, xo, yo, zo, sem, seg_counts, n_seg, &one, 1, n_pts, radius, min_pts, para_f, assign_lp,
                     cluster_id, cluster_num, degree, center, center_cap, clt_sem, clt_sem_cap, n_clusters_out, nullptr,
                     mem_kind, stream);
+}
+
+// =================================================================================================
+// device-side front end of the fused class loop (network/PBNet.py:151-179, 282-294) — see pb_front.cuh.
+// Device pointers only; the small class / segment tables come back to the host (one synchronisation).
+// =================================================================================================
+#include "pb_front.cuh"
+
+extern "C" int pb_group_front(pb_ctx *ctx, const float *xyz, const float *offset, const int64_t *sem, const void *batch,
+                              int batch_is64, int64_t n_pts, int32_t copies, const float *skip_thresh20, float *x, float *y,
+                              float *z, float *xo, float *yo, float *zo, int32_t *sem32, int64_t *point_index,
+                              int32_t *class_keep20, int32_t *seg_counts, int64_t *n_kept_out, void *stream_v) {
+    if (!ctx) return PB_ERR_ARG;
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_pts < 0 || copies < 1 || !skip_thresh20 || !class_keep20 || !seg_counts || !n_kept_out)
+        return fail(ctx, PB_ERR_ARG, "null / negative argument");
+    if ((int64_t)pbf::kMaxSem * copies >= pbf::kDropKey) return fail(ctx, PB_ERR_ARG, "more than 25 scene copies per call");
+    if (n_pts >= ((int64_t)1 << 30)) return fail(ctx, PB_ERR_ARG, "n_pts must be below 2^30");
+    *n_kept_out = 0;
+    for (int c = 0; c < 20; c++) class_keep20[c] = 0;
+    if (n_pts == 0) return PB_OK;
+    if (!xyz || !offset || !sem || !batch || !x || !y || !z || !xo || !yo || !zo || !sem32 || !point_index)
+        return fail(ctx, PB_ERR_ARG, "null data pointer");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream_v, true);
+    const int n = (int)n_pts;
+    const int start2[2] = {0, n};
+    TileHost th;
+    build_tiles(start2, 1, kTile, th);
+    const int T = th.T;
+    uint32_t *key = nullptr, *key_out = nullptr, *order = nullptr;
+    unsigned *hist = nullptr, *state = nullptr;
+    int *tickets = nullptr, *tabs = nullptr, *tile_dev = nullptr, *seg_start = nullptr, *d_err = nullptr;
+    float *d_thr = nullptr;
+    char *zero_begin = nullptr, *zero_end = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        Arena dry;
+        dry.dry = true;
+        Arena &a = pass == 0 ? dry : ctx->arena;
+        key = a.get<uint32_t>(n), key_out = a.get<uint32_t>(n), order = a.get<uint32_t>(n);
+        tile_dev = a.get<int>((size_t)6 * T + 2 + 20);
+        tabs = a.get<int>(pbf::kTabSize);
+        zero_begin = reinterpret_cast<char *>(a.get<char>(0));
+        hist = a.get<unsigned>(pb::kBins), state = a.get<unsigned>((size_t)std::max(th.rows, 1) * pb::kBins);
+        tickets = a.get<int>(4), d_err = a.get<int>(4);
+        zero_end = reinterpret_cast<char *>(a.get<char>(0));
+        if (pass == 0) {
+            int rc = ensure_arena(ctx, dry.off, st);
+            if (rc) return rc;
+        }
+    }
+    std::vector<int> hdr((size_t)6 * T + 2 + 20);
+    std::memcpy(hdr.data(), th.buf.data(), sizeof(int) * (size_t)6 * T);
+    hdr[6 * T] = 0, hdr[6 * T + 1] = n;
+    std::memcpy(hdr.data() + 6 * T + 2, skip_thresh20, 20 * sizeof(float));
+    PB_CUDA(cudaMemcpyAsync(tile_dev, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(zero_begin, 0, zero_end - zero_begin, st));
+    seg_start = tile_dev + 6 * T;
+    d_thr = reinterpret_cast<float *>(tile_dev + 6 * T + 2);
+    pb::TileTab tt;
+    tt.begin = tile_dev, tt.count = tile_dev + T, tt.seg = tile_dev + 2 * T, tt.first = tile_dev + 3 * T, tt.hslot = tile_dev + 4 * T;
+    tt.srow = tile_dev + 5 * T, tt.T = T;
+    pbf::k_front_keys<<<std::min(div_up(n, 256), 148 * 8), 256, 0, st>>>(n_pts, (const long long *)sem, batch, batch_is64, copies, key, hist, d_err);
+    pb::SortArgs<uint32_t> sa;
+    sa.keys_in = key, sa.keys_out = key_out, sa.vals_in = nullptr, sa.vals_out = order, sa.hist = hist, sa.hist_stride = pb::kBins;
+    sa.hist_off = 0, sa.state = state, sa.ticket = tickets, sa.shift = 0, sa.width = pb::kRadixBitsMax;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(pb::k_sort_pass<uint32_t, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<uint32_t, kTileItems>));
+        attr_done = true;
+    }
+    pb::k_sort_pass<uint32_t, kTileItems><<<dim3(T, 1), pb::kTB, sizeof(pb::SortSmem<uint32_t, kTileItems>), st>>>(sa, sa, tt, seg_start);
+    pbf::k_front_tables<<<1, 32, 0, st>>>(hist, copies, d_thr, tabs);
+    pbf::k_front_gather<<<std::min(div_up(n, 256), 148 * 8), 256, 0, st>>>(tabs, copies, order, xyz, offset, x, y, z, xo, yo, zo, sem32,
+                                                                         (long long *)point_index);
+    ctx->launches = 4;
+    std::vector<int> h((size_t)pbf::kTabCnt + 512 + 1);
+    PB_CUDA(cudaMemcpyAsync(h.data(), tabs, sizeof(int) * (pbf::kTabCnt + 512), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(h.data() + pbf::kTabCnt + 512, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (h[pbf::kTabCnt + 512] & pbf::kErrBatch) return fail(ctx, PB_ERR_ARG, "batch index outside [0, cluster_batch)");
+    *n_kept_out = h[0];
+    for (int c = 0; c < 20; c++) class_keep20[c] = h[2 + c];
+    for (int i = 0; i < h[1] * copies; i++) seg_counts[i] = h[pbf::kTabCnt + i];
+    return PB_OK;
 }
 
 // =================================================================================================

@@ -929,16 +929,13 @@ __global__ void k_selftest_division(unsigned long long n_samples, unsigned long 
     if (bad) atomicAdd(mismatches, bad);
 }
 
-__global__ void __launch_bounds__(kCtrWarps * 32)
-k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
-          const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
-          const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster) {
-    __shared__ float buf[kCtrWarps][3][kCtrBuf + 128];
-    __shared__ float rcp[kCtrWarps][kCtrBuf + 128];
-    int K = *d_K;
-    int lane = lane_id(), wid = threadIdx.x >> 5;
-    float(*mybuf)[kCtrBuf + 128] = buf[wid];
-    float *myrcp = rcp[wid];
+// one warp: draws clusters from the ticket counter until none is left (all 32 lanes must call)
+__device__ __forceinline__ void centres_warp(int K, const SegArrays &sg, const int *__restrict__ clt_seg,
+                                             const int *__restrict__ cluster_id, const float *__restrict__ x,
+                                             const float *__restrict__ y, const float *__restrict__ z,
+                                             float *__restrict__ center, int *__restrict__ next_cluster,
+                                             float (*mybuf)[kCtrBuf + 128], float *myrcp) {
+    int lane = lane_id();
     int coord = lane < 3 ? lane : 0;
     while (true) {
         int kk = 0;
@@ -1021,6 +1018,16 @@ k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt
         }
         if (lane < 3) center[3 * kk + lane] = M;
     }
+}
+
+__global__ void __launch_bounds__(kCtrWarps * 32)
+k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
+          const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
+          const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster) {
+    __shared__ float buf[kCtrWarps][3][kCtrBuf + 128];
+    __shared__ float rcp[kCtrWarps][kCtrBuf + 128];
+    const int wid = threadIdx.x >> 5;
+    centres_warp(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, buf[wid], rcp[wid]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,314 @@
+// pb_small.cuh — the grouping path for SMALL calls (the reference's own call pattern: one class of one scene,
+// hundreds to a few thousand points, lib/PB_lib/torch_io/pbnet_ops.py:14-75) as ONE cooperative launch.
+//
+// Round 1 ran every call through the cell-grid pipeline: 46 dependent launches, two radix sorts, a dozen scans — 0.7 ms
+// of fixed latency for a 6 k-point class.  For a segment this small the O(n^2) formulation is cheaper than building any
+// acceleration structure, and it maps onto warp-wide bit operations:
+//   P1  adjacency bitmap + degree   one warp tests 8 query points against the whole segment, 32 candidates per
+//                                   instruction; a ballot is one 32-bit word of the query's adjacency row
+//   P2  parent[u] = smallest-index HP neighbour (first set bit of row & HP mask): a forest that already joins almost
+//       every point of a blob
+//   P3  union-find over the HP graph at WORD granularity: 32 neighbours' parents are compared with the query's root
+//       in one coalesced load; only genuinely foreign neighbours pay a find / union
+//   P4  flatten; roots flagged at their (minimum) point index; block-level scan -> raw ids in seed order
+//       (binary.cu:161-166)
+//   P5  labels: HP -> id of its component; border LP -> maximum id over its HP neighbours (binary.cu:206-213); sizes
+//   P6  fragment filter + compaction (the same block routine the large path uses)
+//   P7  final ids, labelled-point mask
+//   P8  exact 1-NN of the unlabelled points in original coordinates, ties -> largest index
+//       (binary_cuda_functions.cu:273-286)
+//   P9  centres: exact replay of the running mean (binary_cuda_functions.cu:217-246)
+// separated by grid-wide barriers (cooperative groups).  Same predicate, same canonical numbering, same tie rules as the
+// large path — the tests run both on the same inputs.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "pb_fused.cuh"
+
+namespace pbsm {
+
+namespace cg = cooperative_groups;
+using pb::kFull;
+
+constexpr int kMaxSeg = 32;       // segments per small call
+constexpr int kQB = 8;            // query points per P1 task
+constexpr int kThreads = 256;
+
+struct SmallArgs {
+    int n, S, assign_lp;
+    int start[kMaxSeg + 1];       // first point of every segment
+    int mask_off[kMaxSeg + 1];    // first bitmask word of every segment (one bit per point, segments word-aligned)
+    long long adj_off[kMaxSeg + 1];  // first adjacency word of every segment (row-major, mask words per row)
+    float radius[18];
+    int min_pts[18];
+    float thresh[18];
+    const float *x, *y, *z, *xo, *yo, *zo;
+    const int *sem;
+    int *cluster_id, *cluster_num, *degree, *clt_sem;
+    float *center;
+    pb::SegArrays sg;             // start, cls, min_pts, r2, k_base, cluster_num, id_base are used
+    const int *call_first;        // [S] zeros (one call)
+    unsigned *adj, *hpmask, *labmask;
+    int *seg_of, *parent, *flag, *gid_at, *raw_label, *raw_count, *rep, *keep, *kscan, *clt_seg;
+    int *scal;                    // [0] err [2] R [3] K [9] centre ticket
+};
+
+__device__ __forceinline__ int seg_of_point(const SmallArgs &a, int i) {
+    int s = 0;
+    while (s + 1 < a.S && a.start[s + 1] <= i) s++;
+    return s;
+}
+
+// exclusive scan of flag[0..n) by ONE block (kThreads threads, 16 items per thread and trip)
+__device__ __forceinline__ void block_scan_flags(const int *__restrict__ flag, int n, int *__restrict__ out, int *total_out, int *smem) {
+    int carry = 0;
+    for (int base = 0; base < n; base += kThreads * 16) {
+        int i0 = base + threadIdx.x * 16;
+        int v[16], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            v[k] = (i0 + k < n) ? flag[i0 + k] : 0;
+            sum += v[k];
+        }
+        int total;
+        int ex = pb::block_excl_scan_any(sum, smem, total) + carry;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (i0 + k < n) out[i0 + k] = ex;
+            ex += v[k];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_small(SmallArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_scan[40];
+    __shared__ float s_buf[pb::kCtrWarps][3][pb::kCtrBuf + 128];
+    __shared__ float s_rcp[pb::kCtrWarps][pb::kCtrBuf + 128];
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int gthread = blockIdx.x * blockDim.x + threadIdx.x, nthread = gridDim.x * blockDim.x;
+    const int n = a.n, S = a.S;
+    int *d_err = a.scal, *d_R = a.scal + 2, *d_K = a.scal + 3;
+
+    // device copies of the (by-value) segment table for the routines shared with the large path
+    if (gthread <= S) const_cast<int *>(a.sg.start)[gthread] = a.start[gthread];
+    if (gthread < S) const_cast<int *>(a.call_first)[gthread] = 0;
+    // ---------------- P1: adjacency rows + degrees + HP mask + validation -------------------------------------------
+    {
+        int task0[kMaxSeg + 1];  // first task of every segment
+        int nt = 0;
+        for (int s = 0; s < S; s++) task0[s] = nt, nt += (a.start[s + 1] - a.start[s] + kQB - 1) / kQB;
+        task0[S] = nt;
+        for (int t = gwarp; t < nt; t += nwarp) {
+            int s = 0;
+            while (task0[s + 1] <= t) s++;
+            const int b = a.start[s], e = a.start[s + 1], W = a.mask_off[s + 1] - a.mask_off[s];
+            const int q0 = b + (t - task0[s]) * kQB;
+            int cls0 = __ldg(a.sem + b);
+            const bool cls_ok = cls0 >= 2 && cls0 <= 19;
+            if (!cls_ok) cls0 = 2;
+            const float r = a.radius[cls0 - 2];
+            const float r2 = __fmul_rn(r, r);                       // binary_cuda_functions.cu:85
+            const int minp = a.min_pts[cls0 - 2];
+            if (q0 == b && lane == 0) a.sg.cls[s] = cls0, a.sg.min_pts[s] = minp, a.sg.r2[s] = r2;
+            // validation of my query points (every point is a query exactly once)
+            float qx[kQB], qy[kQB], qz[kQB];
+            int cnt[kQB];
+            int err = cls_ok ? 0 : pb::kErrSem;
+#pragma unroll
+            for (int j = 0; j < kQB; j++) {
+                int u = min(q0 + j, e - 1);
+                qx[j] = __ldg(a.x + u), qy[j] = __ldg(a.y + u), qz[j] = __ldg(a.z + u);
+                cnt[j] = 0;
+            }
+            if (lane < kQB && q0 + lane < e) {
+                int u = q0 + lane, c = a.sem[u];
+                a.seg_of[u] = s;
+                if (c < 2 || c > 19) err |= pb::kErrSem;
+                else if (c != cls0) err |= pb::kErrMixed;
+                if (!(isfinite(a.x[u]) && isfinite(a.y[u]) && isfinite(a.z[u]) && isfinite(a.xo[u]) && isfinite(a.yo[u]) && isfinite(a.zo[u])))
+                    err |= pb::kErrNonFinite;
+            }
+            if (err) atomicOr(d_err, err);
+            unsigned *row = a.adj + a.adj_off[s] + (long long)(q0 - b) * W;
+            // candidates: 32 per trip, the next trip's coordinates are fetched while this one is tested
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if (b + lane < e) nx = __ldg(a.x + b + lane), ny = __ldg(a.y + b + lane), nz = __ldg(a.z + b + lane);
+            for (int vb = 0; vb < W; vb++) {
+                const bool valid = b + vb * 32 + lane < e;
+                const float cx = nx, cy = ny, cz = nz;
+                const int vn = b + (vb + 1) * 32 + lane;
+                if (vn < e) nx = __ldg(a.x + vn), ny = __ldg(a.y + vn), nz = __ldg(a.z + vn);
+                unsigned mine = 0u;
+#pragma unroll
+                for (int j = 0; j < kQB; j++) {
+                    bool hit = valid && pb::sqd(qx[j], qy[j], qz[j], cx, cy, cz) <= r2;
+                    unsigned wv = __ballot_sync(kFull, hit);
+                    cnt[j] += __popc(wv);
+                    if (lane == j) mine = wv;
+                }
+                if (lane < kQB && q0 + lane < e) row[(long long)lane * W + vb] = mine;
+            }
+            // degree (self excluded by position, binary_cuda_functions.cu:88), HP rule (:175-186)
+            int mycnt = 0;
+#pragma unroll
+            for (int j = 0; j < kQB; j++)
+                if (lane == j) mycnt = cnt[j];
+            if (lane < kQB && q0 + lane < e) {
+                int u = q0 + lane, d = mycnt - 1;
+                a.degree[u] = d;
+                if (d >= minp) atomicOr(a.hpmask + a.mask_off[s] + ((u - b) >> 5), 1u << ((u - b) & 31));
+            }
+        }
+    }
+    grid.sync();
+    // ---------------- P2: parent = smallest-index HP neighbour (self for the minimum of its neighbourhood) ----------
+    for (int u = gthread; u < n; u += nthread) {
+        int s = a.seg_of[u];
+        const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lu = u - b;
+        const unsigned *hm = a.hpmask + a.mask_off[s];
+        int p = u;
+        if ((hm[lu >> 5] >> (lu & 31)) & 1u) {
+            const unsigned *row = a.adj + a.adj_off[s] + (long long)lu * W;
+            for (int vb = 0; vb <= (lu >> 5); vb++) {
+                unsigned w = row[vb] & hm[vb];
+                if (w) {
+                    p = b + vb * 32 + __ffs(w) - 1;
+                    break;
+                }
+            }
+        }
+        a.parent[u] = p;   // p <= u
+    }
+    grid.sync();
+    // ---------------- P3: union-find over HP neighbours with a smaller index, 32 parents per load --------------------
+    for (int u = gwarp; u < n; u += nwarp) {
+        int s = a.seg_of[u];
+        const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lu = u - b;
+        const unsigned *hm = a.hpmask + a.mask_off[s];
+        if (!((hm[lu >> 5] >> (lu & 31)) & 1u)) continue;
+        const unsigned *row = a.adj + a.adj_off[s] + (long long)lu * W;
+        int r = pb::uf_find(a.parent, u);
+        for (int vb = 0; vb <= (lu >> 5); vb++) {
+            unsigned w = row[vb] & hm[vb];
+            if (vb == (lu >> 5)) w &= (1u << (lu & 31)) - 1u;   // strictly smaller indices: every edge once
+            if (!w) continue;
+            int v = b + vb * 32 + lane;
+            bool foreign = ((w >> lane) & 1u) && __ldcg(a.parent + v) != r;
+            unsigned f = __ballot_sync(kFull, foreign);
+            while (f) {
+                int j = __ffs(f) - 1;
+                f &= f - 1;
+                if (lane == 0) pb::uf_union(a.parent, u, b + vb * 32 + j);
+                __syncwarp();
+            }
+            r = pb::uf_find(a.parent, u);
+        }
+    }
+    grid.sync();
+    // ---------------- P4a: flatten, flag the roots (root = minimum index of its component) ---------------------------
+    for (int u = gthread; u < n; u += nthread) {
+        int s = a.seg_of[u];
+        const int lu = u - a.start[s];
+        if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) {
+            int rt = pb::uf_find(a.parent, u);
+            __stcg(a.parent + u, rt);
+            if (rt == u) a.flag[u] = 1;
+        }
+    }
+    grid.sync();
+    // ---------------- P4b: raw ids = rank of the component's minimum HP index (binary.cu:161-166) --------------------
+    if (blockIdx.x == 0) {
+        block_scan_flags(a.flag, n, a.gid_at, d_R, s_scan);
+        for (int u = threadIdx.x; u < n; u += blockDim.x)
+            if (a.flag[u]) a.rep[a.gid_at[u]] = u;
+    }
+    grid.sync();
+    // ---------------- P5: labels + cluster sizes -----------------------------------------------------------------------
+    for (int p = gwarp; p < n; p += nwarp) {
+        int s = a.seg_of[p];
+        const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lp = p - b;
+        const unsigned *hm = a.hpmask + a.mask_off[s];
+        int label = -1;
+        if ((hm[lp >> 5] >> (lp & 31)) & 1u) {
+            label = a.gid_at[__ldcg(a.parent + p)];
+        } else {  // border LP: the LAST component that reaches it wins = maximum raw id (binary.cu:206-213)
+            const unsigned *row = a.adj + a.adj_off[s] + (long long)lp * W;
+            int best = -1;
+            for (int vb = 0; vb < W; vb++) {
+                unsigned w = row[vb] & hm[vb];
+                if ((w >> lane) & 1u) best = max(best, a.gid_at[__ldcg(a.parent + b + vb * 32 + lane)]);
+            }
+            label = __reduce_max_sync(kFull, best);
+        }
+        if (lane == 0) {
+            a.raw_label[p] = label;
+            if (label >= 0) atomicAdd(a.raw_count + label, 1);
+        }
+    }
+    grid.sync();
+    // ---------------- P6: fragment filter, compaction, per-segment counts ----------------------------------------------
+    if (blockIdx.x == 0)
+        pb::filter_scan_block<false>(n, S, a.sg, d_R, a.rep, a.seg_of, a.raw_count, a.thresh, a.keep, a.kscan, d_K, a.sem,
+                                     a.call_first, a.gid_at, a.cluster_num, s_scan);
+    grid.sync();
+    // ---------------- P7: final ids of the HP stage, labelled mask ----------------------------------------------------
+    {
+        const int words = a.mask_off[S];
+        for (int wd = gwarp; wd < words; wd += nwarp) {
+            int s = 0;
+            while (a.mask_off[s + 1] <= wd) s++;
+            int u = a.start[s] + (wd - a.mask_off[s]) * 32 + lane;
+            bool lab = false;
+            if (u < a.start[s + 1]) {
+                int gi = a.raw_label[u], id = -1;
+                if (gi >= 0 && a.keep[gi]) {
+                    int kk = a.kscan[gi];
+                    id = kk - a.sg.id_base[s];
+                    if (a.rep[gi] == u) a.clt_sem[kk] = a.sg.cls[s], a.clt_seg[kk] = s;
+                    lab = true;
+                }
+                a.cluster_id[u] = id;
+            }
+            unsigned m = __ballot_sync(kFull, lab);
+            if (lane == 0) a.labmask[wd] = m;
+        }
+    }
+    grid.sync();
+    // ---------------- P8: exact 1-NN of the unlabelled points (original coordinates) ----------------------------------
+    if (a.assign_lp) {
+        for (int p = gwarp; p < n; p += nwarp) {
+            int s = a.seg_of[p];
+            const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lp = p - b;
+            const unsigned *lm = a.labmask + a.mask_off[s];
+            if ((lm[lp >> 5] >> (lp & 31)) & 1u) continue;   // labelled
+            if (a.sg.cluster_num[s] <= 0) continue;            // nothing to assign to: stays -1
+            const float px = a.xo[p], py = a.yo[p], pz = a.zo[p];
+            float bestD = __int_as_float(0x7f800000);
+            int bestI = -1;
+            for (int vb = 0; vb < W; vb++) {
+                if ((lm[vb] >> lane) & 1u) {
+                    int v = b + vb * 32 + lane;
+                    float D = pb::sqd(px, py, pz, a.xo[v], a.yo[v], a.zo[v]);
+                    if (D <= bestD) bestD = D, bestI = v;   // ascending v: '<=' keeps the largest index (:282)
+                }
+            }
+            unsigned db = __float_as_uint(bestD);   // D >= 0: the bit pattern is order preserving
+            unsigned dmin = __reduce_min_sync(kFull, db);
+            int imax = __reduce_max_sync(kFull, (db == dmin) ? bestI : -1);
+            if (lane == 0 && imax >= 0) a.cluster_id[p] = a.cluster_id[imax];
+        }
+    }
+    grid.sync();
+    // ---------------- P9: centres --------------------------------------------------------------------------------------
+    if ((threadIdx.x >> 5) < pb::kCtrWarps)
+        pb::centres_warp(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_buf[threadIdx.x >> 5],
+                         s_rcp[threadIdx.x >> 5]);
+}
+
+}  // namespace pbsm

@@ -7,11 +7,76 @@ a ``.cpu()`` round trip per class, per-batch ``.sum()`` loops (``get_batch_offse
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
-from .cluster import default_context
+from ._lib import PBError
+from .cluster import default_context, stream_handle
 from .scenes import COUNT_MEAN
+
+
+def _skip_thresholds(count_mean):
+    """``count_mean[sem_id] * 0.05`` of network/PBNet.py:156 — an fp32 tensor product (entries 0/1 are wall / floor)."""
+    return (torch.as_tensor(np.asarray(count_mean, np.float32)) * 0.05).numpy().astype(np.float32)
+
+
+def group_instances_flat(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem_pred_p: torch.Tensor,
+                         batch_head_p: torch.Tensor, radius: float, min_pts: int, cluster_batch: int,
+                         count_mean=COUNT_MEAN, sem_num: int = 20):
+    """The whole class loop of network/PBNet.py:151-179 on the device: ``pb_group_front`` (class histogram, skip rule,
+    stable partition into class-major / copy-major order, fp32 ``orig + offset``: four kernels, no torch op) followed by
+    ONE ``pb_binary_cluster_batched`` call.  Returns None when no class passes the skip, else a dict of flat results:
+        classes i32[C] (host), seg_counts i32[C, cluster_batch] (host), call_clusters i64[C] (host), point_index i64[n]
+        (= cat of the reference's ins_ind), cluster_id i32[n], cluster_num i32[C*cluster_batch], degree i32[n],
+        center f32[3K], clt_sem i32[K], n_clusters
+    ``batch_head_p`` must hold the scene copy of every point in [0, cluster_batch) (the reference slices the class's
+    points into consecutive per-copy runs, i.e. it additionally assumes the copies are stored one after the other)."""
+    dev = xyz_original.device
+    assert dev.type == "cuda", "group_instances is the device-resident path; use pbnet_ops.cluster for CPU tensors"
+    if sem_num != 20:
+        raise ValueError("the class tables of the path have 20 entries (network/PBNet.py:33-34)")
+    n = int(xyz_original.shape[0])
+    ctx = default_context(dev.index)
+    L = ctx._lib
+    xyz = xyz_original if (xyz_original.dtype == torch.float32 and xyz_original.is_contiguous()) else xyz_original.to(torch.float32).contiguous()
+    off = offset_pred_p if (offset_pred_p.dtype == torch.float32 and offset_pred_p.is_contiguous()) else offset_pred_p.to(torch.float32).contiguous()
+    sem = sem_pred_p if (sem_pred_p.dtype == torch.int64 and sem_pred_p.is_contiguous()) else sem_pred_p.to(torch.int64).contiguous()
+    bh = batch_head_p
+    if bh.dtype not in (torch.int32, torch.int64) or not bh.is_contiguous():
+        bh = bh.to(torch.int64).contiguous()
+    if not (xyz.shape == (n, 3) and off.shape == (n, 3) and sem.shape == (n,) and bh.shape == (n,)):
+        raise ValueError("xyz / offset [N,3], sem / batch [N] expected")
+    for t in (off, sem, bh):
+        if t.device != dev:
+            raise TypeError("all inputs must live on the same CUDA device")
+    buf = torch.empty((6, max(n, 1)), dtype=torch.float32, device=dev)       # x y z xo yo zo of the kept points
+    sem32 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    pidx = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    thr = np.ascontiguousarray(_skip_thresholds(count_mean))
+    keep20 = np.zeros(20, np.int32)
+    segs = np.zeros(20 * cluster_batch, np.int32)
+    n_kept = ctypes.c_int64(0)
+    st = stream_handle(torch.cuda.current_stream(dev))
+    rc = L.pb_group_front(ctx._h, xyz.data_ptr(), off.data_ptr(), sem.data_ptr(), bh.data_ptr(), int(bh.dtype == torch.int64), n,
+                          int(cluster_batch), thr.ctypes.data, buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(),
+                          buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(), sem32.data_ptr(), pidx.data_ptr(),
+                          keep20.ctypes.data, segs.ctypes.data, ctypes.byref(n_kept), st)
+    if rc != 0:
+        raise PBError(rc, L.pb_last_error(ctx._h).decode())
+    m = int(n_kept.value)
+    classes = np.nonzero(keep20)[0].astype(np.int32)
+    if m == 0 or len(classes) == 0:
+        return None
+    seg_counts = segs[:len(classes) * cluster_batch].reshape(len(classes), cluster_batch).copy()
+    r18 = np.full(18, np.float32(radius), np.float32)       # torch.ones(18) * radius -> float32 (pbnet_ops.py:33-36)
+    m18 = np.full(18, int(min_pts), np.int32)
+    out = ctx.binary_cluster(buf[0, :m], buf[1, :m], buf[2, :m], buf[3, :m], buf[4, :m], buf[5, :m], sem32[:m],
+                             seg_counts.reshape(-1), r18, m18, 0.05, True,
+                             call_seg_counts=np.full(len(classes), cluster_batch, np.int32))
+    out.update(classes=classes, seg_counts=seg_counts, point_index=pidx[:m])
+    return out
 
 
 def group_instances(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem_pred_p: torch.Tensor,
@@ -24,44 +89,21 @@ def group_instances(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem
     (network/PBNet.py:156), in class order:
         sem_id, ins_ind (point indices, ascending), seg_counts (host, points per scene copy), cluster_id,
         cluster_num [cluster_batch], den_queue (= degree + 1, as pbnet_ops.cluster returns it), clt_ctr [K,3]
-    """
-    dev = xyz_original.device
-    assert dev.type == "cuda", "group_instances is the device-resident path; use pbnet_ops.cluster for CPU tensors"
-    n = xyz_original.shape[0]
-    sem = sem_pred_p.to(torch.int64)
-    counts = torch.bincount(sem.clamp(0, sem_num - 1), minlength=sem_num)
-    cm = torch.as_tensor(np.asarray(count_mean, np.float32), device=dev)
-    keep_cls = (counts.to(torch.float32) >= cm * 0.05)
-    keep_cls[:2] = False  # wall / floor are skipped (PBNet.py:151-152)
-    sel = keep_cls[sem.clamp(0, sem_num - 1)] & (sem >= 2) & (sem < sem_num)
-    idx = torch.nonzero(sel).view(-1)
-    if idx.numel() == 0:
+    (views of the flat result of ``group_instances_flat``)."""
+    out = group_instances_flat(xyz_original, offset_pred_p, sem_pred_p, batch_head_p, radius, min_pts, cluster_batch,
+                               count_mean, sem_num)
+    if out is None:
         return []
-    key = sem[idx] * cluster_batch + batch_head_p[idx].to(torch.int64)
-    order = torch.argsort(key, stable=True)          # class-major, batch-major, ascending point index inside
-    pidx = idx[order]
-    seg_counts = torch.bincount(key[order], minlength=sem_num * cluster_batch).view(sem_num, cluster_batch)
-    classes = torch.nonzero(keep_cls).view(-1)
-    seg_counts = seg_counts[classes].to(torch.int32).cpu().numpy()            # [n_classes, cluster_batch]
-    classes = classes.cpu().numpy()
-    orig = xyz_original[pidx].to(torch.float32)
-    shifted = orig + offset_pred_p[pidx].to(torch.float32)                     # PBNet.py:165 (fp32 add)
-    so, oo = shifted.t().contiguous(), orig.t().contiguous()
-    sem32 = sem[pidx].to(torch.int32).contiguous()
-    r18 = (torch.ones(18) * radius).to(torch.float32)
-    m18 = (torch.ones(18) * min_pts).to(torch.int32)
-    ctx = default_context(dev.index)
-    out = ctx.binary_cluster(so[0], so[1], so[2], oo[0], oo[1], oo[2], sem32, seg_counts.reshape(-1), r18, m18, 0.05, True,
-                             call_seg_counts=np.full(len(classes), cluster_batch, np.int32))
+    den = out["degree"] + 1
     res = []
     p0 = 0
     k0 = 0
-    for ci, c in enumerate(classes):
-        npts = int(seg_counts[ci].sum())
+    for ci, c in enumerate(out["classes"]):
+        npts = int(out["seg_counts"][ci].sum())
         k = int(out["call_clusters"][ci])
-        res.append(dict(sem_id=int(c), ins_ind=pidx[p0:p0 + npts], cluster_id=out["cluster_id"][p0:p0 + npts],
+        res.append(dict(sem_id=int(c), ins_ind=out["point_index"][p0:p0 + npts], cluster_id=out["cluster_id"][p0:p0 + npts],
                         cluster_num=out["cluster_num"][ci * cluster_batch:(ci + 1) * cluster_batch],
-                        den_queue=out["degree"][p0:p0 + npts] + 1, seg_counts=seg_counts[ci].copy(),
+                        den_queue=den[p0:p0 + npts], seg_counts=out["seg_counts"][ci].copy(),
                         clt_ctr=out["center"][3 * k0:3 * (k0 + k)].view(-1, 3)))
         p0 += npts
         k0 += k
@@ -71,11 +113,6 @@ def group_instances(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem
 # =====================================================================================================
 # local scenes + get_proposal (network/PBNet.py:180-234, 317-346) on the device
 # =====================================================================================================
-import ctypes  # noqa: E402
-
-from ._lib import PBError  # noqa: E402
-from .cluster import stream_handle  # noqa: E402
-
 K_MAX = np.full(20, 6, np.int32)  # network/PBNet.py:35  self.K_max = torch.ones(20) * 6
 
 
@@ -202,26 +239,21 @@ def propose(xyz_original: torch.Tensor, offset_pred_p: torch.Tensor, sem_pred_p:
     Returns dict(groups, scenes, features f32[E,C+2], voxel_features, voxel_coords i32[V,4], voxel_map) where
     ``voxel_map.inverse`` is ``inputs_v2.inverse_mapping`` (:247) and ``scenes['index']`` is ``cat(list_ins_idx)``."""
     from . import voxel
-    groups = group_instances(xyz_original, offset_pred_p, sem_pred_p, batch_head_p, radius, min_pts, cluster_batch, count_mean)
-    if not groups:
-        return dict(groups=[], scenes=None, features=None, voxel_features=None, voxel_coords=None, voxel_map=None)
-    cid = torch.cat([g["cluster_id"] for g in groups])
-    cnum = torch.cat([g["cluster_num"] for g in groups])
-    ctr = torch.cat([g["clt_ctr"].reshape(-1) for g in groups])
-    pmap = torch.cat([g["ins_ind"] for g in groups])
-    seg = np.concatenate([g["seg_counts"] for g in groups])
-    csem = np.array([g["sem_id"] for g in groups], np.int32)
-    calls = np.full(len(groups), cluster_batch, np.int32)
+    flat = group_instances_flat(xyz_original, offset_pred_p, sem_pred_p, batch_head_p, radius, min_pts, cluster_batch, count_mean)
+    if flat is None:
+        return dict(groups=None, scenes=None, features=None, voxel_features=None, voxel_coords=None, voxel_map=None)
+    cid, cnum, ctr, pmap = flat["cluster_id"], flat["cluster_num"], flat["center"], flat["point_index"]
+    seg = flat["seg_counts"].reshape(-1)
+    csem = flat["classes"].astype(np.int32)
+    calls = np.full(len(csem), cluster_batch, np.int32)
     lab = ins_label[pmap].contiguous() if ins_label is not None else None   # ins_ins_label = ins_label[ins_ind] (:163)
     sc = build_local_scenes(cid, cnum, ctr, seg, calls, csem, point_map=pmap, ins_label=lab, k_max=k_max,
                             count_mean=count_mean, want_proposal_id=True)
-    # class of every proposal: clusters are numbered call-major, so the class follows from the per-call cluster counts
-    per_call = torch.stack([g["cluster_num"].sum() for g in groups]).to(torch.int64)
-    cl_sem = torch.repeat_interleave(torch.as_tensor(csem, device=cid.device), per_call)
-    prop_sem = cl_sem[sc["cluster"].to(torch.int64)]
+    # class of every proposal = class of its cluster (clt_sem of the batched call, one entry per cluster, call-major)
+    prop_sem = flat["clt_sem"][sc["cluster"].to(torch.int64)]
     feats = scene_features(point_feat_p, sem_score_sfp, sc["index"], sc["proposal"], prop_sem, sc["dpn"])
     coords = xyz_original[sc["index"]].to(torch.float32) / voxel_size       # :236 sem_xyz / 0.02
     vm = voxel.voxel_map(coords, None, batch=sc["proposal"])
     vfeat = voxel.voxel_rows(feats, vm, "pick")
-    return dict(groups=groups, scenes=sc, proposal_sem=prop_sem, features=feats, voxel_features=vfeat, voxel_coords=vm.vcoords,
+    return dict(groups=flat, scenes=sc, proposal_sem=prop_sem, features=feats, voxel_features=vfeat, voxel_coords=vm.vcoords,
                 voxel_map=vm)

@@ -16,26 +16,37 @@ from torch.autograd import Function
 from .cluster import default_context
 
 
+_TABLES = {}
+
+
+def _tables(radius, min_pts):
+    """``torch.ones(18) * radius`` -> float32, ``torch.ones(18) * min_pts`` -> int32 (pbnet_ops.py:33-36), cached."""
+    key = (float(radius), float(min_pts))
+    t = _TABLES.get(key)
+    if t is None:
+        t = _TABLES[key] = ((torch.ones(18) * radius).to(torch.float32).numpy().copy(),
+                            (torch.ones(18) * min_pts).to(torch.int32).numpy().copy())
+    return t
+
+
 class Cluster(Function):
     @staticmethod
     def forward(ctx, ins_offseted, ins_orig, sem, ins_bp, radius, min_pts, batch_size):
         dev = ins_offseted.device
-        f32 = dict(dtype=torch.float32)
         # SoA split (pbnet_ops.py:16-18, 27-29): one transpose-copy per coordinate set
-        so = ins_offseted.to(**f32).t().contiguous()
-        oo = ins_orig.to(device=dev, **f32).t().contiguous()
+        so = ins_offseted.to(torch.float32).t().contiguous()
+        oo = ins_orig.to(device=dev, dtype=torch.float32).t().contiguous()
         sem32 = sem.to(device=dev, dtype=torch.int32).contiguous()
         # the reference overwrites batch_size with ins_bp.shape[0] (pbnet_ops.py:43)
-        segs = ins_bp.to(torch.int32).cpu()
-        radius18 = (torch.ones(18) * radius).to(torch.float32)  # pbnet_ops.py:33-36
-        min_pts18 = (torch.ones(18) * min_pts).to(torch.int32)
+        segs = ins_bp.detach().to(device="cpu", dtype=torch.int32).numpy()
+        radius18, min_pts18 = _tables(radius, min_pts)
         pb = default_context(dev.index if dev.type == "cuda" else
                              (torch.cuda.current_device() if torch.cuda.is_available() else 0))
         out = pb.binary_cluster(so[0], so[1], so[2], oo[0], oo[1], oo[2], sem32, segs, radius18, min_pts18,
                                 0.05, True)  # para_f, nv_flag: pbnet_ops.py:70-71
-        for t in (out["cluster_id"], out["cluster_num"], out["degree"], out["center"]):
-            ctx.mark_non_differentiable(t)
-        return out["cluster_id"], out["cluster_num"], out["degree"] + 1, out["center"]
+        den = out["degree"] + 1
+        ctx.mark_non_differentiable(out["cluster_id"], out["cluster_num"], den, out["center"])
+        return out["cluster_id"], out["cluster_num"], den, out["center"]
 
     @staticmethod
     def backward(ctx, *a):

@@ -16,13 +16,26 @@ def ctx():
     c.close()
 
 
+@pytest.mark.parametrize("small", [0, 1], ids=["grid-path", "small-call-kernel"])
 @pytest.mark.parametrize("path", H.golden_files(), ids=lambda p: p.split("/")[-1][:-4])
-def test_golden_reference_vectors(ctx, path):
-    """Outputs of the UNMODIFIED compiled reference (tests/golden/make_golden.py) on a B200."""
+def test_golden_reference_vectors(ctx, path, small):
+    """Outputs of the UNMODIFIED compiled reference (tests/golden/make_golden.py) on a B200, through both implementations
+    of a single call: the cell-grid pipeline and the one-launch small-call kernel (pb_small.cuh)."""
     d, ref = H.load_golden(path)
     seg = d["seg_counts"]
-    got = H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]))
-    assert H.diff_report(got, ref) == []
+    ctx.set_small_calls(small)
+    try:
+        for device in (False, True):
+            got = H.run_cuda(ctx, d["xyz_shift"], d["xyz_orig"], d["sem"], seg, d["radius"], d["min_pts"], 0.05, bool(d["nv_flag"]),
+                             device=device)
+            assert H.diff_report(got, ref) == []
+            single = H.is_single_class(d["sem"], seg)
+            if small and single and len(d["sem"]) and len(seg) <= 32:
+                assert ctx.counters()["small_path"] == 1 and ctx.last_launch_count == 1
+            if not small:
+                assert ctx.counters()["small_path"] == 0
+    finally:
+        ctx.set_small_calls(-1)
 
 
 @pytest.mark.parametrize("device", [False, True], ids=["host", "device"])
@@ -31,10 +44,16 @@ def test_scene_per_class_calls_vs_oracle(ctx, seed, npts, copies, device):
     from oracle import pb_oracle as po
     from pbnet_b200 import scenes
     sc = scenes.make_scene(seed, npts)
+    took_small = 0
     for c in scenes.class_calls(sc, copies):
         want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], H.R18, H.M18)
-        got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=device)
-        assert H.diff_report(got, want) == [], f"class {c['sem_id']}"
+        for small in (1, 0):   # the one-launch small-call kernel (when eligible) and the cell-grid pipeline
+            ctx.set_small_calls(small)
+            got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=device)
+            took_small += ctx.counters()["small_path"]
+            assert H.diff_report(got, want) == [], f"class {c['sem_id']} small={small}"
+    ctx.set_small_calls(-1)
+    assert took_small > 0
 
 
 @pytest.mark.parametrize("radius", [0.02, 0.03, 0.06])
@@ -45,8 +64,11 @@ def test_radius_sweep_vs_oracle(ctx, radius):
     r18 = np.full(18, np.float32(radius), np.float32)
     for c in scenes.class_calls(sc, 1):
         want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], r18, H.M18)
-        got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], radius=r18)
-        assert H.diff_report(got, want) == [], f"class {c['sem_id']} r={radius}"
+        for small in (1, 0):
+            ctx.set_small_calls(small)
+            got = H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], radius=r18)
+            assert H.diff_report(got, want) == [], f"class {c['sem_id']} r={radius} small={small}"
+    ctx.set_small_calls(-1)
 
 
 @pytest.mark.parametrize("chunk_points,device", [(0, True), (30000, True), (45000, False), (1, True)],
@@ -126,7 +148,16 @@ def test_centre_division_is_exact(ctx):
     assert ctx.selftest_division(1 << 26, seed=7) == 0
 
 
-def test_edge_cases(ctx):
+@pytest.mark.parametrize("small", [0, 1], ids=["grid-path", "small-call-kernel"])
+def test_edge_cases(ctx, small):
+    ctx.set_small_calls(small)
+    try:
+        _edge_cases(ctx)
+    finally:
+        ctx.set_small_calls(-1)
+
+
+def _edge_cases(ctx):
     from oracle import pb_oracle as po
     from pbnet_b200._lib import PBError
     rng = np.random.Generator(np.random.PCG64(5))

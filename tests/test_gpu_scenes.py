@@ -122,3 +122,34 @@ def test_propose_chain_matches_piecewise_torch():
     assert torch.equal(out["voxel_coords"].to(torch.int64)[vm.inverse], q)
     assert out["voxel_coords"].shape[0] == torch.unique(q, dim=0).shape[0]
     assert torch.equal(out["voxel_features"], want[vm.index])
+
+
+def test_front_end_rejects_bad_copy_index_and_skips_small_classes():
+    """pb_group_front (device-side class loop): a copy index outside [0, cluster_batch) is an error (the reference asserts
+    the per-copy counts add up, network/PBNet.py:282-287); classes below count_mean*0.05 are skipped; no class kept -> None."""
+    import torch
+    from pbnet_b200 import grouping, scenes
+    from pbnet_b200._lib import PBError
+    sc = scenes.make_scene(778, 30_000)
+    xyz, off, sem = _dev(sc["xyz_orig"]), _dev(sc["offset"]), _dev(sc["sem"])
+    bh = torch.zeros(xyz.shape[0], dtype=torch.int32, device="cuda")
+    flat = grouping.group_instances_flat(xyz, off, sem, bh, scenes.RADIUS, scenes.MIN_PTS, 1)
+    cnt = np.bincount(sc["sem"], minlength=20)
+    want = [c for c in range(2, 20) if not (np.float32(cnt[c]) < scenes.COUNT_MEAN[c] * np.float32(0.05))]
+    assert flat["classes"].tolist() == want
+    assert flat["seg_counts"].reshape(-1).tolist() == [int(cnt[c]) for c in want]
+    pi = flat["point_index"].cpu().numpy()
+    o = 0
+    for c in want:   # ins_ind of every class: ascending point indices of that class
+        assert np.array_equal(pi[o:o + cnt[c]], np.nonzero(sc["sem"] == c)[0])
+        o += cnt[c]
+    bad = bh.clone()
+    bad[17] = 1
+    with pytest.raises(PBError):
+        grouping.group_instances_flat(xyz, off, sem, bad, scenes.RADIUS, scenes.MIN_PTS, 1)
+    only_bg = torch.zeros_like(sem)
+    assert grouping.group_instances_flat(xyz, off, only_bg, bh, scenes.RADIUS, scenes.MIN_PTS, 1) is None
+    assert grouping.group_instances(xyz, off, only_bg, bh, scenes.RADIUS, scenes.MIN_PTS, 1) == []
+    # int64 copy indices are accepted as they are
+    flat64 = grouping.group_instances_flat(xyz, off, sem, bh.to(torch.int64), scenes.RADIUS, scenes.MIN_PTS, 1)
+    assert torch.equal(flat64["cluster_id"], flat["cluster_id"]) and torch.equal(flat64["point_index"], flat["point_index"])
