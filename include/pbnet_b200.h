@@ -106,7 +106,7 @@ int pb_binary_cluster_batched(pb_ctx *ctx, const float *x, const float *y, const
  * Results do not depend on the chunking. */
 void pb_set_chunk_points(pb_ctx *ctx, int64_t points);
 
-/* Calls of ONE reference call with at most 32 segments whose adjacency bitmaps fit 16 MB (a segment of up to ~11 k points:
+/* Calls of ONE reference call with at most 32 segments whose adjacency bitmaps fit 12 MB (a segment of up to ~10 k points:
  * the per-class calls of pbnet_ops.cluster) run as ONE cooperative launch of the small-call kernel (pb_small.cuh) instead of
  * the cell-grid pipeline.  mode 0 = never, 1 / -1 = whenever eligible (default).  Results are identical either way. */
 void pb_set_small_calls(pb_ctx *ctx, int mode);

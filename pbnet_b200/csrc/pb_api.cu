@@ -61,6 +61,7 @@ struct pb_ctx {
     float stage_ms[ST_COUNT] = {};
     int64_t counters[16] = {};
     // pinned scratch for scalars read back at the end of a call
+    int *h_small = nullptr;    // pinned [64]: scalars + phase time stamps of the small-call kernel
     int *h_scalars = nullptr;  // [0] err bits [1] C [2] R [3] K [4] Q [5] L
     unsigned long long *h_counters = nullptr;
     // chunked two-stream pipelining of large batched calls
@@ -125,7 +126,8 @@ extern "C" int pb_create(int device, pb_ctx **out) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scalars, 16 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_small, 64 * sizeof(int)) != cudaSuccess) {
         delete ctx;
         return PB_ERR_CUDA;
     }
@@ -165,6 +167,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
@@ -694,8 +697,11 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
 // ----------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int kNotSmall = -1;
-constexpr long long kSmallAdjWords = 1ll << 22;   // 16 MB of adjacency bitmap: one segment of ~11.5 k points
+constexpr long long kSmallAdjWords = 3ll << 20;   // 12 MB of adjacency bitmap: one segment of ~10 k points (measured on a B200:
+                                                  // 0.21 ms at 2.3 k points, 0.36 ms at 6 k vs 0.50 / 0.63 ms through the cell grid; the
+                                                  // O(n^2) phases cross over near 12 k points)
 constexpr int kSmallCentreHead = 256;             // clusters whose centres travel with the first read-back
+constexpr int kSmallHead = 48;                    // ints of scalars in front of the result block (16 scalars + 11 time stamps)
 }  // namespace
 
 static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z, const float *xo, const float *yo,
@@ -710,6 +716,7 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     int mask_words = 0;
     for (int s = 0; s < S; s++) {
         const int ns = start[s + 1] - start[s], W = (ns + 31) / 32;
+        if (W > 32 * pbsm::kWPL) return kNotSmall;
         a.start[s] = start[s], a.mask_off[s] = mask_words, a.adj_off[s] = adj_words;
         adj_words += (long long)ns * W;
         mask_words += W;
@@ -743,25 +750,26 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
         a.seg_of = ar.get<int>(N), a.parent = ar.get<int>(N), a.gid_at = ar.get<int>(N), a.raw_label = ar.get<int>(N);
         a.rep = ar.get<int>(N), a.keep = ar.get<int>(N), a.kscan = ar.get<int>(N), a.clt_seg = ar.get<int>(N);
         a.adj = ar.get<unsigned>((size_t)std::max<long long>(adj_words, 1));
+        a.root0 = ar.get<int>(N), a.best64 = ar.get<unsigned long long>(N);
         // zero-initialised region, ending with the scalars; the result block [scalars | cluster_num | cluster_id | degree]
         // starts there (one read-back when the results go to the host)
         zero_begin = reinterpret_cast<char *>(ar.get<char>(0));
         a.hpmask = ar.get<unsigned>(mask_words), a.labmask = ar.get<unsigned>(mask_words);
         a.flag = ar.get<int>(N), a.raw_count = ar.get<int>(N);
-        outblk = ar.get<int>(16 + pbsm::kMaxSeg + 2 * N);
+        outblk = ar.get<int>(kSmallHead + pbsm::kMaxSeg + 2 * N);
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
         }
     }
     a.scal = outblk;
-    const size_t zero_bytes = reinterpret_cast<char *>(outblk + 16) - zero_begin;
+    const size_t zero_bytes = reinterpret_cast<char *>(outblk + kSmallHead) - zero_begin;
     a.n = n, a.S = S, a.assign_lp = assign_lp;
     for (int i = 0; i < 18; i++) a.radius[i] = radius[i], a.min_pts[i] = min_pts[i], a.thresh[i] = kMeanCount[i] * para_f;
     a.sg.start = d_start, a.call_first = d_callfirst;
     // ---- inputs
     const size_t in_bytes = 7 * N * sizeof(float);
-    const size_t out_ints = 16 + pbsm::kMaxSeg + 2 * N;
+    const size_t out_ints = kSmallHead + pbsm::kMaxSeg + 2 * N;
     const size_t head_bytes = (size_t)kSmallCentreHead * 4 * sizeof(float);
     if (host_io) {
         const size_t need = std::max(in_bytes, out_ints * sizeof(int) + head_bytes);
@@ -778,7 +786,7 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
         PB_CUDA(cudaMemcpyAsync(din, hs, in_bytes, cudaMemcpyHostToDevice, st));
         a.x = din, a.y = din + N, a.z = din + 2 * N, a.xo = din + 3 * N, a.yo = din + 4 * N, a.zo = din + 5 * N;
         a.sem = reinterpret_cast<const int *>(din + 6 * N);
-        a.cluster_num = outblk + 16, a.cluster_id = outblk + 16 + pbsm::kMaxSeg, a.degree = outblk + 16 + pbsm::kMaxSeg + n;
+        a.cluster_num = outblk + kSmallHead, a.cluster_id = outblk + kSmallHead + pbsm::kMaxSeg, a.degree = outblk + kSmallHead + pbsm::kMaxSeg + n;
         a.center = d_center, a.clt_sem = d_cltsem;
     } else {
         a.x = x, a.y = y, a.z = z, a.xo = xo, a.yo = yo, a.zo = zo, a.sem = sem;
@@ -794,17 +802,17 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     ctx->launches = 1;
     // ---- results
     int *hres = reinterpret_cast<int *>(ctx->h_stage);
-    int scal_local[16];
+    int scal_local[kSmallHead];
     const int head = std::min(n, kSmallCentreHead);
     if (host_io) {
         PB_CUDA(cudaMemcpyAsync(hres, outblk, out_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaMemcpyAsync(hres + out_ints, d_center, sizeof(float) * 3 * head, cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaMemcpyAsync(hres + out_ints + 3 * kSmallCentreHead, d_cltsem, sizeof(int) * head, cudaMemcpyDeviceToHost, st));
     } else {
-        PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, outblk, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaMemcpyAsync(ctx->h_small, outblk, sizeof(int) * kSmallHead, cudaMemcpyDeviceToHost, st));
     }
     PB_CUDA(cudaStreamSynchronize(st));
-    const int *sc = host_io ? hres : ctx->h_scalars;
+    const int *sc = host_io ? hres : ctx->h_small;
     std::memcpy(scal_local, sc, sizeof(scal_local));
     const int errbits = scal_local[0];
     if (errbits & pb::kErrSem) return fail(ctx, PB_ERR_SEM_RANGE, "class id outside [2,19]");
@@ -813,9 +821,9 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     const long long K = scal_local[3];
     *n_clusters_out = K;
     if (host_io) {
-        std::memcpy(cluster_num, hres + 16, sizeof(int) * S);
-        std::memcpy(cluster_id, hres + 16 + pbsm::kMaxSeg, sizeof(int) * N);
-        std::memcpy(degree, hres + 16 + pbsm::kMaxSeg + N, sizeof(int) * N);
+        std::memcpy(cluster_num, hres + kSmallHead, sizeof(int) * S);
+        std::memcpy(cluster_id, hres + kSmallHead + pbsm::kMaxSeg, sizeof(int) * N);
+        std::memcpy(degree, hres + kSmallHead + pbsm::kMaxSeg + N, sizeof(int) * N);
     }
     if (K > 0) {
         if (!center || !clt_sem || 3LL * K > center_cap || K > clt_sem_cap)
@@ -832,6 +840,14 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     }
     if (call_clusters) call_clusters[0] = K;
     for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+    {   // phase times of the kernel (globaltimer stamps of the grid's first thread at every barrier)
+        unsigned long long ts[11];
+        std::memcpy(ts, scal_local + 16, sizeof(ts));
+        auto ms = [&](int i0, int i1) { return ts[i1] >= ts[i0] ? (float)((double)(ts[i1] - ts[i0]) * 1e-6) : 0.f; };
+        ctx->stage_ms[ST_DEGREE] = ms(0, 1), ctx->stage_ms[ST_HP] = ms(1, 2), ctx->stage_ms[ST_UNION] = ms(2, 3);
+        ctx->stage_ms[ST_COMPONENTS] = ms(3, 5), ctx->stage_ms[ST_LABEL] = ms(5, 6), ctx->stage_ms[ST_FILTER] = ms(6, 7);
+        ctx->stage_ms[ST_LP_BUILD] = ms(7, 8), ctx->stage_ms[ST_LP_NN] = ms(8, 9), ctx->stage_ms[ST_CENTRES] = ms(9, 10);
+    }
     for (int i = 0; i < 9; i++) ctx->counters[i] = 0;
     ctx->counters[5] = scal_local[2], ctx->counters[6] = 1;
     ctx->counters[9] = 1;   // small-call path taken

@@ -33,6 +33,7 @@ using pb::kFull;
 constexpr int kMaxSeg = 32;       // segments per small call
 constexpr int kQB = 8;            // query points per P1 task
 constexpr int kThreads = 256;
+constexpr int kWPL = 16;           // bitmask words per lane: a segment has at most 32*kWPL words = 16384 points
 
 struct SmallArgs {
     int n, S, assign_lp;
@@ -49,8 +50,10 @@ struct SmallArgs {
     pb::SegArrays sg;             // start, cls, min_pts, r2, k_base, cluster_num, id_base are used
     const int *call_first;        // [S] zeros (one call)
     unsigned *adj, *hpmask, *labmask;
+    int *root0;                   // root of every point in the P2 forest
+    unsigned long long *best64;   // P8: per point, min over candidates of (distance bits << 32 | ~index)
     int *seg_of, *parent, *flag, *gid_at, *raw_label, *raw_count, *rep, *keep, *kscan, *clt_seg;
-    int *scal;                    // [0] err [2] R [3] K [9] centre ticket
+    int *scal;                    // [0] err [2] R [3] K [9] centre ticket [16..39] phase time stamps (globaltimer ns, 64-bit)
 };
 
 __device__ __forceinline__ int seg_of_point(const SmallArgs &a, int i) {
@@ -83,6 +86,14 @@ __device__ __forceinline__ void block_scan_flags(const int *__restrict__ flag, i
     __syncthreads();
 }
 
+__device__ __forceinline__ void stamp(const SmallArgs &a, int k) {  // phase boundaries as seen by thread 0 of the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long *>(a.scal + 16)[k] = t;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_small(SmallArgs a) {
     cg::grid_group grid = cg::this_grid();
@@ -90,11 +101,13 @@ k_small(SmallArgs a) {
     __shared__ float s_buf[pb::kCtrWarps][3][pb::kCtrBuf + 128];
     __shared__ float s_rcp[pb::kCtrWarps][pb::kCtrBuf + 128];
     const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    // warp-task index: consecutive tasks go to DIFFERENT blocks, so a short task list still spreads over all SMs
+    const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarp = (gridDim.x * blockDim.x) >> 5;
     const int gthread = blockIdx.x * blockDim.x + threadIdx.x, nthread = gridDim.x * blockDim.x;
     const int n = a.n, S = a.S;
     int *d_err = a.scal, *d_R = a.scal + 2, *d_K = a.scal + 3;
 
+    stamp(a, 0);
     // device copies of the (by-value) segment table for the routines shared with the large path
     if (gthread <= S) const_cast<int *>(a.sg.start)[gthread] = a.start[gthread];
     if (gthread < S) const_cast<int *>(a.call_first)[gthread] = 0;
@@ -136,23 +149,39 @@ k_small(SmallArgs a) {
             }
             if (err) atomicOr(d_err, err);
             unsigned *row = a.adj + a.adj_off[s] + (long long)(q0 - b) * W;
-            // candidates: 32 per trip, the next trip's coordinates are fetched while this one is tested
-            float nx = 0.f, ny = 0.f, nz = 0.f;
-            if (b + lane < e) nx = __ldg(a.x + b + lane), ny = __ldg(a.y + b + lane), nz = __ldg(a.z + b + lane);
-            for (int vb = 0; vb < W; vb++) {
-                const bool valid = b + vb * 32 + lane < e;
-                const float cx = nx, cy = ny, cz = nz;
-                const int vn = b + (vb + 1) * 32 + lane;
-                if (vn < e) nx = __ldg(a.x + vn), ny = __ldg(a.y + vn), nz = __ldg(a.z + vn);
-                unsigned mine = 0u;
+            // candidates: 32 per word; the coordinates of the next FOUR words are in flight while four are tested (the loop
+            // is bound by L2 latency otherwise: one word of tests is ~100 instructions, a load ~600 cycles)
+            constexpr int PF = 4;
+            float nx[PF], ny[PF], nz[PF];
 #pragma unroll
-                for (int j = 0; j < kQB; j++) {
-                    bool hit = valid && pb::sqd(qx[j], qy[j], qz[j], cx, cy, cz) <= r2;
-                    unsigned wv = __ballot_sync(kFull, hit);
-                    cnt[j] += __popc(wv);
-                    if (lane == j) mine = wv;
+            for (int q = 0; q < PF; q++) {
+                int v = b + q * 32 + lane;
+                nx[q] = ny[q] = nz[q] = 0.f;
+                if (v < e) nx[q] = __ldg(a.x + v), ny[q] = __ldg(a.y + v), nz[q] = __ldg(a.z + v);
+            }
+            for (int vb0 = 0; vb0 < W; vb0 += PF) {
+                float cx[PF], cy[PF], cz[PF];
+#pragma unroll
+                for (int q = 0; q < PF; q++) {
+                    cx[q] = nx[q], cy[q] = ny[q], cz[q] = nz[q];
+                    int v = b + (vb0 + PF + q) * 32 + lane;
+                    if (v < e) nx[q] = __ldg(a.x + v), ny[q] = __ldg(a.y + v), nz[q] = __ldg(a.z + v);
                 }
-                if (lane < kQB && q0 + lane < e) row[(long long)lane * W + vb] = mine;
+#pragma unroll
+                for (int q = 0; q < PF; q++) {
+                    const int vb = vb0 + q;
+                    if (vb >= W) break;
+                    const bool valid = b + vb * 32 + lane < e;
+                    unsigned mine = 0u;
+#pragma unroll
+                    for (int j = 0; j < kQB; j++) {
+                        bool hit = valid && pb::sqd(qx[j], qy[j], qz[j], cx[q], cy[q], cz[q]) <= r2;
+                        unsigned wv = __ballot_sync(kFull, hit);
+                        cnt[j] += __popc(wv);
+                        if (lane == j) mine = wv;
+                    }
+                    if (lane < kQB && q0 + lane < e) row[(long long)lane * W + vb] = mine;
+                }
             }
             // degree (self excluded by position, binary_cuda_functions.cu:88), HP rule (:175-186)
             int mycnt = 0;
@@ -167,6 +196,7 @@ k_small(SmallArgs a) {
         }
     }
     grid.sync();
+    stamp(a, 1);
     // ---------------- P2: parent = smallest-index HP neighbour (self for the minimum of its neighbourhood) ----------
     for (int u = gthread; u < n; u += nthread) {
         int s = a.seg_of[u];
@@ -186,31 +216,84 @@ k_small(SmallArgs a) {
         a.parent[u] = p;   // p <= u
     }
     grid.sync();
-    // ---------------- P3: union-find over HP neighbours with a smaller index, 32 parents per load --------------------
-    for (int u = gwarp; u < n; u += nwarp) {
+    stamp(a, 2);
+    // ---------------- P3: components of the HP graph.
+    //   a) flatten the P2 forest (parent[u] = root of its tree): a neighbour whose PARENT equals the query's root is in the
+    //      query's component for sure, which is the cheap test of b)
+    //   b) union-find at WORD granularity over the HP neighbours with a smaller index (every edge once): the row's words
+    //      are fetched lane-parallel up front, the parent vectors of 8 words are in flight together; lanes whose parent
+    //      differs look their roots up in parallel (compressing paths), only a genuinely different root costs a union
+    for (int u = gthread; u < n; u += nthread) {   // a)
+        int s = a.seg_of[u];
+        const int lu = u - a.start[s];
+        int r = u;
+        if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) {
+            while (true) {
+                int p = __ldcg(a.parent + r);
+                if (p == r) break;
+                r = p;
+            }
+        }
+        a.root0[u] = r;
+    }
+    grid.sync();
+    for (int u = gthread; u < n; u += nthread) a.parent[u] = a.root0[u];
+    grid.sync();
+    for (int u = gwarp; u < n; u += nwarp) {       // b)
         int s = a.seg_of[u];
         const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lu = u - b;
         const unsigned *hm = a.hpmask + a.mask_off[s];
         if (!((hm[lu >> 5] >> (lu & 31)) & 1u)) continue;
         const unsigned *row = a.adj + a.adj_off[s] + (long long)lu * W;
+        const int nwords = (lu >> 5) + 1;   // strictly smaller indices: every edge once
+        unsigned wv[kWPL];
+#pragma unroll
+        for (int i = 0; i < kWPL; i++) {
+            int vb = i * 32 + lane;
+            wv[i] = vb < nwords ? (row[vb] & hm[vb]) : 0u;
+            if (vb == (lu >> 5)) wv[i] &= (1u << (lu & 31)) - 1u;
+        }
         int r = pb::uf_find(a.parent, u);
-        for (int vb = 0; vb <= (lu >> 5); vb++) {
-            unsigned w = row[vb] & hm[vb];
-            if (vb == (lu >> 5)) w &= (1u << (lu & 31)) - 1u;   // strictly smaller indices: every edge once
-            if (!w) continue;
-            int v = b + vb * 32 + lane;
-            bool foreign = ((w >> lane) & 1u) && __ldcg(a.parent + v) != r;
-            unsigned f = __ballot_sync(kFull, foreign);
-            while (f) {
-                int j = __ffs(f) - 1;
-                f &= f - 1;
-                if (lane == 0) pb::uf_union(a.parent, u, b + vb * 32 + j);
-                __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kWPL; i++) {
+            if (i * 32 >= nwords) break;
+            for (int k0 = 0; k0 < 32 && i * 32 + k0 < nwords; k0 += 8) {
+                unsigned w8[8];
+                int pv[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    w8[t] = __shfl_sync(kFull, wv[i], k0 + t);
+                    pv[t] = ((w8[t] >> lane) & 1u) ? __ldcg(a.parent + b + (i * 32 + k0 + t) * 32 + lane) : r;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    unsigned f = __ballot_sync(kFull, pv[t] != r);
+                    if (f) {
+                        const int v = b + (i * 32 + k0 + t) * 32 + lane;
+                        bool changed = false;
+                        while (f) {
+                            int rv = ((f >> lane) & 1u) ? pb::uf_find(a.parent, v) : r;
+                            unsigned g = __ballot_sync(kFull, rv != r);
+                            if (!g) break;
+                            int j = __ffs(g) - 1;
+                            if (lane == 0) pb::uf_union(a.parent, u, b + (i * 32 + k0 + t) * 32 + j);
+                            __syncwarp();
+                            r = pb::uf_find(a.parent, u);
+                            changed = true;
+                            f = g & ~(1u << j);
+                        }
+                        if (changed) {   // the batch's remaining parent vectors were fetched for the old root: refresh them
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                if (q > t) pv[q] = ((w8[q] >> lane) & 1u) ? __ldcg(a.parent + b + (i * 32 + k0 + q) * 32 + lane) : r;
+                        }
+                    }
+                }
             }
-            r = pb::uf_find(a.parent, u);
         }
     }
     grid.sync();
+    stamp(a, 3);
     // ---------------- P4a: flatten, flag the roots (root = minimum index of its component) ---------------------------
     for (int u = gthread; u < n; u += nthread) {
         int s = a.seg_of[u];
@@ -222,6 +305,7 @@ k_small(SmallArgs a) {
         }
     }
     grid.sync();
+    stamp(a, 4);
     // ---------------- P4b: raw ids = rank of the component's minimum HP index (binary.cu:161-166) --------------------
     if (blockIdx.x == 0) {
         block_scan_flags(a.flag, n, a.gid_at, d_R, s_scan);
@@ -229,6 +313,7 @@ k_small(SmallArgs a) {
             if (a.flag[u]) a.rep[a.gid_at[u]] = u;
     }
     grid.sync();
+    stamp(a, 5);
     // ---------------- P5: labels + cluster sizes -----------------------------------------------------------------------
     for (int p = gwarp; p < n; p += nwarp) {
         int s = a.seg_of[p];
@@ -239,10 +324,23 @@ k_small(SmallArgs a) {
             label = a.gid_at[__ldcg(a.parent + p)];
         } else {  // border LP: the LAST component that reaches it wins = maximum raw id (binary.cu:206-213)
             const unsigned *row = a.adj + a.adj_off[s] + (long long)lp * W;
+            unsigned wv[kWPL];
+#pragma unroll
+            for (int i = 0; i < kWPL; i++) {
+                int vb = i * 32 + lane;
+                wv[i] = vb < W ? (row[vb] & hm[vb]) : 0u;
+            }
             int best = -1;
-            for (int vb = 0; vb < W; vb++) {
-                unsigned w = row[vb] & hm[vb];
-                if ((w >> lane) & 1u) best = max(best, a.gid_at[__ldcg(a.parent + b + vb * 32 + lane)]);
+#pragma unroll
+            for (int i = 0; i < kWPL; i++) {
+                if (i * 32 >= W) break;
+                unsigned nz = __ballot_sync(kFull, wv[i] != 0u);   // words of this chunk that hold an HP neighbour
+                while (nz) {
+                    int k = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    unsigned w = __shfl_sync(kFull, wv[i], k);
+                    if ((w >> lane) & 1u) best = max(best, a.gid_at[__ldcg(a.parent + b + (i * 32 + k) * 32 + lane)]);
+                }
             }
             label = __reduce_max_sync(kFull, best);
         }
@@ -252,11 +350,13 @@ k_small(SmallArgs a) {
         }
     }
     grid.sync();
+    stamp(a, 6);
     // ---------------- P6: fragment filter, compaction, per-segment counts ----------------------------------------------
     if (blockIdx.x == 0)
         pb::filter_scan_block<false>(n, S, a.sg, d_R, a.rep, a.seg_of, a.raw_count, a.thresh, a.keep, a.kscan, d_K, a.sem,
                                      a.call_first, a.gid_at, a.cluster_num, s_scan);
     grid.sync();
+    stamp(a, 7);
     // ---------------- P7: final ids of the HP stage, labelled mask ----------------------------------------------------
     {
         const int words = a.mask_off[S];
@@ -274,41 +374,79 @@ k_small(SmallArgs a) {
                     lab = true;
                 }
                 a.cluster_id[u] = id;
+                a.best64[u] = ~0ull;
             }
             unsigned m = __ballot_sync(kFull, lab);
             if (lane == 0) a.labmask[wd] = m;
         }
     }
     grid.sync();
+    stamp(a, 8);
     // ---------------- P8: exact 1-NN of the unlabelled points (original coordinates) ----------------------------------
+    // task = (32 consecutive points as queries, one per lane) x (a slice of 512 candidates staged through shared memory
+    // 32 at a time); a lane walks its candidates in ascending order with '<=' (ties -> largest index, :282); slices merge
+    // through atomicMin on (distance bits << 32 | ~index): smallest distance first, then the largest index.
     if (a.assign_lp) {
-        for (int p = gwarp; p < n; p += nwarp) {
-            int s = a.seg_of[p];
-            const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lp = p - b;
+        constexpr int kSliceWords = 16;
+        float *stage = &s_buf[0][0][0] + (threadIdx.x >> 5) * 96;   // 32 candidates x 3 coordinates per warp
+        int t0[kMaxSeg + 1];
+        int nt = 0;
+        for (int s = 0; s < S; s++) {
+            const int W = a.mask_off[s + 1] - a.mask_off[s];
+            t0[s] = nt;
+            if (a.sg.cluster_num[s] > 0) nt += W * ((W + kSliceWords - 1) / kSliceWords);
+        }
+        t0[S] = nt;
+        for (int t = gwarp; t < nt; t += nwarp) {
+            int s = 0;
+            while (t0[s + 1] <= t) s++;
+            const int b = a.start[s], e = a.start[s + 1], W = a.mask_off[s + 1] - a.mask_off[s];
+            const int nsl = (W + kSliceWords - 1) / kSliceWords;
+            const int qw = (t - t0[s]) / nsl, sl = (t - t0[s]) % nsl;
             const unsigned *lm = a.labmask + a.mask_off[s];
-            if ((lm[lp >> 5] >> (lp & 31)) & 1u) continue;   // labelled
-            if (a.sg.cluster_num[s] <= 0) continue;            // nothing to assign to: stays -1
-            const float px = a.xo[p], py = a.yo[p], pz = a.zo[p];
+            const int u = b + qw * 32 + lane;
+            const bool active = u < e && !((lm[qw] >> lane) & 1u);   // unlabelled point of a segment that has clusters
+            if (!__any_sync(kFull, active)) continue;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (active) px = a.xo[u], py = a.yo[u], pz = a.zo[u];
             float bestD = __int_as_float(0x7f800000);
             int bestI = -1;
-            for (int vb = 0; vb < W; vb++) {
-                if ((lm[vb] >> lane) & 1u) {
-                    int v = b + vb * 32 + lane;
-                    float D = pb::sqd(px, py, pz, a.xo[v], a.yo[v], a.zo[v]);
-                    if (D <= bestD) bestD = D, bestI = v;   // ascending v: '<=' keeps the largest index (:282)
+            const int cw1 = min(W, (sl + 1) * kSliceWords);
+            int cw = sl * kSliceWords;
+            int vn = min(b + cw * 32 + lane, e - 1);
+            float nx = a.xo[vn], ny = a.yo[vn], nz = a.zo[vn];
+            for (; cw < cw1; cw++) {
+                const unsigned lw = lm[cw];
+                __syncwarp();
+                stage[lane] = nx, stage[32 + lane] = ny, stage[64 + lane] = nz;
+                __syncwarp();
+                if (cw + 1 < cw1) {
+                    vn = min(b + (cw + 1) * 32 + lane, e - 1);
+                    nx = a.xo[vn], ny = a.yo[vn], nz = a.zo[vn];
+                }
+                if (!lw) continue;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    float D = pb::sqd(px, py, pz, stage[k], stage[32 + k], stage[64 + k]);
+                    if (((lw >> k) & 1u) && D <= bestD) bestD = D, bestI = b + cw * 32 + k;
                 }
             }
-            unsigned db = __float_as_uint(bestD);   // D >= 0: the bit pattern is order preserving
-            unsigned dmin = __reduce_min_sync(kFull, db);
-            int imax = __reduce_max_sync(kFull, (db == dmin) ? bestI : -1);
-            if (lane == 0 && imax >= 0) a.cluster_id[p] = a.cluster_id[imax];
+            if (active && bestI >= 0)
+                atomicMin(a.best64 + u, ((unsigned long long)__float_as_uint(bestD) << 32) | (unsigned long long)(0xffffffffu - (unsigned)bestI));
         }
     }
     grid.sync();
+    for (int u = gthread; u < n; u += nthread) {
+        unsigned long long bv = a.best64[u];
+        if (a.assign_lp && a.cluster_id[u] < 0 && bv != ~0ull) a.cluster_id[u] = a.cluster_id[0xffffffffu - (unsigned)(bv & 0xffffffffull)];
+    }
+    grid.sync();
+    stamp(a, 9);
     // ---------------- P9: centres --------------------------------------------------------------------------------------
     if ((threadIdx.x >> 5) < pb::kCtrWarps)
         pb::centres_warp(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_buf[threadIdx.x >> 5],
                          s_rcp[threadIdx.x >> 5]);
+    stamp(a, 10);   // end of block 0's own centres (the last phase is not followed by a barrier)
 }
 
 }  // namespace pbsm
