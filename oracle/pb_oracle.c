@@ -374,6 +374,129 @@ static int grid_run(const grid_t *g, int64_t cx0, int64_t cx1, int64_t cy, int64
     return 1;
 }
 
+/* ---- LP assignment of one range of points (the grid variant's per-query search); queries are independent
+ *      (binary_cuda_functions.cu:258-302 runs one thread per noise point), so large segments — the C3 / C4 stress cases of
+ *      bench.py — spread them over the host cores with pthreads; results do not depend on it ---- */
+typedef struct {
+    const grid_t *lgp;
+    const float *xo, *yo, *zo;
+    const int *sem, *ids;
+    int *newid;
+    const int *lab;
+    int n_lab;
+    unsigned lab_classes;
+    int last_lab;
+    double gh;
+    int RING_MAX;
+    int n;
+    int64_t nnt, nnoise;
+    volatile int next; /* block ticket (threads) */
+} nn_ctx_t;
+
+static void nn_range(nn_ctx_t *c, int p0, int p1, int64_t *nnt_out, int64_t *nnoise_out) {
+    const grid_t lg = *c->lgp;
+    const float *xo = c->xo, *yo = c->yo, *zo = c->zo;
+    const int *sem = c->sem, *ids = c->ids, *lab = c->lab;
+    int *newid = c->newid;
+    const int n_lab = c->n_lab, last_lab = c->last_lab, RING_MAX = c->RING_MAX;
+    const unsigned lab_classes = c->lab_classes;
+    const double gh = c->gh;
+    int64_t nnt = 0, nnoise = 0;
+    for (int p = p0; p < p1; p++) {
+        if (ids[p] != -1) continue;
+        nnoise++;
+        if (!(lab_classes & (1u << sem[p]))) { /* fallback :287-300 */
+            newid[p] = ids[last_lab];
+            continue;
+        }
+        float px = xo[p], py = yo[p], pz = zo[p];
+        int64_t cx, cy, cz;
+        grid_cell(&lg, px, py, pz, &cx, &cy, &cz);
+        float best = 0.f;
+        int bestq = -1;
+        int done = 0;
+        for (int k = 0; k <= RING_MAX && !done; k++) {
+            /* scan the shell of Chebyshev radius k, row by row */
+            for (int64_t dz = -k; dz <= k; dz++)
+                for (int64_t dy = -k; dy <= k; dy++) {
+                    int full = (dz == -k || dz == k || dy == -k || dy == k);
+                    for (int part = 0; part < (full ? 1 : (k == 0 ? 1 : 2)); part++) {
+                        int64_t x0, x1;
+                        if (full) {
+                            x0 = cx - k;
+                            x1 = cx + k;
+                        } else {
+                            x0 = x1 = (part == 0) ? cx - k : cx + k;
+                        }
+                        int b, e;
+                        if (!grid_run(&lg, x0, x1, cy + dy, cz + dz, &b, &e)) continue;
+                        for (int j = b; j < e; j++) {
+                            int q = lg.ord[j];
+                            if (sem[q] != sem[p]) continue;
+                            float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
+                            nnt++;
+                            if (bestq < 0 || d < best || (d == best && q > bestq)) {
+                                best = d;
+                                bestq = q;
+                            }
+                        }
+                    }
+                }
+            /* every unscanned point is farther than k*gh in true distance */
+            double lim = (double)k * gh;
+            if (bestq >= 0 && (double)best < lim * lim * (1.0 - 1e-5)) done = 1;
+        }
+        if (!done) { /* brute force over all labelled points (literal scan) */
+            bestq = -1;
+            for (int i = 0; i < n_lab; i++) {
+                int q = lab[i];
+                if (sem[q] != sem[p]) continue;
+                float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
+                nnt++;
+                if (bestq < 0 || d <= best) {
+                    best = d;
+                    bestq = q;
+                }
+            }
+        }
+        newid[p] = ids[bestq];
+    }
+    *nnt_out = nnt;
+    *nnoise_out = nnoise;
+}
+
+#include <pthread.h>
+#include <unistd.h>
+static void *nn_worker(void *arg) {
+    nn_ctx_t *c = (nn_ctx_t *)arg;
+    int64_t nnt = 0, nnoise = 0;
+    for (;;) {
+        int blk = __sync_fetch_and_add(&c->next, 1);
+        long p0 = (long)blk * 1024;
+        if (p0 >= c->n) break;
+        int64_t a = 0, b = 0;
+        nn_range(c, (int)p0, (int)(p0 + 1024 < c->n ? p0 + 1024 : c->n), &a, &b);
+        nnt += a, nnoise += b;
+    }
+    __sync_fetch_and_add(&c->nnt, nnt);
+    __sync_fetch_and_add(&c->nnoise, nnoise);
+    return NULL;
+}
+static void nn_run(nn_ctx_t *c) {
+    long nthreads = c->n > 200000 ? sysconf(_SC_NPROCESSORS_ONLN) : 1;
+    if (nthreads > 64) nthreads = 64;
+    if (nthreads <= 1) {
+        nn_range(c, 0, c->n, &c->nnt, &c->nnoise);
+        return;
+    }
+    pthread_t th[64];
+    int started = 0;
+    for (long t = 0; t < nthreads; t++)
+        if (pthread_create(&th[started], NULL, nn_worker, c) == 0) started++;
+    if (started == 0) nn_worker(c);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
+
 static int grid_segment(int n, const float *x, const float *y, const float *z, const float *xo,
                         const float *yo, const float *zo, const int *sem, const float *radius,
                         const int *min_pts, float para_f, int nv_flag, int *ids, int *den, int acc,
@@ -537,65 +660,9 @@ static int grid_segment(int n, const float *x, const float *y, const float *z, c
             memcpy(newid, ids, sizeof(int) * n);
             int last_lab = lab[n_lab - 1];
             int64_t nnt = 0, nnoise = 0;
-            for (int p = 0; p < n; p++) {
-                if (ids[p] != -1) continue;
-                nnoise++;
-                if (!(lab_classes & (1u << sem[p]))) { /* fallback :287-300 */
-                    newid[p] = ids[last_lab];
-                    continue;
-                }
-                float px = xo[p], py = yo[p], pz = zo[p];
-                int64_t cx, cy, cz;
-                grid_cell(&lg, px, py, pz, &cx, &cy, &cz);
-                float best = 0.f;
-                int bestq = -1;
-                int done = 0;
-                for (int k = 0; k <= RING_MAX && !done; k++) {
-                    /* scan the shell of Chebyshev radius k, row by row */
-                    for (int64_t dz = -k; dz <= k; dz++)
-                        for (int64_t dy = -k; dy <= k; dy++) {
-                            int full = (dz == -k || dz == k || dy == -k || dy == k);
-                            for (int part = 0; part < (full ? 1 : (k == 0 ? 1 : 2)); part++) {
-                                int64_t x0, x1;
-                                if (full) {
-                                    x0 = cx - k;
-                                    x1 = cx + k;
-                                } else {
-                                    x0 = x1 = (part == 0) ? cx - k : cx + k;
-                                }
-                                int b, e;
-                                if (!grid_run(&lg, x0, x1, cy + dy, cz + dz, &b, &e)) continue;
-                                for (int j = b; j < e; j++) {
-                                    int q = lg.ord[j];
-                                    if (sem[q] != sem[p]) continue;
-                                    float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
-                                    nnt++;
-                                    if (bestq < 0 || d < best || (d == best && q > bestq)) {
-                                        best = d;
-                                        bestq = q;
-                                    }
-                                }
-                            }
-                        }
-                    /* every unscanned point is farther than k*gh in true distance */
-                    double lim = (double)k * gh;
-                    if (bestq >= 0 && (double)best < lim * lim * (1.0 - 1e-5)) done = 1;
-                }
-                if (!done) { /* brute force over all labelled points (literal scan) */
-                    bestq = -1;
-                    for (int i = 0; i < n_lab; i++) {
-                        int q = lab[i];
-                        if (sem[q] != sem[p]) continue;
-                        float d = sqd(px, py, pz, xo[q], yo[q], zo[q]);
-                        nnt++;
-                        if (bestq < 0 || d <= best) {
-                            best = d;
-                            bestq = q;
-                        }
-                    }
-                }
-                newid[p] = ids[bestq];
-            }
+            nn_ctx_t nc = {&lg, xo, yo, zo, sem, ids, newid, lab, n_lab, lab_classes, last_lab, gh, RING_MAX, n, 0, 0, 0};
+            nn_run(&nc);
+            nnt = nc.nnt, nnoise = nc.nnoise;
             memcpy(ids, newid, sizeof(int) * n);
             free(newid);
             grid_free(&lg);

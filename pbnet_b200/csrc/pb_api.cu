@@ -69,6 +69,7 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
+    int deg_slice_mult = 48; // PB_DEG_SLICES (measured on one 224 k-point scene: k_degree 271 us at 16, 211 us at 48): warps per SM that k_degree aims for on small problems (window splitting)
     int small_mode = -1;   // PB_SMALL=0: never use the small-call kernel; 1: whenever it is eligible; -1: automatic
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
     size_t h_stage_cap = 0;
@@ -147,6 +148,8 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         const char *sg = getenv("PB_STAGGER");
         ctx->stagger = sg && sg[0] == '1';
+        const char *ds = getenv("PB_DEG_SLICES");
+        if (ds && atoi(ds) > 0) ctx->deg_slice_mult = atoi(ds);
         const char *sm = getenv("PB_SMALL");
         ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
         const char *fh = getenv("PB_FUSE_HP");
@@ -221,7 +224,10 @@ extern "C" int64_t pb_counter(const pb_ctx *ctx, int i) { return (ctx && i >= 0 
 // ====================================================================================================
 namespace {
 
-constexpr int kTileItems = 16;                     // items per thread of the tile kernels (large path)
+#ifndef PB_TILE_ITEMS
+#define PB_TILE_ITEMS 16
+#endif
+constexpr int kTileItems = PB_TILE_ITEMS;          // items per thread of the tile kernels (large path)
 constexpr int kTile = pb::kTB * kTileItems;        // 4096 points per tile
 
 // Host-built, segment-aligned tile table of one chunk (pb::TileTab): [begin | count | seg | first | hslot | srow] x T
@@ -596,7 +602,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     {
         // small problems: several warps share one 128-point window and split its candidate stream
         const int windows = div_up(n, pb::kWindow);
-        const int nslice = std::max(1, std::min(32, (148 * 16) / windows));
+        const int nslice = std::max(1, std::min(32, (148 * ctx->deg_slice_mult) / windows));
         pb::HpOut hp;
         hp.pts4_w = reinterpret_cast<int *>(w.pts4), hp.degree_out = d_degree, hp.cell_hp = w.cell_hp, hp.cell_minhp = w.cell_minhp;
         hp.cell_first = w.cell_first, hp.counters = cnt;
@@ -672,7 +678,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         L++;
     }
     mark();  // CENTRES
-    pb::k_centres<<<gPersist, pb::kCtrWarps * 32, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
+    pb::k_centres<<<std::min(gPersist, 148 * 4), 256, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
                                                             w.d_scalars + 9);
     L++;
     mark();  // D2H

@@ -929,105 +929,146 @@ __global__ void k_selftest_division(unsigned long long n_samples, unsigned long 
     if (bad) atomicAdd(mismatches, bad);
 }
 
-// one warp: draws clusters from the ticket counter until none is left (all 32 lanes must call)
-__device__ __forceinline__ void centres_warp(int K, const SegArrays &sg, const int *__restrict__ clt_seg,
-                                             const int *__restrict__ cluster_id, const float *__restrict__ x,
-                                             const float *__restrict__ y, const float *__restrict__ z,
-                                             float *__restrict__ center, int *__restrict__ next_cluster,
-                                             float (*mybuf)[kCtrBuf + 128], float *myrcp) {
-    int lane = lane_id();
-    int coord = lane < 3 ? lane : 0;
-    while (true) {
-        int kk = 0;
-        if (lane == 0) kk = atomicAdd(next_cluster, 1);
-        kk = __shfl_sync(kFull, kk, 0);
-        if (kk >= K) break;
-        int s = clt_seg[kk];
-        int local = kk - sg.id_base[s];
-        int b = sg.start[s], e = sg.start[s + 1];
-        float M = 0.f;  // lane c < 3 carries coordinate c
-        int cnt = 0;
-        int fill = 0;
-        for (int ub = b; ub < e; ub += 128) {
-            // 128 points per trip, all 16 loads in flight together (the scan is pure memory latency)
-            int id[4];
-            float vx[4], vy[4], vz[4];
+// Block-level formulation (round 2): a block of 8 warps draws clusters from the ticket counter.  Warps 1-7 scan the
+// cluster's segment chunk by chunk and compact the members' coordinates (ascending point order) and the reciprocals of
+// their running counts into one half of a double buffer while warp 0 replays the recurrence over the other half — the
+// chain never waits for global memory, and the scan of a 27 k-point segment takes 25 trips instead of 215.
+constexpr int kCtrGatherWarps = 7;
+constexpr int kCtrChunkPts = kCtrGatherWarps * 160;   // points scanned per chunk (5 per gather lane)
+
+struct CtrSmem {
+    float buf[2][3][kCtrChunkPts];
+    float rcp[2][kCtrChunkPts];
+    int wcount[kCtrGatherWarps];
+    int m[2];       // members in each half
+    int cluster;    // ticket
+};
+
+__device__ __forceinline__ void ctr_gather(CtrSmem &sm, int half, int ub, int e, int local, int cnt_before,
+                                           const int *__restrict__ cluster_id, const float *__restrict__ x,
+                                           const float *__restrict__ y, const float *__restrict__ z) {
+    // called by warps 1..7; warp gw owns points [ub + gw*160, +160)
+    const int lane = lane_id(), gw = (threadIdx.x >> 5) - 1;
+    int id[5];
+    float vx[5], vy[5], vz[5];
+    unsigned mk[5];
+    int total = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int u = ub + 32 * j + lane;
-                bool ok = u < e;
-                id[j] = ok ? cluster_id[u] : -2;
-                vx[j] = ok ? x[u] : 0.f;
-                vy[j] = ok ? y[u] : 0.f;
-                vz[j] = ok ? z[u] : 0.f;
-            }
+    for (int j = 0; j < 5; j++) {
+        int u = ub + gw * 160 + j * 32 + lane;
+        bool ok = u < e;
+        id[j] = ok ? cluster_id[u] : -2;
+        vx[j] = ok ? x[u] : 0.f, vy[j] = ok ? y[u] : 0.f, vz[j] = ok ? z[u] : 0.f;
+    }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                bool hit = id[j] == local;
-                unsigned m = __ballot_sync(kFull, hit);
-                if (hit) {
-                    int o = fill + __popc(m & ((1u << lane) - 1));
-                    mybuf[0][o] = vx[j];
-                    mybuf[1][o] = vy[j];
-                    mybuf[2][o] = vz[j];
-                }
-                fill += __popc(m);
-            }
-            if (fill >= kCtrBuf || ub + 128 >= e) {  // flush: lanes 0..2 replay the recurrence in order
-                for (int t = lane; t < fill; t += 32) myrcp[t] = __frcp_rn((float)(cnt + t + 1));
-                __syncwarp();
-                const float *src = mybuf[coord];
-                bool fast = cnt + fill < (1 << 24) - 1;
-                if (fast) {
-                    // branch-free chain (FSUB, FMUL, 4 FFMA, FADD per member); the range guard of div_by_count
-                    // is evaluated off the chain and, if it ever trips, the flush is replayed with div.rn.f32
-                    float M0 = M;
-                    bool odd = false;
-#pragma unroll 4
-                    for (int t = 0; t < fill; t++) {
-                        float v = src[t];
-                        float y = myrcp[t];
-                        float fn = (float)(cnt + t + 1);
-                        float a = __fsub_rn(v, M);
-                        float q = __fmul_rn(a, y);
-                        float r = __fmaf_rn(-fn, q, a);
-                        q = __fmaf_rn(r, y, q);
-                        r = __fmaf_rn(-fn, q, a);
-                        q = __fmaf_rn(r, y, q);
-                        float aa = fabsf(a);
-                        odd |= !(aa > 1e-30f && aa < 1e30f) && a != 0.f;
-                        M = __fadd_rn(M, q);
-                    }
-                    if (odd) {
-                        M = M0;
-                        fast = false;
-                    } else {
-                        cnt += fill;
-                    }
-                }
-                if (!fast) {
-                    for (int t = 0; t < fill; t++) {
-                        float v = src[t];
-                        cnt++;
-                        M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
-                    }
-                }
-                fill = 0;
-                __syncwarp();
-            }
+    for (int j = 0; j < 5; j++) {
+        mk[j] = __ballot_sync(kFull, id[j] == local);
+        total += __popc(mk[j]);
+    }
+    if (lane == 0) sm.wcount[gw] = total;
+    asm volatile("bar.sync 1, 224;" ::: "memory");   // the seven gather warps only
+    int off = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < kCtrGatherWarps; k++) {
+        int c = sm.wcount[k];
+        off += k < gw ? c : 0;
+        all += c;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        if (id[j] == local) {
+            int o = off + __popc(mk[j] & ((1u << lane) - 1u));
+            sm.buf[half][0][o] = vx[j], sm.buf[half][1][o] = vy[j], sm.buf[half][2][o] = vz[j];
+            sm.rcp[half][o] = __frcp_rn((float)(cnt_before + o + 1));
         }
-        if (lane < 3) center[3 * kk + lane] = M;
+        off += __popc(mk[j]);
+    }
+    if (gw == 0 && lane == 0) sm.m[half] = all;
+    asm volatile("bar.sync 1, 224;" ::: "memory");   // wcount may be rewritten by the next chunk only after everyone read it
+}
+
+// lanes 0..2 of the calling warp replay x, y, z side by side over one half of the buffer
+__device__ __forceinline__ void ctr_chain(const CtrSmem &sm, int half, int fill, int &cnt, float &M, int coord) {
+    const float *src = sm.buf[half][coord];
+    const float *myrcp = sm.rcp[half];
+    bool fast = cnt + fill < (1 << 24) - 1;
+    if (fast) {
+        // branch-free chain (FSUB, FMUL, 4 FFMA, FADD per member); the range guard of div_by_count is evaluated off the
+        // chain and, if it ever trips, the half is replayed with div.rn.f32
+        float M0 = M;
+        bool odd = false;
+#pragma unroll 4
+        for (int t = 0; t < fill; t++) {
+            float v = src[t];
+            float y = myrcp[t];
+            float fn = (float)(cnt + t + 1);
+            float a = __fsub_rn(v, M);
+            float q = __fmul_rn(a, y);
+            float r = __fmaf_rn(-fn, q, a);
+            q = __fmaf_rn(r, y, q);
+            r = __fmaf_rn(-fn, q, a);
+            q = __fmaf_rn(r, y, q);
+            float aa = fabsf(a);
+            odd |= !(aa > 1e-30f && aa < 1e30f) && a != 0.f;
+            M = __fadd_rn(M, q);
+        }
+        if (odd) {
+            M = M0;
+            fast = false;
+        } else {
+            cnt += fill;
+        }
+    }
+    if (!fast) {
+        for (int t = 0; t < fill; t++) {
+            float v = src[t];
+            cnt++;
+            M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
+        }
     }
 }
 
-__global__ void __launch_bounds__(kCtrWarps * 32)
+// whole block (8 warps = 256 threads) must call
+__device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const int *__restrict__ clt_seg,
+                                              const int *__restrict__ cluster_id, const float *__restrict__ x,
+                                              const float *__restrict__ y, const float *__restrict__ z,
+                                              float *__restrict__ center, int *__restrict__ next_cluster, CtrSmem &sm) {
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int coord = lane < 3 ? lane : 0;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm.cluster = atomicAdd(next_cluster, 1);
+        __syncthreads();
+        const int kk = sm.cluster;
+        if (kk >= K) break;
+        const int s = clt_seg[kk];
+        const int local = kk - sg.id_base[s];
+        const int b = sg.start[s], e = sg.start[s + 1];
+        const int nchunks = (e - b + kCtrChunkPts - 1) / kCtrChunkPts;
+        float M = 0.f;   // lane c < 3 of warp 0 carries coordinate c
+        int cnt = 0;     // members replayed so far (warp 0) / gathered so far (warps 1..7)
+        if (wid > 0) ctr_gather(sm, 0, b, e, local, 0, cluster_id, x, y, z);
+        int gathered = 0;
+        for (int c = 0; c < nchunks; c++) {
+            __syncthreads();                      // half c&1 is complete
+            const int fill = sm.m[c & 1];
+            if (wid == 0) {
+                ctr_chain(sm, c & 1, fill, cnt, M, coord);
+            } else {
+                gathered += fill;
+                if (c + 1 < nchunks) ctr_gather(sm, (c + 1) & 1, b + (c + 1) * kCtrChunkPts, e, local, gathered, cluster_id, x, y, z);
+            }
+        }
+        if (wid == 0 && lane < 3) center[3 * kk + lane] = M;
+    }
+}
+
+__global__ void __launch_bounds__(256)
 k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
           const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
           const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster) {
-    __shared__ float buf[kCtrWarps][3][kCtrBuf + 128];
-    __shared__ float rcp[kCtrWarps][kCtrBuf + 128];
-    const int wid = threadIdx.x >> 5;
-    centres_warp(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, buf[wid], rcp[wid]);
+    __shared__ CtrSmem sm;
+    centres_block(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, sm);
 }
 
 // ------------------------------------------------------------------------------------------------

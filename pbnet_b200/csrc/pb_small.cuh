@@ -98,8 +98,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_small(SmallArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_scan[40];
-    __shared__ float s_buf[pb::kCtrWarps][3][pb::kCtrBuf + 128];
-    __shared__ float s_rcp[pb::kCtrWarps][pb::kCtrBuf + 128];
+    __shared__ pb::CtrSmem s_ctr;
     const int lane = threadIdx.x & 31;
     // warp-task index: consecutive tasks go to DIFFERENT blocks, so a short task list still spreads over all SMs
     const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -388,7 +387,7 @@ k_small(SmallArgs a) {
     // through atomicMin on (distance bits << 32 | ~index): smallest distance first, then the largest index.
     if (a.assign_lp) {
         constexpr int kSliceWords = 16;
-        float *stage = &s_buf[0][0][0] + (threadIdx.x >> 5) * 96;   // 32 candidates x 3 coordinates per warp
+        float *stage = &s_ctr.buf[0][0][0] + (threadIdx.x >> 5) * 96;   // 32 candidates x 3 coordinates per warp
         int t0[kMaxSeg + 1];
         int nt = 0;
         for (int s = 0; s < S; s++) {
@@ -443,9 +442,7 @@ k_small(SmallArgs a) {
     grid.sync();
     stamp(a, 9);
     // ---------------- P9: centres --------------------------------------------------------------------------------------
-    if ((threadIdx.x >> 5) < pb::kCtrWarps)
-        pb::centres_warp(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_buf[threadIdx.x >> 5],
-                         s_rcp[threadIdx.x >> 5]);
+    pb::centres_block(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_ctr);
     stamp(a, 10);   // end of block 0's own centres (the last phase is not followed by a barrier)
 }
 
