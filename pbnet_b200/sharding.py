@@ -15,12 +15,23 @@ from .workload import shard_scenes  # noqa: F401  (re-export)
 class Rank0Gather:
     """Variable-length gather of a 1-D tensor to rank 0 with the size exchange and the padded buffers set up
     ONCE (per-step cost = one buffer copy + one ``dist.gather``).  Works on any backend (nccl: device
-    tensors, gloo: CPU tensors)."""
+    tensors, gloo: CPU tensors).
 
-    def __init__(self, numel: int, dtype: torch.dtype, device, pad_value: int = -1):
+    ``narrow_to`` (e.g. ``torch.int16`` for cluster ids, which restart at 0 in every call and stay far below 32768)
+    halves the bytes on the wire; the caller promises the values fit.  ``overlap=True`` issues the collective
+    asynchronously on a side stream: ``__call__`` only waits until the local tensor has been copied into the send
+    buffer (so the producer may overwrite it in the next step) and returns; the transfer itself overlaps the next step's
+    kernels.  ``finish()`` waits for the last transfer and returns the per-rank views on rank 0."""
+
+    def __init__(self, numel: int, dtype: torch.dtype, device, pad_value: int = -1, narrow_to: torch.dtype | None = None,
+                 overlap: bool = False):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.numel = int(numel)
+        self.wire_dtype = narrow_to or dtype
+        self.overlap = bool(overlap)
+        self._work = None
+        self._last = None
         if self.world == 1:
             self.sizes = [self.numel]
             return
@@ -29,18 +40,59 @@ class Rank0Gather:
         dist.all_gather(sizes, n)
         self.sizes = [int(s.item()) for s in sizes]
         pad = max(self.sizes)
-        self.send = torch.full((pad,), pad_value, dtype=dtype, device=device)
-        self.recv = [torch.empty(pad, dtype=dtype, device=device) for _ in range(self.world)] if self.rank == 0 else None
+        self.send = torch.full((pad,), pad_value, dtype=self.wire_dtype, device=device)
+        self.recv = [torch.empty(pad, dtype=self.wire_dtype, device=device) for _ in range(self.world)] if self.rank == 0 else None
+        # a gather only moves bytes: the collectives see uint8 views (neither NCCL nor gloo has an int16 type)
+        self._send_b = self.send.view(torch.uint8)
+        self._recv_b = [r.view(torch.uint8) for r in self.recv] if self.rank == 0 else None
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if (self.cuda and self.overlap) else None
+        self.copied = torch.cuda.Event() if self.side is not None else None
 
-    def __call__(self, local: torch.Tensor):
-        """Returns the list of per-rank tensors (views into the receive buffers) on rank 0, None elsewhere."""
-        if self.world == 1:
-            return [local]
-        self.send[:self.numel].copy_(local)
-        dist.gather(self.send, self.recv, dst=0)
+    def _views(self):
         if self.rank != 0:
             return None
         return [r[:s] for r, s in zip(self.recv, self.sizes)]
+
+    def __call__(self, local: torch.Tensor):
+        """Blocking mode: returns the list of per-rank tensors (views into the receive buffers) on rank 0, None elsewhere.
+        Overlap mode: starts the gather and returns None; the result of the LAST call comes from ``finish()``."""
+        if self.world == 1:
+            self._last = [local]
+            return self._last
+        if self.side is None:
+            self.send[:self.numel].copy_(local)
+            if self.overlap:   # CPU / gloo: asynchronous work handle
+                if self._work is not None:
+                    self._work.wait()
+                self._work = dist.gather(self._send_b, self._recv_b, dst=0, async_op=True)
+                return None
+            dist.gather(self._send_b, self._recv_b, dst=0)
+            return self._views()
+        main = torch.cuda.current_stream(self.send.device)
+        self.side.wait_stream(main)                       # the producer of `local` has finished
+        with torch.cuda.stream(self.side):
+            if self._work is not None:
+                self._work.wait()                         # the previous transfer no longer reads `send`
+            self.send[:self.numel].copy_(local)           # (narrowing) copy, then the collective behind it
+            self.copied.record(self.side)
+            self._work = dist.gather(self._send_b, self._recv_b, dst=0, async_op=True)
+        main.wait_event(self.copied)                      # `local` may be overwritten from here on
+        return None
+
+    def finish(self):
+        """Waits for the outstanding transfer (overlap mode) and returns the per-rank views on rank 0."""
+        if self.world == 1:
+            return self._last
+        if self._work is not None:
+            if self.side is not None:
+                with torch.cuda.stream(self.side):
+                    self._work.wait()
+                torch.cuda.current_stream(self.send.device).wait_stream(self.side)
+            else:
+                self._work.wait()
+            self._work = None
+        return self._views()
 
 
 def gather_to_rank0(local: torch.Tensor, pad_value: int = -1):

@@ -38,6 +38,13 @@ def _worker(rank, world, port, sizes, q):
     w = workload.build(shards[rank], sizes, 1, workers=1, cache_dir=None)
     ids = torch.from_numpy(_run_calls(w))
     got = sharding.gather_to_rank0(ids)
+    # the overlapped, int16-on-the-wire form bench.py uses over NCCL: two steps in flight, result of the last one
+    g16 = sharding.Rank0Gather(ids.numel(), torch.int32, "cpu", narrow_to=torch.int16, overlap=True)
+    g16(torch.zeros_like(ids))
+    assert g16(ids) is None
+    got16 = g16.finish()
+    if rank == 0:
+        assert all(a.dtype == torch.int16 and torch.equal(a.to(torch.int32), b) for a, b in zip(got16, got))
     scene = sharding.gather_to_rank0(torch.from_numpy(w["call_scene"].astype(np.int32)))
     pts = sharding.gather_to_rank0(torch.from_numpy(w["call_points"].astype(np.int32)))
     if rank == 0:
