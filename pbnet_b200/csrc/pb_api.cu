@@ -69,6 +69,8 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
+    int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
+                             // registers stay free for the other chunk's latency-bound kernels (overlap experiment)
     int deg_slice_mult = 48; // PB_DEG_SLICES (measured on one 224 k-point scene: k_degree 271 us at 16, 211 us at 48): warps per SM that k_degree aims for on small problems (window splitting)
     int small_mode = -1;   // PB_SMALL=0: never use the small-call kernel; 1: whenever it is eligible; -1: automatic
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
@@ -148,6 +150,8 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         const char *sg = getenv("PB_STAGGER");
         ctx->stagger = sg && sg[0] == '1';
+        const char *dm = getenv("PB_DEG_SMEM");
+        if (dm && atoi(dm) > 0) ctx->deg_smem = atoi(dm);
         const char *ds = getenv("PB_DEG_SLICES");
         if (ds && atoi(ds) > 0) ctx->deg_slice_mult = atoi(ds);
         const char *sm = getenv("PB_SMALL");
@@ -608,12 +612,12 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         hp.cell_first = w.cell_first, hp.counters = cnt;
         const dim3 g(div_up(n, pb::kWindow * 4), nslice);
         if (nslice == 1 && !MIXED && ctx->fuse_hp) {  // one warp owns a window's whole candidate stream: HP rule + cell statistics fused in
-            pb::k_degree<true><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
+            pb::k_degree<true><<<g, 128, ctx->deg_smem, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
             PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
             mark();  // HP
         } else {
             if (nslice > 1) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
-            pb::k_degree<false><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
+            pb::k_degree<false><<<g, 128, nslice == 1 ? ctx->deg_smem : 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
             PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
             mark();  // HP
             pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
@@ -931,9 +935,11 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         // automatic: two chunks once a call has >= 6 M points (smaller chunks lose more to launch gaps and
         // kernel tails than the overlap wins: 48 ms at 2 chunks, 51 at 4, 59 at 10 for 28.8 M points)
         // host data: three chunks on the prioritised stream pair (the first H2D copy is the exposed head of the pipeline)
-        const int auto_chunks = host_io ? 3 : 2;
+        // (round 2, measured on 3.6 M points = one rank's share of C1 at 8 GPUs: 6.36 ms unchunked, 6.18 ms at 2 chunks,
+        // 7.1 / 7.4 ms at 3 / 4 chunks; from host memory 8.7 -> 7.9 ms at 2 chunks)
+        const int auto_chunks = n >= 6000000 ? (host_io ? 3 : 2) : (n >= 1500000 ? 2 : 1);
         long long target = ctx->chunk_points > 0 ? ctx->chunk_points
-                           : (ctx->chunk_points == 0 && n >= 6000000 ? ((long long)n + auto_chunks - 1) / auto_chunks : (long long)n + 1);
+                           : (ctx->chunk_points == 0 && auto_chunks > 1 ? ((long long)n + auto_chunks - 1) / auto_chunks : (long long)n + 1);
         int c = 0;
         while (c < n_calls) {
             Chunk ch;
