@@ -993,25 +993,42 @@ __device__ __forceinline__ void ctr_chain(const CtrSmem &sm, int half, int fill,
     const float *myrcp = sm.rcp[half];
     bool fast = cnt + fill < (1 << 24) - 1;
     if (fast) {
-        // branch-free chain (FSUB, FMUL, 4 FFMA, FADD per member); the range guard of div_by_count is evaluated off the
-        // chain and, if it ever trips, the half is replayed with div.rn.f32
+        // The recurrence runs on the ONE-correction quotient q1 (FSUB, FMUL, 2 FFMA, FADD on the chain: 5 dependent
+        // operations per member instead of 7); the second Markstein correction q2 = RN(a/n) is computed next to it, off
+        // the chain, and compared: if they ever differ (rare: q1 is already the correctly rounded quotient almost always),
+        // or the range guard of div_by_count trips, the half is replayed with div.rn.f32.  Results are bit-identical to
+        // M += (x - M) / n with IEEE division either way.
         float M0 = M;
         bool odd = false;
-#pragma unroll 4
-        for (int t = 0; t < fill; t++) {
-            float v = src[t];
-            float y = myrcp[t];
-            float fn = (float)(cnt + t + 1);
+        auto step = [&](float v, float y, float fn) {
             float a = __fsub_rn(v, M);
             float q = __fmul_rn(a, y);
             float r = __fmaf_rn(-fn, q, a);
-            q = __fmaf_rn(r, y, q);
-            r = __fmaf_rn(-fn, q, a);
-            q = __fmaf_rn(r, y, q);
+            float q1 = __fmaf_rn(r, y, q);
+            M = __fadd_rn(M, q1);
+            float r1 = __fmaf_rn(-fn, q1, a);
+            float q2 = __fmaf_rn(r1, y, q1);
             float aa = fabsf(a);
-            odd |= !(aa > 1e-30f && aa < 1e30f) && a != 0.f;
-            M = __fadd_rn(M, q);
+            odd |= (q2 != q1) | (!(aa > 1e-30f && aa < 1e30f) && a != 0.f);
+        };
+        // blocks of four members; the NEXT block's coordinates and reciprocals are fetched (two 16-byte shared loads) while
+        // this one runs, so the chain never waits for shared memory (counts stay below 2^24: float increments are exact)
+        float fn = (float)cnt;
+        int t = 0;
+        float4 v4 = *reinterpret_cast<const float4 *>(src), y4 = *reinterpret_cast<const float4 *>(myrcp);
+        for (; t + 4 <= fill; t += 4) {
+            const int tn = min(t + 4, kCtrChunkPts - 4);
+            const float4 nv = *reinterpret_cast<const float4 *>(src + tn), ny = *reinterpret_cast<const float4 *>(myrcp + tn);
+            step(v4.x, y4.x, fn + 1.f);
+            step(v4.y, y4.y, fn + 2.f);
+            step(v4.z, y4.z, fn + 3.f);
+            step(v4.w, y4.w, fn + 4.f);
+            fn += 4.f;
+            v4 = nv, y4 = ny;
         }
+        if (t < fill) step(v4.x, y4.x, fn + 1.f);
+        if (t + 1 < fill) step(v4.y, y4.y, fn + 2.f);
+        if (t + 2 < fill) step(v4.z, y4.z, fn + 3.f);
         if (odd) {
             M = M0;
             fast = false;
