@@ -6,7 +6,6 @@
 // (lib/PB_lib/src/pbnet/binary.cu).  Here ALL segments of ALL calls go through one fixed sequence
 // of ~25 launches per chunk (two chunk streams for large batches); the host reads three integers (the cell extents that
 // size the sort keys) in between and synchronises once at the end.
-#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -354,9 +353,9 @@ void plan(Arena &a, Work &w, long long n, int S, int T_max, int rows_max, int sl
     w.rel_state = a.get<unsigned long long>(std::max(T_max, 1));
     w.cnt18 = a.get<int>(mixed ? (size_t)S * pb::kCls + 1 : 1);
     w.zeroA_end = reinterpret_cast<char *>(a.get<char>(0));
-    // ---- zero-initialised region B: sort look-back state + digit histograms for up to 2*kMaxPasses passes
+    // ---- zero-initialised region B: sort look-back state + digit histograms for up to kMaxPassesGroup passes
     w.zeroB_begin = reinterpret_cast<char *>(a.get<char>(0));
-    w.zeroB_cap = ((size_t)std::max(rows_max, 1) + (size_t)std::max(slots_max, 1)) * 2 * pb::kMaxPasses * pb::kBins * sizeof(unsigned);
+    w.zeroB_cap = ((size_t)std::max(rows_max, 1) + (size_t)std::max(slots_max, 1)) * pb::kMaxPassesGroup * pb::kBins * sizeof(unsigned);
     a.get<char>(w.zeroB_cap);
 }
 
@@ -397,6 +396,81 @@ void launch_scan(cudaStream_t st, const int *in, int n_host, const int *n_dev, i
 }
 }  // namespace
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Generic stable LSD radix sort of n (key[, payload]) pairs over key bits [0, end_bit) with the hand-written tile sort
+// (pb_sort.cuh, one segment): what voxelize, the local scenes, the evaluation post-processing and the mesh normals use
+// (thrust / CUB in the reference and in round 1).  Inputs are preserved; the result lands in key_out / val_out.
+// ----------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct RadixTmp {   // scratch of ONE sort, carved from caller-provided device memory
+    static size_t bytes(size_t n, size_t key_size) {
+        const size_t T = (n + kTile - 1) / kTile + 1;
+        auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+        return al(n * key_size) + al(n * 4) * 2 + al((6 * T + 2) * 4) + al((size_t)pb::kMaxPasses * pb::kBins * 4) +
+               al((size_t)pb::kMaxPasses * T * pb::kBins * 4) + al(64) + 1024;
+    }
+};
+
+template <typename KeyT>
+int radix_sort(pb_ctx *ctx, void *tmp, const KeyT *key_in, KeyT *key_out, const uint32_t *val_in, uint32_t *val_out, int n,
+               int end_bit, cudaStream_t st, int64_t *launches) {
+    if (n <= 0) return PB_OK;
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    TileHost th;
+    const int start2[2] = {0, n};
+    build_tiles(start2, 1, kTile, th);
+    const int T = th.T;
+    char *p = reinterpret_cast<char *>(tmp);
+    KeyT *key_tmp = reinterpret_cast<KeyT *>(p); p += al((size_t)n * sizeof(KeyT));
+    uint32_t *val_tmp = reinterpret_cast<uint32_t *>(p); p += al((size_t)n * 4);
+    uint32_t *val_dummy = reinterpret_cast<uint32_t *>(p); p += al((size_t)n * 4);
+    int *tile_dev = reinterpret_cast<int *>(p); p += al(((size_t)6 * T + 2) * 4);
+    char *zero_begin = p;
+    unsigned *hist = reinterpret_cast<unsigned *>(p); p += al((size_t)pb::kMaxPasses * pb::kBins * 4);
+    const pb::PassPlan plan = pb::make_pass_plan(std::max(1, std::min(end_bit, (int)sizeof(KeyT) * 8)));
+    unsigned *state = reinterpret_cast<unsigned *>(p); p += al((size_t)plan.npass * std::max(th.rows, 1) * pb::kBins * 4);
+    int *tickets = reinterpret_cast<int *>(p); p += al(64);
+    if (!val_out) val_out = val_dummy;   // keys only: the payloads still travel (into scratch)
+    std::vector<int> hdr((size_t)6 * T + 2);
+    std::memcpy(hdr.data(), th.buf.data(), sizeof(int) * (size_t)6 * T);
+    hdr[6 * T] = 0, hdr[6 * T + 1] = n;
+    PB_CUDA(cudaMemcpyAsync(tile_dev, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemsetAsync(zero_begin, 0, p - zero_begin, st));
+    pb::TileTab tt;
+    tt.begin = tile_dev, tt.count = tile_dev + T, tt.seg = tile_dev + 2 * T, tt.first = tile_dev + 3 * T, tt.hslot = tile_dev + 4 * T;
+    tt.srow = tile_dev + 5 * T, tt.T = T;
+    const int *seg_start = tile_dev + 6 * T;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[sizeof(KeyT) == 8]) {
+        cudaFuncSetAttribute(pb::k_sort_pass<KeyT, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<KeyT, kTileItems>));
+        attr_done[sizeof(KeyT) == 8] = true;
+    }
+    if (T > 1) {
+        pb::k_radix_hist<KeyT><<<std::min(div_up(n, pb::kTB * 8), 148 * 8), pb::kTB, 0, st>>>(key_in, n, plan, hist);
+        if (launches) (*launches)++;
+    }
+    // ping-pong between the scratch buffer and the output so that the LAST pass writes the output; the input is only read
+    const KeyT *kin = key_in;
+    const uint32_t *vin = val_in;
+    for (int ps = 0; ps < plan.npass; ps++) {
+        const bool to_out = ((plan.npass - 1 - ps) & 1) == 0;
+        pb::SortArgs<KeyT> a;
+        a.keys_in = kin, a.keys_out = to_out ? key_out : key_tmp, a.vals_in = vin, a.vals_out = to_out ? val_out : val_tmp;
+        a.hist = hist, a.hist_stride = plan.npass * pb::kBins, a.hist_off = ps * pb::kBins;
+        a.state = state + (size_t)ps * std::max(th.rows, 1) * pb::kBins, a.ticket = tickets + ps;
+        a.shift = plan.shift[ps], a.width = plan.width[ps];
+        pb::k_sort_pass<KeyT, kTileItems><<<dim3(T, 1), pb::kTB, sizeof(pb::SortSmem<KeyT, kTileItems>), st>>>(a, a, tt, seg_start);
+        if (launches) (*launches)++;
+        kin = a.keys_out, vin = a.vals_out;
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace
 
 namespace {
 
@@ -1334,10 +1408,7 @@ extern "C" int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int s
         int *head = a.get<int>(N), *ex = a.get<int>(N);
         int *mnmx = a.get<int>(16);
         int *blocks = a.get<int>(N / pb::kScanTile + 2);
-        size_t cub_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
-        void *cub_tmp = a.get<char>(cub_bytes);
+        void *sort_tmp = a.get<char>(RadixTmp::bytes(N, sizeof(uint64_t)));
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
@@ -1369,10 +1440,24 @@ extern "C" int pb_voxelize(pb_ctx *ctx, const void *coords, int coord_f64, int s
             pbv::k_quantize<double><<<g, T, 0, st>>>((const double *)c_in, stride, has_batch_col, b_in, n, voxel_size, q, mnmx, mnmx + 4);
         else
             pbv::k_quantize<float><<<g, T, 0, st>>>((const float *)c_in, stride, has_batch_col, b_in, n, (float)voxel_size, q, mnmx, mnmx + 4);
+        // the key holds only the occupied bits of (batch, x, y, z) relative to the per-call minimum: the host reads the
+        // extents (one small synchronisation) to size the radix passes — 26 bits = 3 passes for a ScanNet scene at 2 cm
+        PB_CUDA(cudaMemcpyAsync(ctx->h_scalars, mnmx, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        int key_bits = 0;
+        for (int k = 0; k < 4; k++) {
+            long long ext = (long long)ctx->h_scalars[4 + k] - ctx->h_scalars[k];
+            if (ext > 65535) return fail(ctx, PB_ERR_RANGE, "voxel grid spans more than 65535 cells along an axis");
+            key_bits += pb::bit_width_i((int)ext);
+        }
         pbv::k_vox_keys<<<g, T, 0, st>>>(q, n, mnmx, mnmx + 4, key, val, d_err);
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, key, key_alt, val, ord, (int)n, 0, 64, st));
+        L += 2;
+        {
+            int rc = radix_sort<uint64_t>(ctx, sort_tmp, key, key_alt, val, ord, (int)n, key_bits, st, &L);
+            if (rc) return rc;
+        }
         pbv::k_vox_heads<<<g, T, 0, st>>>(key_alt, n, head);
-        L += 3 + 10;
+        L++;
         launch_scan(st, head, (int)n, nullptr, ex, d_V, blocks, L);
         pbv::k_vox_table<<<g, T, 0, st>>>(q, ord, head, ex, n, d_vcoords, d_index, d_inverse, d_order, d_vstart, d_V);
         L++;
@@ -1616,12 +1701,7 @@ extern "C" int pb_local_scenes_plan(pb_ctx *ctx, const int32_t *cluster_id, cons
         unsigned long long *best = a.get<unsigned long long>(K);
         uint64_t *lkey = train ? a.get<uint64_t>(N) : nullptr, *lkey_alt = train ? a.get<uint64_t>(N) : nullptr;
         int *blocks = a.get<int>(std::max(N, (size_t)K) / pb::kScanTile + 2);
-        size_t cub_bytes = 0, cub64 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32);
-        if (train) cub::DeviceRadixSort::SortKeys(nullptr, cub64, (const uint64_t *)nullptr, (uint64_t *)nullptr, n, 0, 64);
-        cub_bytes = std::max(cub_bytes, cub64);
-        void *cub_tmp = a.get<char>(cub_bytes);
+        void *sort_tmp = a.get<char>(RadixTmp::bytes(N, train ? sizeof(uint64_t) : sizeof(uint32_t)));
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
@@ -1643,16 +1723,20 @@ extern "C" int pb_local_scenes_plan(pb_ctx *ctx, const int32_t *cluster_id, cons
         pbs::k_cluster_seg<<<div_up(S, T), T, 0, st>>>(S, gstart, cseg);
         int bits = 1;
         while ((1 << bits) <= K) bits++;
-        size_t cb = cub_bytes;
-        PB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, key, key_alt, val, members, n, 0, bits, st));
-        L += 2 + 2 + (bits + 7) / 8;
+        L += 2;
+        {
+            int rc = radix_sort<uint32_t>(ctx, sort_tmp, key, key_alt, val, members, n, bits, st, &L);
+            if (rc) return rc;
+        }
         launch_scan(st, size, K + 1, nullptr, mstart, d_scal + 3, blocks, L);
         if (train) {
             pbs::k_label_keys<<<div_up(n, T), T, 0, st>>>(n, key, (const long long *)ins_label, K, lkey, d_scal);
-            cb = cub_bytes;
-            PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, lkey, lkey_alt, n, 0, 32 + bits, st));
+            {
+                int rc = radix_sort<uint64_t>(ctx, sort_tmp, lkey, lkey_alt, nullptr, nullptr, n, 32 + bits, st, &L);
+                if (rc) return rc;
+            }
             pbs::k_label_mode<<<div_up(n, T), T, 0, st>>>(n, lkey_alt, K, best);
-            L += 2 + 2 + (32 + bits + 7) / 8;
+            L += 2;
         }
         pbs::k_cluster_plan<<<div_up(K, 128), 128, 0, st>>>(K, cseg, gstart, d_sem, center, size, d_thr, d_kmax, best, train ? 1 : 0,
                                                             para, nb, len, valid, mode);
@@ -1823,8 +1907,7 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     int *inter = nullptr, *order = nullptr, *pick_rank = nullptr, *picked = nullptr, *alive = nullptr, *newid = nullptr;
     long long *prop_sem = nullptr, *d_table = nullptr;
     unsigned long long *best = nullptr;
-    void *cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    void *sort_tmp = nullptr;
     for (int pass = 0; pass < 2; pass++) {
         Arena dry;
         dry.dry = true;
@@ -1836,9 +1919,7 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
         inter = a.get<int>((size_t)vmax * vmax), order = a.get<int>(vmax), pick_rank = a.get<int>(vmax), picked = a.get<int>(vmax);
         alive = a.get<int>(vmax), newid = a.get<int>((size_t)vmax + 1);
         best = a.get<unsigned long long>((size_t)std::max(nsp, 1));
-        cub_bytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)Mz, 0, 64);
-        cub_tmp = a.get<char>(cub_bytes);
+        sort_tmp = a.get<char>(RadixTmp::bytes(Mz, sizeof(uint64_t)));
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
@@ -1852,9 +1933,11 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     pbe::k_pair_keys<<<div_up(std::max<long long>(M, P), T), T, 0, st>>>(M, P, point_num, n3, (const long long *)proposals_idx,
                                                                           (const long long *)proposals_offset, (const long long *)pred_sem,
                                                                           d_table, n_table, key, prop_sem, d_err);
-    size_t cb = cub_bytes;
     int bits1 = bit_width_u64((unsigned long long)P * (unsigned long long)n3 + 1);
-    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, (int)M, 0, bits1, st));
+    {
+        int rc = radix_sort<uint64_t>(ctx, sort_tmp, key, key_alt, nullptr, nullptr, (int)M, bits1, st, nullptr);
+        if (rc) return rc;
+    }
     pbe::k_pair_heads<<<div_up(M, T), T, 0, st>>>(M, n3, key_alt, head, npoint);
     pbe::k_valid<<<div_up(P, T), T, 0, st>>>(P, clt_score, score_thresh, npoint, npoint_thresh, valid);
     L += 3 + 2 + (bits1 + 7) / 8;
@@ -1880,8 +1963,10 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     PB_CUDA(cudaMemsetAsync(inter, 0, sizeof(int) * (size_t)V * V, st));
     pbe::k_point_keys<<<div_up(M, T), T, 0, st>>>(M, n3, key_alt, head, valid, vid, d_V, key2);
     int bits2 = bit_width_u64((unsigned long long)n3 * (unsigned long long)V + 1);
-    cb = cub_bytes;
-    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key2, key2_alt, (int)M, 0, bits2, st));
+    {
+        int rc = radix_sort<uint64_t>(ctx, sort_tmp, key2, key2_alt, nullptr, nullptr, (int)M, bits2, st, nullptr);
+        if (rc) return rc;
+    }
     pbe::k_intersections<<<div_up(M, T), T, 0, st>>>(M, key2_alt, d_V, inter);
     pbe::k_nms<<<1, 1024, 0, st>>>(d_V, vlist, clt_score, inter, nms_thresh, order, pick_rank, picked, d_C);
     // ---- per-point labels, superpoint vote, rebuilt clusters ---------------------------------------------------------------
@@ -1889,8 +1974,10 @@ extern "C" int pb_eval_postprocess(pb_ctx *ctx, const int64_t *proposals_idx, in
     pbe::k_paint<<<div_up(M, T), T, 0, st>>>(M, key2_alt, d_V, pick_rank, label);
     pbe::k_vote_keys<<<div_up(n3, T), T, 0, st>>>(n3, (const long long *)superpoint, nsp, label, d_C, key, d_err);
     int bits3 = bit_width_u64((unsigned long long)std::max(nsp, 1) * (unsigned long long)(V + 1) + 1);
-    cb = cub_bytes;
-    PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, n3, 0, bits3, st));
+    {
+        int rc = radix_sort<uint64_t>(ctx, sort_tmp, key, key_alt, nullptr, nullptr, n3, bits3, st, nullptr);
+        if (rc) return rc;
+    }
     PB_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)std::max(nsp, 1), st));
     PB_CUDA(cudaMemsetAsync(alive, 0, sizeof(int) * (size_t)V, st));
     PB_CUDA(cudaMemcpyAsync(ctx->h_scalars + 4, d_scal, sizeof(int), cudaMemcpyDeviceToHost, st));  // superpoint range check
@@ -1931,8 +2018,7 @@ extern "C" int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *
     float *d_xyz = nullptr, *d_out = nullptr, *fnormal = nullptr, *farea = nullptr;
     int *d_face = nullptr, *d_err = nullptr;
     uint64_t *key = nullptr, *key_alt = nullptr;
-    void *cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    void *sort_tmp = nullptr;
     for (int pass = 0; pass < 2; pass++) {
         Arena dry;
         dry.dry = true;
@@ -1943,9 +2029,7 @@ extern "C" int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *
         fnormal = a.get<float>(std::max<size_t>(NK, 1)), farea = a.get<float>(std::max<size_t>(F, 1));
         key = a.get<uint64_t>(std::max<size_t>(NK, 1)), key_alt = a.get<uint64_t>(std::max<size_t>(NK, 1));
         d_err = a.get<int>(4);
-        cub_bytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)std::max<size_t>(NK, 1), 0, 64);
-        cub_tmp = a.get<char>(cub_bytes);
+        sort_tmp = a.get<char>(RadixTmp::bytes(std::max<size_t>(NK, 1), sizeof(uint64_t)));
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
@@ -1964,9 +2048,10 @@ extern "C" int pb_cal_normal_line(pb_ctx *ctx, const float *xyz, const int32_t *
     const uint64_t *skey = key_alt;
     if (num_face > 0) {
         pbn::k_face_normals<<<div_up(num_face, T), T, 0, st>>>(x_in, f_in, num_face, num_vtx, fnormal, farea, key, d_err);
-        size_t cb = cub_bytes;
-        PB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cb, key, key_alt, (int)NK, 0, 64, st));
-        ctx->launches += 1 + 10;
+        // key = vertex << 32 | face (all ones for the unused corners of degenerate faces): 32 + bits(num_vtx) key bits
+        int rc = radix_sort<uint64_t>(ctx, sort_tmp, key, key_alt, nullptr, nullptr, (int)NK, 32 + pb::bit_width_i(num_vtx), st, &ctx->launches);
+        if (rc) return rc;
+        ctx->launches += 1;
     }
     pbn::k_vertex_normals<<<div_up(num_vtx, T), T, 0, st>>>(num_vtx, (long long)NK, skey, fnormal, farea, o);
     ctx->launches++;

@@ -244,7 +244,7 @@ k_keys(TileTab tt, SegArrays sg, KeysArgs ka, const float *__restrict__ x, const
        const float *__restrict__ z, const float *__restrict__ xo, const float *__restrict__ yo,
        const float *__restrict__ zo, const int *__restrict__ sem, void *__restrict__ key1, uint32_t *__restrict__ key2,
        int *err, const float *__restrict__ radius_tab, int *__restrict__ cnt18) {
-    __shared__ unsigned shist[2 * kMaxPasses * kBins];  // 20 KB
+    __shared__ unsigned shist[kMaxPassesGroup * kBins];  // 18 KB
     for (int t = blockIdx.x; t < tt.T; t += gridDim.x)
         keys_tile<MIXED, ITEMS>(tt, t, sg, ka, x, y, z, xo, yo, zo, sem, key1, key2, err, radius_tab, cnt18, shist);
 }

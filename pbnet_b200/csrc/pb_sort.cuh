@@ -21,7 +21,8 @@ namespace pb {
 constexpr int kTB = 256;            // threads per block of every tile kernel
 constexpr int kRadixBitsMax = 9;
 constexpr int kBins = 1 << kRadixBitsMax;  // 512
-constexpr int kMaxPasses = 5;       // 42 key bits / 9
+constexpr int kMaxPasses = 8;       // 64 key bits / 9 (the grouping path needs at most 5 + 4)
+constexpr int kMaxPassesGroup = 9;  // passes of BOTH grouping sorts together: 42-bit cell keys (5) + 32-bit Morton/class keys (4)
 
 // Segment-aligned tiles of the point range (host-built, one upload per call)
 struct TileTab {
@@ -245,6 +246,28 @@ k_sort_pass(SortArgs<KeyT> a0, SortArgs<KeyT> a1, TileTab tt, const int *__restr
     const int t = s.tile;
     if (t >= tt.T) return;
     sort_tile<KeyT, ITEMS>(a, tt, seg_start, t, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic use (voxelize, local scenes, evaluation, normals): ONE segment covering all n keys.  The digit histograms of all
+// passes come from one sweep over the keys (the grouping path gets them for free from k_keys).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(kTB)
+k_radix_hist(const KeyT *__restrict__ keys, int n, PassPlan plan, unsigned *__restrict__ hist) {
+    __shared__ unsigned sh[kMaxPasses * kBins];
+    const int nh = plan.npass * kBins;
+    for (int i = threadIdx.x; i < nh; i += kTB) sh[i] = 0u;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * kTB + threadIdx.x; i < n; i += (long long)gridDim.x * kTB) {
+        KeyT k = keys[i];
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; p++)
+            if (p < plan.npass) atomicAdd(sh + p * kBins + ((unsigned)(k >> plan.shift[p]) & ((1u << plan.width[p]) - 1u)), 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nh; i += kTB)
+        if (sh[i]) atomicAdd(hist + i, sh[i]);
 }
 
 }  // namespace pb

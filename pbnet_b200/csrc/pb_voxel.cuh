@@ -50,7 +50,11 @@ __global__ void k_quantize(const T *__restrict__ coords, int stride, int has_bat
     }
 }
 
-// K-V2  64-bit key = (b-bmin)<<48 | (x-xmin)<<32 | (y-ymin)<<16 | (z-zmin); lexicographic (b,x,y,z)
+// K-V2  key = (b-bmin) | (x-xmin) | (y-ymin) | (z-zmin), each field as wide as its occupied range (the host sizes the radix
+//       passes from the same extents); lexicographic (b,x,y,z)
+__device__ __forceinline__ int vox_bits(int ext) {  // bits needed for values 0..ext, at least 1 (= pb::bit_width_i)
+    return ext > 0 ? 32 - __clz(ext) : 1;
+}
 __global__ void k_vox_keys(const int4 *__restrict__ q, long long n, const int *__restrict__ mn, const int *__restrict__ mx,
                            uint64_t *__restrict__ key, uint32_t *__restrict__ val, int *err) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,10 +63,11 @@ __global__ void k_vox_keys(const int4 *__restrict__ q, long long n, const int *_
         for (int k = 0; k < 4; k++)
             if ((long long)mx[k] - mn[k] > 65535) atomicOr(err, 4);  // PB_ERR_RANGE
     }
+    const int wx = vox_bits(mx[1] - mn[1]), wy = vox_bits(mx[2] - mn[2]), wz = vox_bits(mx[3] - mn[3]);
     int4 v = q[i];
     uint64_t b = (uint64_t)(unsigned)(v.x - mn[0]) & 0xffff, x = (uint64_t)(unsigned)(v.y - mn[1]) & 0xffff,
              y = (uint64_t)(unsigned)(v.z - mn[2]) & 0xffff, z = (uint64_t)(unsigned)(v.w - mn[3]) & 0xffff;
-    key[i] = (b << 48) | (x << 32) | (y << 16) | z;
+    key[i] = (b << (wx + wy + wz)) | (x << (wy + wz)) | (y << wz) | z;
     val[i] = (uint32_t)i;
 }
 
