@@ -32,7 +32,7 @@ REF_WRAPPER = "/root/reference/lib/PB_lib/torch_io/pbnet_ops.py"
 
 
 def wrapper_pyc() -> str:
-    return os.path.join(OUT, "ref_pbnet_ops.pyc")
+    return os.path.join(OUT, "ref_pbnet_ops.pyc.bin")
 
 
 def build_wrapper(force: bool = False) -> str | None:

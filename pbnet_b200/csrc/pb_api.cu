@@ -68,6 +68,8 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
+    int tile_mode = -1;      // PB_TILES: 1 = tiles of 1024 points, 0 = 4096, -1 = by problem size
+    int label_ppw = 0;       // PB_LABEL_PPW: points per warp of k_label (0 = by problem size)
     int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
                              // registers stay free for the other chunk's latency-bound kernels (overlap experiment)
     int deg_slice_mult = 48; // PB_DEG_SLICES (measured on one 224 k-point scene: k_degree 271 us at 16, 211 us at 48): warps per SM that k_degree aims for on small problems (window splitting)
@@ -149,6 +151,10 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         const char *sg = getenv("PB_STAGGER");
         ctx->stagger = sg && sg[0] == '1';
+        const char *tm = getenv("PB_TILES");
+        if (tm) ctx->tile_mode = tm[0] == '1' ? 1 : (tm[0] == '0' ? 0 : -1);
+        const char *lp = getenv("PB_LABEL_PPW");
+        if (lp && atoi(lp) > 0) ctx->label_ppw = atoi(lp);
         const char *dm = getenv("PB_DEG_SMEM");
         if (dm && atoi(dm) > 0) ctx->deg_smem = atoi(dm);
         const char *ds = getenv("PB_DEG_SLICES");
@@ -232,6 +238,7 @@ namespace {
 #endif
 constexpr int kTileItems = PB_TILE_ITEMS;          // items per thread of the tile kernels (large path)
 constexpr int kTile = pb::kTB * kTileItems;        // 4096 points per tile
+constexpr int kTileItemsSmall = 4;                 // below 256 k points per chunk: tiles of 1024 points
 
 // Host-built, segment-aligned tile table of one chunk (pb::TileTab): [begin | count | seg | first | hslot | srow] x T
 struct TileHost {
@@ -515,6 +522,9 @@ ChunkDev header_views(const Work &w, int S, int T) {
 }
 
 // Front of a chunk: copies, initialisation, validation + bounding boxes, per-segment parameters, cell extents -> host.
+// ITEMS = keys per thread of the tile kernels: 16 (tiles of 4096 points) on large problems, 4 (1024 points) below 256 k
+// points, where the per-tile latency chain — not the bandwidth — sets the time of the tile kernels.
+template <int ITEMS>
 int enqueue_front(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, bool mixed, const float *radius, const int *min_pts,
                   const float *thresh, cudaStream_t st, int64_t &L, std::vector<int> &hdr_host) {
     const int n = io.n, S = io.S, T = io.tiles->T;
@@ -555,7 +565,7 @@ int enqueue_front(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, bool mi
     const float *dxo = host_io ? w.xo : io.xo, *dyo = host_io ? w.yo : io.yo, *dzo = host_io ? w.zo : io.zo;
     const int *dsem = host_io ? w.sem : io.sem;
     if (io.ev) cudaEventRecord(io.ev[ST_PREP], st);
-    pb::k_prep<kTileItems><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.d_scalars);
+    pb::k_prep<ITEMS><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, dx, dy, dz, dxo, dyo, dzo, dsem, w.seg_of, w.d_scalars);
     pb::k_seg_params<<<div_up(std::max(S, 1), 256), 256, 0, st>>>(S, w.sg, dsem, d.radius, d.min_pts, w.d_scalars + 10, w.d_scalars);
     L += 2;
     PB_CUDA(cudaMemcpyAsync(io.h_scalars + 10, w.d_scalars + 10, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
@@ -563,14 +573,14 @@ int enqueue_front(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, bool mi
     return PB_OK;
 }
 
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 void launch_sort_passes(Work &w, const pb::TileTab &tt, const int *seg_start, const pb::PassPlan &p1, const pb::PassPlan &p2,
                         int rows, cudaStream_t st, int64_t &L, int which) {
     // which: 0 = sort 1 only (KeyT = its key type), 1 = sort 2 only, 2 = both (same key type)
     const int stride = (p1.npass + p2.npass) * pb::kBins;
     const size_t state_pass = (size_t)std::max(rows, 1) * pb::kBins;
     const int np = which == 0 ? p1.npass : (which == 1 ? p2.npass : std::max(p1.npass, p2.npass));
-    const size_t smem = sizeof(pb::SortSmem<KeyT, kTileItems>);
+    const size_t smem = sizeof(pb::SortSmem<KeyT, ITEMS>);
     for (int p = 0; p < np; p++) {
         pb::SortArgs<KeyT> a[2];
         int na = 0;
@@ -592,13 +602,13 @@ void launch_sort_passes(Work &w, const pb::TileTab &tt, const int *seg_start, co
         }
         if (na == 0) continue;
         if (na == 1) a[1] = a[0];
-        pb::k_sort_pass<KeyT, kTileItems><<<dim3(tt.T, na), pb::kTB, smem, st>>>(a[0], a[1], tt, seg_start);
+        pb::k_sort_pass<KeyT, ITEMS><<<dim3(tt.T, na), pb::kTB, smem, st>>>(a[0], a[1], tt, seg_start);
         L++;
     }
 }
 
 // Everything after the key layout is known.  No host synchronisation.
-template <bool MIXED>
+template <bool MIXED, int ITEMS>
 int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assign_lp, cudaStream_t st, int64_t &L) {
     const int n = io.n, S = io.S, T = io.tiles->T;
     const bool prof = io.ev != nullptr;
@@ -640,15 +650,15 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     if (rows > 0 || slots > 0) PB_CUDA(cudaMemsetAsync(w.zeroB_begin, 0, zeroB, st));
 
     const int Tz = std::max(T, 1);
-    pb::k_keys<MIXED, kTileItems><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, ka, dx, dy, dz, dxo, dyo, dzo, dsem, w.key1[0],
+    pb::k_keys<MIXED, ITEMS><<<std::min(Tz, 148 * 16), pb::kTB, 0, st>>>(d.tt, w.sg, ka, dx, dy, dz, dxo, dyo, dzo, dsem, w.key1[0],
                                                                              w.key2[0], d_err, d.radius, w.cnt18);
     L++;
     mark();  // SORT
     if (ka.key64) {
-        launch_sort_passes<uint64_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 0);
-        if (assign_lp) launch_sort_passes<uint32_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 1);
+        launch_sort_passes<uint64_t, ITEMS>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 0);
+        if (assign_lp) launch_sort_passes<uint32_t, ITEMS>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, 1);
     } else {
-        launch_sort_passes<uint32_t>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, assign_lp ? 2 : 0);
+        launch_sort_passes<uint32_t, ITEMS>(w, d.tt, d.seg_start, ka.plan1, ka.plan2, rows, st, L, assign_lp ? 2 : 0);
     }
     const void *skey = w.key1[ka.plan1.npass & 1];
     const uint32_t *order1 = w.v1[ka.plan1.npass & 1];
@@ -662,9 +672,9 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     go.fcell_key = w.fcell_key, go.cc_key = w.cc_key, go.d_F = d_F, go.d_Cc = d_Cc, go.d_rows = d_rows;
     go.stateA = w.gridA, go.stateB = w.gridB, go.ticket = w.tickets + 10;
     if (ka.key64)
-        pb::k_grid_build<uint64_t, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint64_t *>(skey), order1, dx, dy, dz, go);
+        pb::k_grid_build<uint64_t, ITEMS><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint64_t *>(skey), order1, dx, dy, dz, go);
     else
-        pb::k_grid_build<uint32_t, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint32_t *>(skey), order1, dx, dy, dz, go);
+        pb::k_grid_build<uint32_t, ITEMS><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, ka.lay, reinterpret_cast<const uint32_t *>(skey), order1, dx, dy, dz, go);
     pb::k_runs<<<gPersist, T256, 0, st>>>(w.sg, w.cc_key, d_Cc, w.runs9);
     L += 2;
     pb::Grid grid;
@@ -721,7 +731,8 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     L++;
     mark();  // LABEL
     {
-        const int ppw = n >= (1 << 18) ? 32 : (n >= (1 << 16) ? 16 : 8);
+        int ppw = n >= (1 << 17) ? 32 : (n >= (1 << 15) ? 16 : 8);   // measured on a 137 k-point scene: 131 / 123 / 117 / 106 us at 4 / 8 / 16 / 32
+        if (ctx->label_ppw > 0) ppw = ctx->label_ppw;
         pb::k_label<MIXED><<<div_up(div_up(n, ppw), 4), 128, 0, st>>>(n, w.sg, grid, w.pts4, w.cell_hp, w.cell_gid, w.raw_label,
                                                                       w.raw_count, dsem, w.cell_gid18, ppw);
     }
@@ -736,7 +747,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         ro.cluster_id = d_cluster_id, ro.clt_sem = io.clt_sem_out, ro.clt_seg = w.clt_seg, ro.qlist = w.qlist, ro.inv2 = w.inv2;
         ro.lpos = w.lpos, ro.seg_lastlab = w.seg_lastlab, ro.lab4 = w.lab4, ro.d_Q = d_Q, ro.d_L = d_L, ro.state = w.rel_state;
         ro.ticket = w.tickets + 11;
-        pb::k_relabel_scan<MIXED, kTileItems><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, w.raw_label, w.keep, w.kscan, assign_lp, w.rep, dsem,
+        pb::k_relabel_scan<MIXED, ITEMS><<<Tz, pb::kTB, 0, st>>>(d.tt, n, w.sg, w.raw_label, w.keep, w.kscan, assign_lp, w.rep, dsem,
                                                                      order2, dxo, dyo, dzo, ro);
         L++;
     }
@@ -998,6 +1009,10 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
                              (int)sizeof(pb::SortSmem<uint64_t, kTileItems>));
         cudaFuncSetAttribute(pb::k_sort_pass<uint32_t, kTileItems>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(pb::SortSmem<uint32_t, kTileItems>));
+        cudaFuncSetAttribute(pb::k_sort_pass<uint64_t, kTileItemsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<uint64_t, kTileItemsSmall>));
+        cudaFuncSetAttribute(pb::k_sort_pass<uint32_t, kTileItemsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(pb::SortSmem<uint32_t, kTileItemsSmall>));
         smem_attr_done = true;
     }
 
@@ -1041,6 +1056,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     const int G = (int)chunks.size();
     const bool multi = G > 1;
     const int slots = multi ? 2 : 1;
+    const bool small_tiles = ctx->tile_mode == 1 || (ctx->tile_mode < 0 && n < 262144);
     // per-chunk host tables: local segment starts, first segment of every segment's call, tile table
     std::vector<std::vector<int>> lstart(G), lcall(G);
     std::vector<TileHost> tiles(G);
@@ -1053,7 +1069,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         for (int s = 0; s <= cS; s++) lstart[gi][s] = start[ch.s0 + s] - ch.p0;
         for (int c = ch.c0; c < ch.c1; c++)
             for (int s = call_seg0[c]; s < call_seg0[c + 1]; s++) lcall[gi][s - ch.s0] = call_seg0[c] - ch.s0;
-        build_tiles(lstart[gi].data(), cS, kTile, tiles[gi]);
+        build_tiles(lstart[gi].data(), cS, small_tiles ? pb::kTB * kTileItemsSmall : kTile, tiles[gi]);
         n_max = std::max(n_max, cn), S_max = std::max(S_max, cS), T_max = std::max(T_max, tiles[gi].T);
         rows_max = std::max(rows_max, tiles[gi].rows), hslots_max = std::max(hslots_max, tiles[gi].slots);
     }
@@ -1142,7 +1158,8 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     int fronts = 0;
     auto front = [&](int gi) -> int {
         make_io(gi);
-        return enqueue_front(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host);
+        return small_tiles ? enqueue_front<kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host)
+                           : enqueue_front<kTileItems>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host);
     };
     for (; fronts < std::min(G, slots); fronts++) {
         int rc = front(fronts);
@@ -1150,8 +1167,13 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     for (int gi = 0; gi < G; gi++) {
         PB_CUDA(cudaEventSynchronize(ios[gi].ev_front));
-        int rc = mixed ? enqueue_rest<true>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
-                       : enqueue_rest<false>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
+        int rc;
+        if (small_tiles)
+            rc = mixed ? enqueue_rest<true, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
+                       : enqueue_rest<false, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
+        else
+            rc = mixed ? enqueue_rest<true, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
+                       : enqueue_rest<false, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
         if (rc) return rc;
         if (fronts < G) {  // the next chunk of this slot
             rc = front(fronts++);

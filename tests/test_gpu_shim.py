@@ -33,9 +33,9 @@ def _shim():
 
 def _reference_wrapper():
     """The reference's own pbnet_ops module object, loaded from its byte code with the shim as ``PB_lib``."""
-    pyc = os.path.join(REF_DIR, "ref_pbnet_ops.pyc")
+    pyc = os.path.join(REF_DIR, "ref_pbnet_ops.pyc.bin")
     if not os.path.exists(pyc):
-        pytest.skip("oracle/_ref/ref_pbnet_ops.pyc missing (run __graft_entry__.build() where /root/reference exists)")
+        pytest.skip("oracle/_ref/ref_pbnet_ops.pyc.bin missing (run __graft_entry__.build() where /root/reference exists)")
     shim = _shim()
     loader = importlib.machinery.SourcelessFileLoader("ref_pbnet_ops", pyc)
     spec = importlib.util.spec_from_loader("ref_pbnet_ops", loader)
