@@ -395,8 +395,11 @@ __device__ __forceinline__ void grid_build_tile(const TileTab &tt, int t, int n,
     __syncthreads();
 }
 
+#ifndef PB_GRID_MINB
+#define PB_GRID_MINB 3
+#endif
 template <typename KeyT, int ITEMS>
-__global__ void __launch_bounds__(kTB, 3)
+__global__ void __launch_bounds__(kTB, PB_GRID_MINB)
 k_grid_build(TileTab tt, int n, SegArrays sg, KeyLayout lay, const KeyT *__restrict__ skey, const uint32_t *__restrict__ order,
              const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, GridOut g) {
     __shared__ GridSmem s;

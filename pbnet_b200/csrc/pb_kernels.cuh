@@ -533,7 +533,9 @@ k_union(SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int *__rest
         }
         int rootA = uf_find(parent, A);
         const float4 pA = __ldg(pts4 + cell_first[A]);  // representative: the cell's first HP
-        for (int k = 0; k < kRuns; k++) {
+        // only the stencil rows that hold a cell with a larger ordinal (every cell pair is examined from its smaller side)
+        for (unsigned rows = __ballot_sync(kFull, f1 > max(f0, A + 1)); rows; rows &= rows - 1) {
+            const int k = __ffs(rows) - 1;
             int b = __shfl_sync(kFull, f0, k), e = __shfl_sync(kFull, f1, k);
             for (int fb = max(b, A + 1); fb < e; fb += 32) {
                 int B = fb + lane;
@@ -703,7 +705,8 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
             }
         }
         int best = -1;
-        for (int k = 0; k < kRuns; k++) {
+        for (unsigned rows = __ballot_sync(kFull, f1 > f0); rows; rows &= rows - 1) {   // non-empty stencil rows only
+            const int k = __ffs(rows) - 1;
             int b = __shfl_sync(kFull, f0, k), e = __shfl_sync(kFull, f1, k);
             for (int fb = b; fb < e; fb += 32) {
                 int B = fb + lane;
