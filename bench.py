@@ -276,6 +276,12 @@ def c1_config(args, world, n_scenes_total):
             f"{args.scaling} scaling")
 
 
+def c1_config_dict(args, world, n_scenes_total):
+    """`config` of BOTH arms (identical by construction; per-run details live in `workload_detail` / `cpu_baseline.sample`)."""
+    return {"workload": c1_config(args, world, n_scenes_total),
+            "l2": "no flush needed: the inputs and the workspace of one step are gigabytes per rank, far beyond the 126 MB L2"}
+
+
 def run_reference_arm(args):
     """The reference's own implementation of the path on the box: the UNMODIFIED compiled PB_lib (its only implementation
     is host-driven CUDA with CPU tensors in/out) on a bounded sample of the arm's workload; rank 0 only."""
@@ -289,7 +295,7 @@ def run_reference_arm(args):
     w = workload.build(sample_scenes, sizes, args.copies)
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": c1_config(args, world, n_scenes_total)},
+            "dtype": "f32", "data": "synthetic", "config": c1_config_dict(args, world, n_scenes_total),
             "gpus_used": 1,
             "note": "the reference has no multi-GPU inference path (eval is single-GPU, config/config_test.py:32): at --gpus N "
                     "this arm still runs on ONE GPU driven by one host thread, so an N>1 ratio against it is N GPUs vs 1"}
@@ -792,13 +798,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": c1_config(args, world, n_scenes_total),
-                       "points_total": total_points, "points_rank0": n, "calls_rank0": int(len(csc)), "segments_rank0": S,
-                       "clusters_rank0": int(n_clusters),
-                       "l2": "inputs + workspace of one step are ~%.1f GB per rank, far beyond the 126 MB L2; no flush needed" % (
-                           (28 + 430) * n / 1e9),
-                       "collective": "NCCL gather of the cluster ids (int16 on the wire) to rank 0 once per step, issued on a side stream so "
-                                     "that it overlaps the next step; the last one is awaited inside the timed region" if world > 1 else "none"},
+            "config": c1_config_dict(args, world, n_scenes_total),
+            "workload_detail": {"points_total": total_points, "points_rank0": n, "calls_rank0": int(len(csc)), "segments_rank0": S,
+                                "clusters_rank0": int(n_clusters),
+                                "working_set": "inputs + workspace of one step are ~%.1f GB per rank" % ((28 + 430) * n / 1e9),
+                                "collective": "NCCL gather of the cluster ids (int16 on the wire) to rank 0 once per step, issued on a "
+                                              "side stream so that it overlaps the next step; the last one is awaited inside the timed "
+                                              "region" if world > 1 else "none"},
             "e2e": {"value": total_points / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pb_binary_cluster_batched via pbnet_b200.cluster.Context.binary_cluster, pinned host buffers "
                            "(one batched call for the whole shard; the per-class reference call pattern is `e2e_dropin`)",

@@ -68,6 +68,8 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
+    int host_split[8] = {150, 425, 425, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
+                             // (measured at C1, end to end: 45.9 ms with equal thirds, 44.1 ms with 15 / 42.5 / 42.5 %, 47-50 ms with 4-5 chunks)
     int tile_mode = -1;      // PB_TILES: 1 = tiles of 1024 points, 0 = 4096, -1 = by problem size
     int label_ppw = 0;       // PB_LABEL_PPW: points per warp of k_label (0 = by problem size)
     int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
@@ -151,6 +153,15 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         const char *sg = getenv("PB_STAGGER");
         ctx->stagger = sg && sg[0] == '1';
+        const char *hs = getenv("PB_HOST_SPLIT");
+        if (hs) {
+            int k = 0;
+            for (const char *q = hs; *q && k < 8;) {
+                ctx->host_split[k++] = atoi(q);
+                while (*q && *q != ',') q++;
+                if (*q == ',') q++;
+            }
+        }
         const char *tm = getenv("PB_TILES");
         if (tm) ctx->tile_mode = tm[0] == '1' ? 1 : (tm[0] == '0' ? 0 : -1);
         const char *lp = getenv("PB_LABEL_PPW");
@@ -1036,7 +1047,14 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ch.s0 = call_seg0[c];
             ch.p0 = start[ch.s0];
             long long pts = 0;
-            while (c < n_calls && pts < target) {  // whole calls until the chunk reaches the target size
+            // host data, automatic chunking: unequal chunks (PB_HOST_SPLIT, per mille of the call) — a small first chunk
+            // shortens the exposed head of the pipeline (its H2D copy), a small last one the exposed read-back
+            long long tgt = target;
+            if (host_io && ctx->chunk_points == 0 && auto_chunks == 3 && ctx->host_split[0] > 0) {
+                const int k = (int)chunks.size();
+                tgt = k < 8 && ctx->host_split[k] > 0 ? (long long)n * ctx->host_split[k] / 1000 : (long long)n;
+            }
+            while (c < n_calls && pts < tgt) {  // whole calls until the chunk reaches the target size
                 pts += start[call_seg0[c + 1]] - start[call_seg0[c]];
                 c++;
             }

@@ -35,18 +35,26 @@ class Cluster(Function):
     def forward(ctx, ins_offseted, ins_orig, sem, ins_bp, radius, min_pts, batch_size):
         dev = ins_offseted.device
         # the reference overwrites batch_size with ins_bp.shape[0] (pbnet_ops.py:43)
-        segs = ins_bp.detach().to(device="cpu", dtype=torch.int32).numpy()
+        segs = ins_bp.numpy() if (ins_bp.dtype == torch.int32 and ins_bp.device.type == "cpu" and not ins_bp.requires_grad) \
+            else ins_bp.detach().to(device="cpu", dtype=torch.int32).numpy()
         radius18, min_pts18 = _tables(radius, min_pts)
         if dev.type != "cuda":
             # CPU tensors (the reference's call pattern, network/PBNet.py:176): SoA split (pbnet_ops.py:16-18, 27-29) through
             # numpy — torch's strided CPU copy takes 0.33 ms for a 27 k x 3 transpose, numpy 0.04 ms
-            so = np.ascontiguousarray(ins_offseted.detach().to(torch.float32).numpy().T)
-            oo = np.ascontiguousarray(ins_orig.detach().to(device="cpu", dtype=torch.float32).numpy().T)
-            sem32 = sem.detach().to(device="cpu", dtype=torch.int32).contiguous().numpy()
+            def soa(t):
+                if t.dtype != torch.float32 or t.device.type != "cpu" or t.requires_grad:
+                    t = t.detach().to(device="cpu", dtype=torch.float32)
+                return np.ascontiguousarray(t.numpy().T)
+            so, oo = soa(ins_offseted), soa(ins_orig)
+            sem32 = sem.detach().cpu().numpy().astype(np.int32, copy=False)
+            if not sem32.flags["C_CONTIGUOUS"]:
+                sem32 = np.ascontiguousarray(sem32)
             pb = default_context(torch.cuda.current_device() if torch.cuda.is_available() else 0)
             out = pb.binary_cluster(so[0], so[1], so[2], oo[0], oo[1], oo[2], sem32, segs, radius18, min_pts18, 0.05, True)
-            res = (torch.from_numpy(out["cluster_id"]), torch.from_numpy(out["cluster_num"]),
-                   torch.from_numpy(out["degree"] + 1), torch.from_numpy(np.ascontiguousarray(out["center"])))
+            deg = out["degree"]
+            deg += 1                                   # den_queue + 1 (pbnet_ops.py:75); the array is ours
+            res = (torch.from_numpy(out["cluster_id"]), torch.from_numpy(out["cluster_num"]), torch.from_numpy(deg),
+                   torch.from_numpy(out["center"]))
             ctx.mark_non_differentiable(*res)
             return res
         # CUDA tensors: zero-copy, results stay on the device
