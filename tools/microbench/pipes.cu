@@ -150,6 +150,89 @@ __global__ void k_test3(float *out, float a, float b, unsigned long long *cyc) {
     if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);  // slowest warp of the grid
 }
 
+
+// ---- round 2: the DOT form of the pair test (filter; the exact sequence only re-runs when a lane is inside the error band) ----
+// v = qx*cx' + qy*cy' + qz*cz' + (|q|^2 - r^2) + |c|^2 with cx' = -2 cx ...: 3 FFMA2 + FADD2 per two tests; the sign bit of v is
+// the verdict.  COUNT: 0 = cnt += bits >> 31 (LEA.HI), 1 = FSETP + predicated IADD, 2 = none (fp32 work only).
+// DETECT: 1 = running minimum of |v| (FMNMX3 with |.| modifiers), 0 = none.
+constexpr int NP = 4;  // query pairs per thread (the kernel holds 3 pairs against 2-4 candidates in flight)
+template <int COUNT, int DETECT>
+__global__ void __launch_bounds__(1024) k_dot(float *out, float a, float b, unsigned long long *cyc) {
+    unsigned long long qx[NP], qy[NP], qz[NP], tq[NP];
+    unsigned cnt[2 * NP];
+    float m = 1e30f;
+    for (int i = 0; i < NP; i++) {
+        const float *src = out + 8 * i + threadIdx.x;  // opaque values: no register sharing between the operands
+        qx[i] = pk(src[0], src[1]), qy[i] = pk(src[2], src[3]), qz[i] = pk(src[4], src[5]), tq[i] = pk(src[6], src[7]);
+        cnt[2 * i] = cnt[2 * i + 1] = 0;
+    }
+    float cx = a, cy = b, cz = a + b, cn = a * b;
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            unsigned long long t, cxx = pk(cx, cx), cyy = pk(cy, cy), czz = pk(cz, cz), cnn = pk(cn, cn);
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(qz[i]), "l"(czz), "l"(tq[i]));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(qy[i]), "l"(cyy));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(qx[i]), "l"(cxx));
+            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(t) : "l"(cnn));
+            unsigned v0, v1;
+            asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(v0), "=r"(v1) : "l"(t));
+            if (COUNT == 0) {
+                cnt[2 * i] += v0 >> 31;
+                cnt[2 * i + 1] += v1 >> 31;
+            } else if (COUNT == 1) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, 0f00000000;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[2 * i]) : "f"(__uint_as_float(v0)));
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, 0f00000000;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[2 * i + 1]) : "f"(__uint_as_float(v1)));
+            } else {
+                cnt[2 * i] ^= v0, cnt[2 * i + 1] ^= v1;  // keeps the result live with one LOP3 per test
+            }
+            if (DETECT) m = fminf(m, fminf(fabsf(__uint_as_float(v0)), fabsf(__uint_as_float(v1))));
+        }
+        cx += 1e-7f, cy += 2e-7f, cz -= 1e-7f, cn += 3e-7f;
+    }
+    unsigned long long t1 = clock64();
+    unsigned s = 0;
+    for (int i = 0; i < 2 * NP; i++) s += cnt[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s + m;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);
+}
+
+// the exact packed test with the counting done by LEA.HI on the sign of (d - r2): 7 packed + 2 integer per two tests
+__global__ void __launch_bounds__(1024) k_test2b(float *out, float a, float b, unsigned long long *cyc) {
+    unsigned long long qq[8];
+    unsigned cnt[16];
+    for (int i = 0; i < 8; i++) qq[i] = pk(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f + i), cnt[2 * i] = cnt[2 * i + 1] = 0;
+    unsigned long long cx = pk(a, a), cy = pk(b, b), cz = pk(a + b, a + b), rr = pk(b, b), step = pk(1e-7f, 1e-7f);
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned long long dx, dy, dz, d;
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(cx), "l"(qq[i]));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(cy), "l"(qq[i]));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(cz), "l"(qq[i]));
+            asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(dy));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dx));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dz));
+            asm volatile("sub.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(rr));
+            unsigned v0, v1;
+            asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(v0), "=r"(v1) : "l"(d));
+            cnt[2 * i] += v0 >> 31, cnt[2 * i + 1] += v1 >> 31;
+        }
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cx) : "l"(step));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cy) : "l"(step));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(cz) : "l"(step));
+    }
+    unsigned long long t1 = clock64();
+    unsigned s = 0;
+    for (int i = 0; i < 16; i++) s += cnt[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);
+}
+
 // every launch is preceded by a reset of the cycle counter (atomicMax over all warps)
 #define RESET() cudaMemset(cyc, 0, 8)
 int main() {
@@ -172,6 +255,16 @@ int main() {
         printf("%-30s %.3f warp-tests/cycle/SM  (packed f32x2, 5 instr per test)\n", "pair test, f32x2", (double)ITERS * 16 * warps / h);
         RESET(); k_test3<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-tests/cycle/SM  (packed + sign-bit funnel shift, 4.5 instr per test)\n", "pair test, f32x2+SHF", (double)ITERS * 16 * warps / h);
+
+#define RUND(C, D, label) RESET(); k_dot<C, D><<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("%-30s %.3f warp-tests/cycle/SM  (%s)\n", "pair test, DOT form", (double)ITERS * 2 * NP * warps / h, label);
+        RUND(2, 0, "3 FFMA2 + FADD2 + 2 LOP3 per two tests: fp32 work only")
+        RUND(0, 0, "cnt += bits >> 31, no detection")
+        RUND(1, 0, "FSETP + @p IADD, no detection")
+        RUND(0, 1, "cnt += bits >> 31, min|v| detection")
+        RUND(1, 1, "FSETP + @p IADD, min|v| detection")
+        RESET(); k_test2b<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-30s %.3f warp-tests/cycle/SM  (exact packed test, 7 packed + 2 LEA.HI per two tests)\n", "pair test, f32x2+LEA", (double)ITERS * 16 * warps / h);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
