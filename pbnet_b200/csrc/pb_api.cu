@@ -79,7 +79,8 @@ struct pb_ctx {
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
     size_t h_stage_cap = 0;
     int coop_blocks_per_sm = 0, sm_count = 0;
-    bool fuse_hp = false;  // PB_FUSE_HP=1: HP rule + cell statistics as an epilogue of k_degree instead of a separate pass
+    int deg_minb = 8;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
+    bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
                            // (measured at C1: 39.9 ms fused vs 37.9 ms with k_hp_cells: the epilogue's atomics and dependent
                            // loads sit on the fp32-bound kernel's critical path)
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -172,8 +173,10 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         if (ds && atoi(ds) > 0) ctx->deg_slice_mult = atoi(ds);
         const char *sm = getenv("PB_SMALL");
         ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
-        const char *fh = getenv("PB_FUSE_HP");
-        ctx->fuse_hp = fh && fh[0] == '1';
+        const char *dsy = getenv("PB_DEG_SYM");
+        if (dsy) ctx->deg_sym = dsy[0] != '0';
+        const char *dmb = getenv("PB_DEG_MINB_SYM");
+        if (dmb) ctx->deg_minb = atoi(dmb) == 9 ? 9 : 8;
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
@@ -702,23 +705,18 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         // small problems: several warps share one 128-point window and split its candidate stream
         const int windows = div_up(n, pb::kWindow);
         const int nslice = std::max(1, std::min(32, (148 * ctx->deg_slice_mult) / windows));
-        pb::HpOut hp;
-        hp.pts4_w = reinterpret_cast<int *>(w.pts4), hp.degree_out = d_degree, hp.cell_hp = w.cell_hp, hp.cell_minhp = w.cell_minhp;
-        hp.cell_first = w.cell_first, hp.counters = cnt;
         const dim3 g(div_up(n, pb::kWindow * 4), nslice);
-        if (nslice == 1 && !MIXED && ctx->fuse_hp) {  // one warp owns a window's whole candidate stream: HP rule + cell statistics fused in
-            pb::k_degree<true><<<g, 128, ctx->deg_smem, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
-            PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
-            mark();  // HP
-        } else {
-            if (nslice > 1) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
-            pb::k_degree<false><<<g, 128, nslice == 1 ? ctx->deg_smem : 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, hp);
-            PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
-            mark();  // HP
-            pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
-                                                                   w.cell_minhp, cnt, dsem, d.min_pts, w.cell_min18, w.cell_first);
-            L++;
-        }
+        // symmetric counting: candidates' degrees are accumulated with RED, so the array starts at zero
+        if (nslice > 1 || ctx->deg_sym) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
+        const size_t dsm = nslice == 1 ? ctx->deg_smem : 0;
+        if (!ctx->deg_sym) pb::k_degree<false, PB_DEG_MINB><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+        else if (ctx->deg_minb == 9) pb::k_degree<true, 9><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+        else pb::k_degree<true, 8><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+        PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
+        mark();  // HP
+        pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
+                                                               w.cell_minhp, cnt, dsem, d.min_pts, w.cell_min18, w.cell_first);
+        L++;
     }
     L++;
     mark();  // UNION

@@ -248,95 +248,114 @@ __device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-b
 
 // One group of up to 128 query points [g0, g0+total).  Lane l of pair p owns the two ADJACENT sorted points
 // base + 64p + 2l and +1 (base = g0 rounded down to even), fetched with one 64-bit load per coordinate: the
-// loaded register pair is directly the packed operand of FADD2 (no re-packing moves).
-// HP epilogue of a degree group (FUSE_HP, large problems where one warp owns the whole candidate stream of its window):
-// degree scatter to input order, HP rule (binary_cuda_functions.cu:175-186), HP bit in pts4.w, per-cell HP count /
-// minimum HP index / first HP position — what round 1 did in a separate pass over the points (k_hp_cells).
-struct HpOut {
-    int *pts4_w;          // pts4 viewed as int[4N]: word 4i+3 = orig index | HP bit
-    int *degree_out;      // [N] input order
-    int *cell_hp, *cell_minhp, *cell_first;
-    unsigned long long *counters;  // profiling: [1] sum of degrees, [2] HP count (or nullptr)
-};
+// loaded register pair is directly the packed operand of FADD2 (no re-packing moves).  Slots outside the group
+// get x = NaN: they can never pass the test.
+//
+// SYMMETRIC counting (round 2).  The neighbour relation is symmetric and the predicate is bit-symmetric
+// (fl(a-b) = -fl(b-a), only squares are used), so every unordered pair is tested ONCE: a group streams only the
+// candidates that come LATER in the sorted order — the rest of its own coarse row up to cell cx'max+1 and the four
+// later stencil rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) — and a hit counts for both sides.  The query's
+// side is the lane's register counter as before.  The candidate's side is the growth of the lane's counters over
+// one candidate (an IADD3 sum), at most 2P <= 6 per lane: four candidates share one register, one byte each (a
+// byte's warp sum is <= 192), ONE REDUX.SUM adds it over the warp and lanes 0..3 add their byte to the candidates'
+// degrees with one RED.  Pairs inside the group are tested one-sided (every lane against all points of the
+// group), which also supplies the self hit the reference counts and subtracts (binary_cuda_functions.cu:88).
+// tools/microbench/pipes.cu (profiles/microbench_pipes_r02.txt): the symmetric candidate loop costs 1.17-1.20x
+// the one-sided loop per executed test and resolves two ordered pairs per test.
+template <int P>
+__device__ __forceinline__ int slot_sum(const int (&cnt)[2 * P]) {
+    int t = cnt[0] + cnt[1];
+#pragma unroll
+    for (int s = 2; s < 2 * P; s++) t += cnt[s];
+    return t;
+}
 
-template <int P, bool FUSE_HP>
+template <int P, bool SYM>
 __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
-                                             int *__restrict__ deg_sorted, int slice, int nslice, int min_pts,
-                                             const HpOut &hp, unsigned &dsum, unsigned &hsum) {
+                                             int *__restrict__ deg_sorted, int slice, int nslice) {
     const float4 *__restrict__ pts4 = g.pts4;
     const int base = g0 & ~1;
+    const float qnan = __int_as_float(0x7fc00000);
     unsigned long long qx[P], qy[P], qz[P];
     int cnt[2 * P];
 #pragma unroll
     for (int p = 0; p < P; p++) {
         int i = base + 64 * p + 2 * lane;
-        if (i >= g0 + total) i = base;  // stay inside the arrays; the result is masked below
+        const bool in0 = i >= g0 && i < g0 + total, in1 = i + 1 < g0 + total;  // i + 1 > g0 always
+        if (i >= g0 + total) i = base;  // stay inside the arrays
         qx[p] = ldg_pair(g.sx + i), qy[p] = ldg_pair(g.sy + i), qz[p] = ldg_pair(g.sz + i);
+        if (SYM) {
+            float x0, x1;
+            unpack2(qx[p], x0, x1);
+            qx[p] = pack2(in0 ? x0 : qnan, in1 ? x1 : qnan);
+        }
         cnt[2 * p] = cnt[2 * p + 1] = 0;
     }
+    int prev = 0;
+    // ranges: SYM: k = 4 the rest of the own row, 5..8 the later rows (both sides counted), then k = 9: the group itself
+    //         (one-sided); one-sided build: k = 0..8 the nine stencil rows
 #pragma unroll 1
-    for (int k = 0; k < kRuns; k++) {
+    for (int k = SYM ? 4 : 0; k < (SYM ? kRuns + 1 : kRuns); k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
+        const bool both = SYM && k < kRuns;
         // batches of 4 candidates; with nslice > 1 (small problems) the batches are dealt round-robin to the
         // nslice warps that share this window, so one long candidate stream is not one warp's latency
 #pragma unroll 1
         for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
-            if (j + 4 <= e) {
-                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-                test_candidate<P>(qx, qy, qz, q0, r2, cnt);
-                test_candidate<P>(qx, qy, qz, q1, r2, cnt);
-                test_candidate<P>(qx, qy, qz, q2, r2, cnt);
-                test_candidate<P>(qx, qy, qz, q3, r2, cnt);
-            } else {
-                for (int jj = j; jj < e; jj++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
+            if (!both) {
+                if (j + 4 <= e) {
+                    float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+                    test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+                    test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+                    test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+                    test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+                } else {
+                    for (int jj = j; jj < e; jj++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
+                }
+                continue;
             }
+            float4 q0 = __ldg(pts4 + j), q1, q2, q3;
+            if (j + 4 <= e) {
+                q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+            } else {  // the last batch of a range is padded with NaN candidates
+                q1 = __ldg(pts4 + min(j + 1, e - 1)), q2 = __ldg(pts4 + min(j + 2, e - 1)), q3 = q0;
+                if (j + 1 >= e) q1.x = qnan;
+                if (j + 2 >= e) q2.x = qnan;
+                q3.x = qnan;
+            }
+            test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+            const int t0 = slot_sum<P>(cnt);
+            test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+            const int t1 = slot_sum<P>(cnt);
+            test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+            const int t2 = slot_sum<P>(cnt);
+            test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+            const int t3 = slot_sum<P>(cnt);
+            const unsigned packed = (unsigned)(t0 - prev) + ((unsigned)(t1 - t0) << 8) + ((unsigned)(t2 - t1) << 16) +
+                                    ((unsigned)(t3 - t2) << 24);
+            prev = t3;
+            const unsigned hits = (__reduce_add_sync(kFull, packed) >> (8 * (lane & 3))) & 0xffu;
+            if (lane < 4 && hits) atomicAdd(deg_sorted + j + lane, (int)hits);  // padded candidates never hit
         }
     }
 #pragma unroll
     for (int s = 0; s < 2 * P; s++) {
         int i = base + 64 * (s >> 1) + 2 * lane + (s & 1);
-        const bool in = i >= g0 && i < g0 + total;
-        if (!FUSE_HP) {
-            if (in) {  // binary_cuda_functions.cu:88  ans - 1 (self)
-                if (nslice == 1) deg_sorted[i] = cnt[s] - 1;
-                else atomicAdd(deg_sorted + i, cnt[s] - (slice == 0 ? 1 : 0));  // deg_sorted zeroed by the host
-            }
-        } else {
-            const unsigned act = __ballot_sync(kFull, in);
-            if (in) {
-                const int d = cnt[s] - 1;
-                const int orig = hp.pts4_w[4 * (long long)i + 3];
-                const bool is_hp = d >= min_pts;
-                hp.degree_out[orig] = d;
-                if (is_hp) hp.pts4_w[4 * (long long)i + 3] = orig | kHpBit;
-                const int c = g.fcell_of[i];
-                const unsigned grp = __match_any_sync(act, c);
-                const unsigned hpm = __ballot_sync(act, is_hp) & grp;
-                const int mn = __reduce_min_sync(grp, is_hp ? orig : 0x7fffffff);
-                const int first = __reduce_min_sync(grp, is_hp ? i : 0x7fffffff);
-                if (hpm && lane == __ffs(grp) - 1) {
-                    atomicAdd(hp.cell_hp + c, __popc(hpm));
-                    atomicMin(hp.cell_minhp + c, mn);
-                    atomicMin(hp.cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
-                }
-            }
-            if (hp.counters) {  // profiling only (every lane accumulates the warp totals)
-                dsum += __reduce_add_sync(kFull, in ? (unsigned)(cnt[s] - 1) : 0u);
-                hsum += __popc(__ballot_sync(kFull, in && cnt[s] - 1 >= min_pts));
-            }
+        if (i >= g0 && i < g0 + total) {  // binary_cuda_functions.cu:88  ans - 1 (self)
+            const int d = cnt[s] - (slice == 0 ? 1 : 0);
+            if (!SYM && nslice == 1) deg_sorted[i] = d;
+            else if (d) atomicAdd(deg_sorted + i, d);  // deg_sorted zeroed by the host
         }
     }
 }
 
 // one 128-point window; `warp` = window index, (slice, nslice) = this warp's share of the window (small problems)
-template <bool FUSE_HP>
+template <bool SYM>
 __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const Grid &g, int *__restrict__ deg_sorted,
-                                              unsigned long long *__restrict__ n_tests, const HpOut &hp, int warp, int slice,
-                                              int nslice) {
+                                              unsigned long long *__restrict__ n_tests, int warp, int slice, int nslice) {
     int lane = lane_id();
     long long base = (long long)warp * kWindow;
     if (base >= n) return;
-    unsigned dsum = 0, hsum = 0;
     int end = (int)min((long long)n, base + kWindow);
     // group heads of the window (a group = points of one coarse row): one coalesced read of row_of, four ballots
     unsigned hm[kWindow / 32];
@@ -383,41 +402,34 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
             int cmin = g.fcell_cc[fmin], cmax = g.fcell_cc[fmax];
             const int seg = (int)(g.fcell_key[fmin] >> kSegShift);
             float r2 = sg.r2[seg];
-            const int min_pts = FUSE_HP ? sg.min_pts[seg] : 0;
             int jb = 0, je = 0;
-            if (lane < kRuns) {
+            if (lane < kRuns && (!SYM || lane >= 4)) {
                 int c0 = g.runs9[(long long)cmin * kRuns + lane].x, c1 = g.runs9[(long long)cmax * kRuns + lane].y;
                 if (c1 > c0) {
                     jb = g.cc_pstart[c0];
                     je = g.cc_pstart[c1];
                 }
+                if (SYM && lane == 4) jb = gend;  // the own row: only what follows the group (its end cell is never empty)
             }
-            if (n_tests && sub == 0) {
-                unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
-                tests += (unsigned long long)cand * (unsigned)total;
-            }
+            unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
+            if (SYM && lane == kRuns) jb = pos, je = gend;  // range 9: the group itself, one-sided
+            if (n_tests && sub == 0) tests += (unsigned long long)(cand + (SYM ? (unsigned)total : 0u)) * (unsigned)total;
             const int sl = sub, ns = cs;
             switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
-                case 1: degree_group<1, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
-                case 2: degree_group<2, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
-                default: degree_group<3, FUSE_HP>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns, min_pts, hp, dsum, hsum); break;
+                case 1: degree_group<1, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                case 2: degree_group<2, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                default: degree_group<3, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
             }
         }
         pos = gend;
     }
-    if (n_tests && lane == 0) {
-        atomicAdd(n_tests, tests);
-        if (FUSE_HP && hp.counters) {
-            atomicAdd(hp.counters + 1, (unsigned long long)dsum);
-            atomicAdd(hp.counters + 2, (unsigned long long)hsum);
-        }
-    }
+    if (n_tests && lane == 0) atomicAdd(n_tests, tests);
 }
 
-template <bool FUSE_HP>
-__global__ void __launch_bounds__(128, PB_DEG_MINB)
-k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests, HpOut hp) {
-    degree_window<FUSE_HP>(n, sg, g, deg_sorted, n_tests, hp, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y);
+template <bool SYM, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
+    degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y);
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order

@@ -233,6 +233,74 @@ __global__ void __launch_bounds__(1024) k_test2b(float *out, float a, float b, u
     if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);
 }
 
+
+// ---- round 2: SYMMETRIC counting.  Every unordered pair is tested once: a hit counts for the lane's query (register) and for the
+// candidate.  The candidate's share is the growth of the lane's slot counters (IADD3 sums), reduced over the warp with one
+// REDUX.SUM and added to the candidate's degree with one RED by lane 0.  P query pairs per lane, one candidate per inner step.
+template <int P, int SYM>
+__global__ void __launch_bounds__(1024) k_sym(float *out, int *deg, float a, float b, unsigned long long *cyc) {
+    unsigned long long qx[P], qy[P], qz[P];
+    int cnt[2 * P];
+    for (int i = 0; i < P; i++) {
+        const float *src = out + 6 * i + threadIdx.x;
+        qx[i] = pk(src[0], src[1]), qy[i] = pk(src[2], src[3]), qz[i] = pk(src[4], src[5]);
+        cnt[2 * i] = cnt[2 * i + 1] = 0;
+    }
+    float cx = a, cy = b, cz = a + b;
+    int prev = 0;
+    unsigned packed = 0;
+    int *dst = deg + (blockIdx.x * 32 + (threadIdx.x >> 5)) * 64;
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {   // four candidates per trip, as in k_degree
+            unsigned long long cxx = pk(cx, cx), cyy = pk(cy, cy), czz = pk(cz, cz);
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                unsigned long long dx, dy, dz, d;
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(cxx), "l"(qx[i]));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(cyy), "l"(qy[i]));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(czz), "l"(qz[i]));
+                asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(dy));
+                asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dx));
+                asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(d) : "l"(dz));
+                float d0, d1;
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[2 * i]) : "f"(d0), "f"(b));
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt[2 * i + 1]) : "f"(d1), "f"(b));
+            }
+            if (SYM == 1) {
+                int tot = 0;
+#pragma unroll
+                for (int i = 0; i < 2 * P; i++) tot += cnt[i];
+                int hits = __reduce_add_sync(0xffffffffu, tot - prev);
+                prev = tot;
+                if ((threadIdx.x & 31) == 0) atomicAdd(dst + ((4 * it + c) & 63), hits);
+            }
+            if (SYM == 2) {  // a lane's hits per candidate are <= 2P <= 6: four candidates share one register (one byte each),
+                int tot = 0; //  the warp sum of a byte is <= 192
+#pragma unroll
+                for (int i = 0; i < 2 * P; i++) tot += cnt[i];
+                packed += (unsigned)(tot - prev) << (8 * c);
+                prev = tot;
+            }
+            cx += 1e-7f, cy += 2e-7f, cz -= 1e-7f;
+        }
+        if (SYM == 2) {
+            unsigned r = __reduce_add_sync(0xffffffffu, packed);
+            packed = 0;
+            const int l = threadIdx.x & 31;
+            if (l < 4) atomicAdd(dst + ((4 * it + l) & 63), (int)((r >> (8 * l)) & 0xffu));
+        }
+    }
+    unsigned long long t1 = clock64();
+    int s = 0;
+    for (int i = 0; i < 2 * P; i++) s += cnt[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+    if ((threadIdx.x & 31) == 0) atomicMax(cyc, t1 - t0);
+}
+
 // every launch is preceded by a reset of the cycle counter (atomicMax over all warps)
 #define RESET() cudaMemset(cyc, 0, 8)
 int main() {
@@ -240,6 +308,9 @@ int main() {
     unsigned long long *cyc, h;
     cudaMalloc(&out, 148 * 1024 * 4 * sizeof(float));
     cudaMalloc(&cyc, 8);
+    int *deg;
+    cudaMalloc(&deg, 148 * 32 * 64 * sizeof(int));
+    cudaMemset(deg, 0, 148 * 32 * 64 * sizeof(int));
     const char *names[] = {"FFMA x=x*a+b", "FADD", "FMUL", "FFMA x=y*y+x", "FFMA2 with repack (3 instr)"};
     for (int warps = 4; warps <= 32; warps *= 2) {
         int threads = warps * 32;  // per SM (one block per SM)
@@ -265,6 +336,15 @@ int main() {
         RUND(1, 1, "FSETP + @p IADD, min|v| detection")
         RESET(); k_test2b<<<148, threads>>>(out, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("%-30s %.3f warp-tests/cycle/SM  (exact packed test, 7 packed + 2 LEA.HI per two tests)\n", "pair test, f32x2+LEA", (double)ITERS * 16 * warps / h);
+
+#define RUNS(P, SYM, label) RESET(); k_sym<P, SYM><<<148, threads>>>(out, deg, 1.0001f, 0.0016f, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("%-30s %.3f warp-tests/cycle/SM  (%s)\n", "pair test, candidate loop", (double)ITERS * 4 * 2 * P * warps / h, label);
+        RUNS(2, 0, "P=2, one-sided (the product's loop without the loads)")
+        RUNS(2, 1, "P=2, symmetric: + 2 IADD3 + REDUX + RED per candidate; every test counts twice")
+        RUNS(3, 0, "P=3, one-sided")
+        RUNS(3, 1, "P=3, symmetric")
+        RUNS(2, 2, "P=2, symmetric, four candidates per REDUX (byte-packed)")
+        RUNS(3, 2, "P=3, symmetric, four candidates per REDUX (byte-packed)")
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
