@@ -34,10 +34,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "points grouped/sec (binarize+search+cluster+vote)"
 UNIT = "points/s"
-# ceiling of the packed fp32x2 pair test measured with tools/microbench/pipes.cu on this pool's B200
-# (profiles/microbench_pipes_r01_v2.txt, slowest-warp timing, no loop-invariant operands): 0.485 warp-tests/clk/SM —
-# the fp32 pipe retires 6 operations per test (3 FADD, FMUL, 2 FFMA); the scalar form tops out at 0.332
+# ceilings of the packed fp32x2 pair test measured with tools/microbench/pipes.cu on this pool's B200 (slowest-warp timing, no
+# loop-invariant operands; profiles/microbench_pipes_r01_v2.txt, profiles/microbench_pipes_r02.txt), in warp-tests/clk/SM:
+#   0.485  the one-sided candidate loop (3 FADD2 + FMUL2 + 2 FFMA2 + 2 FSETP + 2 IADD per two tests; the scalar form: 0.332)
+#   0.387  the SYMMETRIC candidate loop of round 2 at two query pairs per lane (+ IADD3 slot sums, one REDUX + RED per four
+#          candidates; 0.414 at three pairs per lane) - every executed test settles BOTH directions of a pair
 PAIR_TEST_CEILING = 0.485
+PAIR_TEST_CEILING_SYM = 0.387
 
 
 def measured_peaks():
@@ -392,10 +395,9 @@ def degree_roofline(n, counters, deg_ms_total, ms_step, clocks, world):
     peak, peak_src = measured_peaks()
     cells = max(1, counters["cells"])
     chunks = max(1, counters.get("chunks", 1))
-    # algorithmic bytes of k_degree: per point 16 B pts4 + 4 B row_of read, 4 B degree write (+ 4 B degree
-    # scatter to input order and the HP bit since the HP epilogue is fused); per fine cell 12 B (key, coarse ordinal);
-    # per coarse cell 76 B (9 stencil rows + point offset)
-    deg_bytes = (24.0 * n + 12.0 * cells + 76.0 * counters.get("coarse_cells", 0)) / chunks   # per launch
+    # algorithmic bytes of k_degree: per point 16 B pts4 + 4 B row_of read, 4 B zero fill + 4 B degree
+    # accumulation (RED); per fine cell 12 B (key, coarse ordinal); per coarse cell 76 B (9 stencil rows + point offset)
+    deg_bytes = (28.0 * n + 12.0 * cells + 76.0 * counters.get("coarse_cells", 0)) / chunks   # per launch
     traffic = None
     try:  # dram__bytes_read+write per launch from the newest committed ncu --set full capture of the same workload
         cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_k_degree.json")))
@@ -407,19 +409,30 @@ def degree_roofline(n, counters, deg_ms_total, ms_step, clocks, world):
     deg_ms = deg_ms_total / chunks
     achieved = deg_bytes / (deg_ms * 1e-3) / 1e9 if deg_ms > 0 else None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    alu_peak = 148 * 32 * PAIR_TEST_CEILING * sm_mhz * 1e6
+    intra = counters.get("intra_tests", 0)
+    sym = intra > 0                                   # the symmetric kernel reports its one-sided share
+    ceiling = PAIR_TEST_CEILING_SYM if sym else PAIR_TEST_CEILING
+    alu_peak = 148 * 32 * ceiling * sm_mhz * 1e6
     tests_per_s = counters["pair_tests"] / (deg_ms_total * 1e-3) if deg_ms_total > 0 else None
+    ordered = 2 * (counters["pair_tests"] - intra) + intra if sym else counters["pair_tests"]
     roof = {"bound": "hbm", "kernel": "k_degree", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
             "traffic_source": "profiles/ncu_r*_k_degree.json (ncu --set full capture of this workload, per launch)" if traffic else None,
             "launches_per_step": chunks, "avg_launch_ms": deg_ms, "share_of_step": deg_ms_total / ms_step if ms_step else None,
             "algorithmic_bytes_per_launch": deg_bytes,
             "note": "k_degree is fp32-pipe bound, not HBM bound: see roofline_alu (SURVEY.md §8d asks for both)"}
-    alu = {"kernel": "k_degree", "pair_tests_per_step": counters["pair_tests"], "achieved": tests_per_s, "peak": alu_peak,
+    alu = {"kernel": "k_degree", "counting": "symmetric" if sym else "one-sided",
+           "pair_tests_per_step": counters["pair_tests"], "achieved": tests_per_s, "peak": alu_peak,
            "unit": "pair tests/s", "frac": (tests_per_s / alu_peak) if tests_per_s else None,
            "pair_tests_per_point": counters["pair_tests"] / max(1, n),
-           "peak_def": f"148 SM x 32 lanes x {PAIR_TEST_CEILING} warp-tests/clk/SM (builder-measured ceiling of the packed fp32x2 pair "
-                       "test, tools/microbench/pipes.cu, profiles/microbench_pipes_r01_v2.txt) x measured SM clock"}
+           "ordered_pairs_settled_per_step": ordered,
+           "ordered_pairs_per_s": ordered / (deg_ms_total * 1e-3) if deg_ms_total > 0 else None,
+           "vs_one_sided_ceiling": (ordered / (deg_ms_total * 1e-3)) / (148 * 32 * PAIR_TEST_CEILING * sm_mhz * 1e6) if deg_ms_total > 0 else None,
+           "peak_def": f"148 SM x 32 lanes x {ceiling} warp-tests/clk/SM (builder-measured ceiling of the "
+                       f"{'symmetric' if sym else 'one-sided'} packed fp32x2 candidate loop, tools/microbench/pipes.cu, "
+                       "profiles/microbench_pipes_r02.txt) x measured SM clock; `vs_one_sided_ceiling` = ordered pairs settled "
+                       f"per second / the one-sided ceiling ({PAIR_TEST_CEILING}): above 1 means the symmetric kernel does what no "
+                       "one-sided kernel could"}
     return roof, alu
 
 

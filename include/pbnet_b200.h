@@ -125,7 +125,9 @@ const char *pb_stage_name(int i);
 float pb_stage_ms(const pb_ctx *ctx, int i);
 /* counters of the last call: [0] pair tests issued by the degree kernel, [1] sum of degrees,
  * [2] HP count, [3] LP-assignment queries, [4] occupied grid cells, [5] raw clusters before the filter,
- * [6] chunks, [7] 1 if the mixed-class kernels were needed, [8] occupied coarse cells */
+ * [6] chunks, [7] 1 if the mixed-class kernels were needed, [8] occupied coarse cells, [9] 1 if the one-launch
+ * small-call kernel ran, [10] the share of [0] that was tested one-sided (pairs inside one query group); the other
+ * tests of [0] are symmetric: one test settles both directions of a pair */
 int64_t pb_counter(const pb_ctx *ctx, int i);
 
 /* ------------------------------------------------------------------------------------------------

@@ -79,7 +79,7 @@ struct pb_ctx {
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
     size_t h_stage_cap = 0;
     int coop_blocks_per_sm = 0, sm_count = 0;
-    int deg_minb = 8;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
+    int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
                            // (measured at C1: 39.9 ms fused vs 37.9 ms with k_hp_cells: the epilogue's atomics and dependent
                            // loads sit on the fp32-bound kernel's critical path)
@@ -176,7 +176,7 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         const char *dsy = getenv("PB_DEG_SYM");
         if (dsy) ctx->deg_sym = dsy[0] != '0';
         const char *dmb = getenv("PB_DEG_MINB_SYM");
-        if (dmb) ctx->deg_minb = atoi(dmb) == 9 ? 9 : 8;
+        if (dmb && atoi(dmb) >= 6 && atoi(dmb) <= 9) ctx->deg_minb = atoi(dmb);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
@@ -711,6 +711,8 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         const size_t dsm = nslice == 1 ? ctx->deg_smem : 0;
         if (!ctx->deg_sym) pb::k_degree<false, PB_DEG_MINB><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
         else if (ctx->deg_minb == 9) pb::k_degree<true, 9><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+        else if (ctx->deg_minb == 7) pb::k_degree<true, 7><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
+        else if (ctx->deg_minb == 6) pb::k_degree<true, 6><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
         else pb::k_degree<true, 8><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
         PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
         mark();  // HP
@@ -1267,6 +1269,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
         for (int i = 0; i < 6; i++) ctx->counters[i] = 0;
         ctx->counters[8] = 0;
+        ctx->counters[10] = 0;
         for (int gi = 0; gi < G; gi++) {
             cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
             for (int i = 0; i < ST_COUNT; i++) {
@@ -1279,6 +1282,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ctx->counters[0] += (int64_t)hc[0];
             ctx->counters[1] += (int64_t)hc[1];
             ctx->counters[2] += (int64_t)hc[2];
+            ctx->counters[10] += (int64_t)hc[3];
             ctx->counters[3] += hs[4];
             ctx->counters[4] += hs[1];
             ctx->counters[5] += hs[2];

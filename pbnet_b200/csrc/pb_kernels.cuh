@@ -35,7 +35,10 @@ constexpr int kHpBit = 0x80000000;
 #ifndef PB_DEG_MINB
 #define PB_DEG_MINB 9
 #endif
-constexpr int kWindow = 128;                   // query points per warp in k_degree (2 adjacent pairs per lane)
+#ifndef PB_DEG_WINDOW
+#define PB_DEG_WINDOW 128
+#endif
+constexpr int kWindow = PB_DEG_WINDOW;         // query points per warp in k_degree (a multiple of 64: 2 or 3 adjacent pairs per lane)
 
 enum ErrBit { kErrSem = 1, kErrNonFinite = 2, kErrRange = 4, kErrMixed = 8, kErrRadius = 16 };
 constexpr int kCls = 18;  // classes 2..19
@@ -249,7 +252,7 @@ __device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-b
 // One group of up to 128 query points [g0, g0+total).  Lane l of pair p owns the two ADJACENT sorted points
 // base + 64p + 2l and +1 (base = g0 rounded down to even), fetched with one 64-bit load per coordinate: the
 // loaded register pair is directly the packed operand of FADD2 (no re-packing moves).  Slots outside the group
-// get x = NaN: they can never pass the test.
+// get x = NaN: they can never pass the test (their hits would otherwise be credited to the candidates).
 //
 // SYMMETRIC counting (round 2).  The neighbour relation is symmetric and the predicate is bit-symmetric
 // (fl(a-b) = -fl(b-a), only squares are used), so every unordered pair is tested ONCE: a group streams only the
@@ -262,6 +265,17 @@ __device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-b
 // group), which also supplies the self hit the reference counts and subtracts (binary_cuda_functions.cu:88).
 // tools/microbench/pipes.cu (profiles/microbench_pipes_r02.txt): the symmetric candidate loop costs 1.17-1.20x
 // the one-sided loop per executed test and resolves two ordered pairs per test.
+// warp sum without the convergence check the intrinsic carries (all 32 lanes are always here)
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+// RED.ADD predicated on a non-zero addend (no branch)
+__device__ __forceinline__ void red_add_nz(int *p, unsigned v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.global.add.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int P>
 __device__ __forceinline__ int slot_sum(const int (&cnt)[2 * P]) {
     int t = cnt[0] + cnt[1];
@@ -291,18 +305,46 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
         }
         cnt[2 * p] = cnt[2 * p + 1] = 0;
     }
-    int prev = 0;
+    unsigned nprev = 0;                                  // -(sum of the slot counters after the previous candidate)
+    const unsigned sh = 8 * (lane & 3), lmask = lane < 4 ? 0xffu : 0u;
+    int *const dq = deg_sorted + lane;
     // ranges: SYM: k = 4 the rest of the own row, 5..8 the later rows (both sides counted), then k = 9: the group itself
     //         (one-sided); one-sided build: k = 0..8 the nine stencil rows
 #pragma unroll 1
     for (int k = SYM ? 4 : 0; k < (SYM ? kRuns + 1 : kRuns); k++) {
         int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
-        const bool both = SYM && k < kRuns;
         // batches of 4 candidates; with nslice > 1 (small problems) the batches are dealt round-robin to the
         // nslice warps that share this window, so one long candidate stream is not one warp's latency
+        if (SYM && k < kRuns) {
 #pragma unroll 1
-        for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
-            if (!both) {
+            for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
+                if (j + 4 <= e) {
+                    float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+                    test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+                    const unsigned t0 = (unsigned)slot_sum<P>(cnt);
+                    test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+                    const unsigned t1 = (unsigned)slot_sum<P>(cnt);
+                    test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+                    const unsigned t2 = (unsigned)slot_sum<P>(cnt);
+                    test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+                    const unsigned t3 = (unsigned)slot_sum<P>(cnt);
+                    // (t0 - prev) + (t1 - t0) << 8 + (t2 - t1) << 16 + (t3 - t2) << 24, as four multiply-adds (mod 2^32)
+                    const unsigned packed = t0 * 0xffffff01u + t1 * 0xffff0100u + t2 * 0xff010000u + t3 * 0x01000000u + nprev;
+                    nprev = 0u - t3;
+                    red_add_nz(dq + j, (warp_sum(packed) >> sh) & lmask);
+                } else {
+                    for (int jj = j; jj < e; jj++) {
+                        test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
+                        const unsigned t = (unsigned)slot_sum<P>(cnt);
+                        const unsigned hits = warp_sum(t + nprev);
+                        nprev = 0u - t;
+                        red_add_nz(deg_sorted + jj, lane == 0 ? hits : 0u);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
                 if (j + 4 <= e) {
                     float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
                     test_candidate<P>(qx, qy, qz, q0, r2, cnt);
@@ -312,30 +354,7 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
                 } else {
                     for (int jj = j; jj < e; jj++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
                 }
-                continue;
             }
-            float4 q0 = __ldg(pts4 + j), q1, q2, q3;
-            if (j + 4 <= e) {
-                q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-            } else {  // the last batch of a range is padded with NaN candidates
-                q1 = __ldg(pts4 + min(j + 1, e - 1)), q2 = __ldg(pts4 + min(j + 2, e - 1)), q3 = q0;
-                if (j + 1 >= e) q1.x = qnan;
-                if (j + 2 >= e) q2.x = qnan;
-                q3.x = qnan;
-            }
-            test_candidate<P>(qx, qy, qz, q0, r2, cnt);
-            const int t0 = slot_sum<P>(cnt);
-            test_candidate<P>(qx, qy, qz, q1, r2, cnt);
-            const int t1 = slot_sum<P>(cnt);
-            test_candidate<P>(qx, qy, qz, q2, r2, cnt);
-            const int t2 = slot_sum<P>(cnt);
-            test_candidate<P>(qx, qy, qz, q3, r2, cnt);
-            const int t3 = slot_sum<P>(cnt);
-            const unsigned packed = (unsigned)(t0 - prev) + ((unsigned)(t1 - t0) << 8) + ((unsigned)(t2 - t1) << 16) +
-                                    ((unsigned)(t3 - t2) << 24);
-            prev = t3;
-            const unsigned hits = (__reduce_add_sync(kFull, packed) >> (8 * (lane & 3))) & 0xffu;
-            if (lane < 4 && hits) atomicAdd(deg_sorted + j + lane, (int)hits);  // padded candidates never hit
         }
     }
 #pragma unroll
@@ -379,7 +398,7 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
     const bool by_group = gs > 1;
     const int team = slice / cs, sub = slice % cs;
     if (by_group && team >= gs) return;  // nslice not a multiple of cs: the last warps idle
-    unsigned long long tests = 0;
+    unsigned long long tests = 0, intra = 0;
     int gi = 0, pos = (int)base;
     while (pos < end) {  // uniform
         // group end: next head after pos
@@ -413,17 +432,28 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
             }
             unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
             if (SYM && lane == kRuns) jb = pos, je = gend;  // range 9: the group itself, one-sided
-            if (n_tests && sub == 0) tests += (unsigned long long)(cand + (SYM ? (unsigned)total : 0u)) * (unsigned)total;
+            if (n_tests && sub == 0) {
+                tests += (unsigned long long)(cand + (SYM ? (unsigned)total : 0u)) * (unsigned)total;
+                if (SYM) intra += (unsigned long long)total * (unsigned)total;  // the one-sided share
+            }
             const int sl = sub, ns = cs;
             switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
                 case 1: degree_group<1, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
                 case 2: degree_group<2, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+#if PB_DEG_WINDOW > 192
+                case 3: degree_group<3, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+                default: degree_group<4, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+#else
                 default: degree_group<3, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
+#endif
             }
         }
         pos = gend;
     }
-    if (n_tests && lane == 0) atomicAdd(n_tests, tests);
+    if (n_tests && lane == 0) {
+        atomicAdd(n_tests, tests);
+        if (SYM) atomicAdd(n_tests + 3, intra);
+    }
 }
 
 template <bool SYM, int MINB>
