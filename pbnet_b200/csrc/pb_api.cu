@@ -68,8 +68,10 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
-    int host_split[8] = {150, 425, 425, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
-                             // (measured at C1, end to end: 45.9 ms with equal thirds, 44.1 ms with 15 / 42.5 / 42.5 %, 47-50 ms with 4-5 chunks)
+    int host_split[8] = {200, 400, 400, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
+                             // (measured at C1, end to end, one-sided k_degree: 45.9 ms with equal thirds, 44.1 ms with 15 / 42.5 / 42.5 %,
+                             // 47-50 ms with 4-5 chunks; symmetric k_degree: 38.2 ms at 15 / 42.5 / 42.5, 37.3 ms at 20 / 40 / 40,
+                             // 37.9 ms at 10 / 30 / 60, 38.4-40.2 ms with 4 chunks: e2e ~ compute + first H2D + last D2H)
     int tile_mode = -1;      // PB_TILES: 1 = tiles of 1024 points, 0 = 4096, -1 = by problem size
     int label_ppw = 0;       // PB_LABEL_PPW: points per warp of k_label (0 = by problem size)
     int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
@@ -81,8 +83,6 @@ struct pb_ctx {
     int coop_blocks_per_sm = 0, sm_count = 0;
     int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
-                           // (measured at C1: 39.9 ms fused vs 37.9 ms with k_hp_cells: the epilogue's atomics and dependent
-                           // loads sit on the fp32-bound kernel's critical path)
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int *h_chunk_scalars = nullptr;
     unsigned long long *h_chunk_counters = nullptr;

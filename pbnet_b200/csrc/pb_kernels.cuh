@@ -265,6 +265,15 @@ __device__ __forceinline__ unsigned long long ldg_pair(const float *p) {  // 8-b
 // group), which also supplies the self hit the reference counts and subtracts (binary_cuda_functions.cu:88).
 // tools/microbench/pipes.cu (profiles/microbench_pipes_r02.txt): the symmetric candidate loop costs 1.17-1.20x
 // the one-sided loop per executed test and resolves two ordered pairs per test.
+// candidates are streamed: the line a few batches ahead is pulled into L1 while the current batch is tested (the
+// first use of a freshly loaded candidate was the kernel's top stall: 37 % of the candidate loads missed L1)
+#ifndef PB_DEG_PREFETCH
+#define PB_DEG_PREFETCH 64
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+    if (PB_DEG_PREFETCH > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // warp sum without the convergence check the intrinsic carries (all 32 lanes are always here)
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
     unsigned r;
@@ -320,6 +329,7 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
             for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
                 if (j + 4 <= e) {
                     float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+                    prefetch_l1(pts4 + j + PB_DEG_PREFETCH);
                     test_candidate<P>(qx, qy, qz, q0, r2, cnt);
                     const unsigned t0 = (unsigned)slot_sum<P>(cnt);
                     test_candidate<P>(qx, qy, qz, q1, r2, cnt);
