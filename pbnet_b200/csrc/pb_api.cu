@@ -68,10 +68,12 @@ struct pb_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
-    int host_split[8] = {200, 400, 400, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
-                             // (measured at C1, end to end, one-sided k_degree: 45.9 ms with equal thirds, 44.1 ms with 15 / 42.5 / 42.5 %,
-                             // 47-50 ms with 4-5 chunks; symmetric k_degree: 38.2 ms at 15 / 42.5 / 42.5, 37.3 ms at 20 / 40 / 40,
-                             // 37.9 ms at 10 / 30 / 60, 38.4-40.2 ms with 4 chunks: e2e ~ compute + first H2D + last D2H)
+    int host_split[8] = {150, 350, 500, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
+                             // (measured at C1, end to end: e2e ~ compute + first H2D + what is left of the last read-back.
+                             //  one-sided k_degree: 45.9 ms with equal thirds, 44.1 ms at 15 / 42.5 / 42.5 %, 47-50 ms with 4-5 chunks;
+                             //  symmetric k_degree: 38.2 ms at 15 / 42.5 / 42.5, 37.3 ms at 20 / 40 / 40, 38.4-40.2 ms with 4 chunks;
+                             //  with the early read-backs (PB_EARLY_D2H) the last chunk may grow: 35.6 ms at 15 / 35 / 50,
+                             //  35.9 at 12 / 33 / 55, 37.4 at 20 / 40 / 40, 37.7 without the early read-backs)
     int tile_mode = -1;      // PB_TILES: 1 = tiles of 1024 points, 0 = 4096, -1 = by problem size
     int label_ppw = 0;       // PB_LABEL_PPW: points per warp of k_label (0 = by problem size)
     int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
@@ -84,6 +86,10 @@ struct pb_ctx {
     int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t copy_st = nullptr;  // host outputs that are final early (the degrees) leave on their own stream
+    cudaEvent_t ev_hp[2] = {nullptr, nullptr}, ev_degdone[2] = {nullptr, nullptr};  // per work-area slot
+    cudaEvent_t ev_ids[2] = {nullptr, nullptr}, ev_idsdone[2] = {nullptr, nullptr};
+    int early_d2h = 3;     // PB_EARLY_D2H: bit 0 = degrees leave after k_hp_cells, bit 1 = ids leave before k_centres (host outputs)
     int *h_chunk_scalars = nullptr;
     unsigned long long *h_chunk_counters = nullptr;
     size_t h_chunk_cap = 0;
@@ -175,12 +181,21 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
         const char *dsy = getenv("PB_DEG_SYM");
         if (dsy) ctx->deg_sym = dsy[0] != '0';
+        const char *ed = getenv("PB_EARLY_D2H");
+        if (ed) ctx->early_d2h = atoi(ed) & 3;
         const char *dmb = getenv("PB_DEG_MINB_SYM");
         if (dmb && atoi(dmb) >= 6 && atoi(dmb) <= 9) ctx->deg_minb = atoi(dmb);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking);
+    for (int k = 0; k < 2; k++) {
+        cudaEventCreateWithFlags(&ctx->ev_hp[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_degdone[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_ids[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_idsdone[k], cudaEventDisableTiming);
+    }
     *out = ctx;
     return PB_OK;
 }
@@ -204,9 +219,14 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int k = 0; k < 2; k++) {
         if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+        if (ctx->ev_hp[k]) cudaEventDestroy(ctx->ev_hp[k]);
+        if (ctx->ev_degdone[k]) cudaEventDestroy(ctx->ev_degdone[k]);
+        if (ctx->ev_ids[k]) cudaEventDestroy(ctx->ev_ids[k]);
+        if (ctx->ev_idsdone[k]) cudaEventDestroy(ctx->ev_idsdone[k]);
         if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
         if (ctx->auxp[k]) cudaStreamDestroy(ctx->auxp[k]);
     }
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -511,6 +531,7 @@ struct ChunkIO {          // one chunk = a run of consecutive calls; all pointer
     cudaEvent_t ev_front;   // recorded after the extents are on their way to the host
     cudaEvent_t ev_deg[2];  // always-on pair around k_degree
     cudaEvent_t wait_deg;   // k_degree of the previous chunk (other stream) finished, or nullptr
+    int slot;               // work-area slot of the chunk (its early-copy events)
 };
 
 struct ChunkDev {  // device views of the header block, valid after enqueue_front
@@ -719,6 +740,12 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
                                                                w.cell_minhp, cnt, dsem, d.min_pts, w.cell_min18, w.cell_first);
         L++;
+        if (host_io && (ctx->early_d2h & 1)) {  // the degrees are final: their read-back overlaps the rest of the chunk instead of trailing it
+            PB_CUDA(cudaEventRecord(ctx->ev_hp[io.slot], st));
+            PB_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_hp[io.slot], 0));
+            PB_CUDA(cudaMemcpyAsync(io.degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_st));
+            PB_CUDA(cudaEventRecord(ctx->ev_degdone[io.slot], ctx->copy_st));
+        }
     }
     L++;
     mark();  // UNION
@@ -777,6 +804,12 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
                                                    w.box_hi, w.box2_lo, w.box2_hi, d_cluster_id, dsem, w.lab_start18, w.seg_lastlab);
         L++;
     }
+    if (host_io && (ctx->early_d2h & 2)) {  // the ids are final: their read-back overlaps the centre replay
+        PB_CUDA(cudaEventRecord(ctx->ev_ids[io.slot], st));
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_ids[io.slot], 0));
+        PB_CUDA(cudaMemcpyAsync(io.cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_st));
+        PB_CUDA(cudaEventRecord(ctx->ev_idsdone[io.slot], ctx->copy_st));
+    }
     mark();  // CENTRES
     pb::k_centres<<<std::min(gPersist, 148 * 4), 256, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
                                                             w.d_scalars + 9);
@@ -785,8 +818,10 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 10, cudaMemcpyDeviceToHost, st));
     if (prof) PB_CUDA(cudaMemcpyAsync(io.h_counters, w.d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     if (host_io) {
-        PB_CUDA(cudaMemcpyAsync(io.cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(io.degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (ctx->early_d2h & 2) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_idsdone[io.slot], 0));  // issued earlier on the copy stream
+        else PB_CUDA(cudaMemcpyAsync(io.cluster_id, w.cluster_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (ctx->early_d2h & 1) PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_degdone[io.slot], 0));
+        else PB_CUDA(cudaMemcpyAsync(io.degree, w.degree, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));  // issued after k_hp_cells on the copy stream
         PB_CUDA(cudaMemcpyAsync(io.cluster_num, w.cluster_num, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
     }
     mark();  // end
@@ -1169,6 +1204,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         io.ev_front = ctx->front_ev[gi];
         io.ev_deg[0] = ctx->deg_ev[2 * gi], io.ev_deg[1] = ctx->deg_ev[2 * gi + 1];
         io.wait_deg = (ctx->stagger && gi > 0) ? ctx->deg_ev[2 * (gi - 1) + 1] : nullptr;
+        io.slot = gi % slots;
     };
     // Fronts run ahead by at most one chunk per stream slot: chunk gi+2 reuses the work area of chunk gi, so its front is
     // enqueued behind the rest of chunk gi (same stream).  The host waits for a front only to read three integers (the cell

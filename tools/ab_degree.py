@@ -33,6 +33,8 @@ for cfg in args.configs.split(";"):
         os.environ[k] = v
     for prof in (False, True):
         ctx = Context(0, profiling=prof)
+        if os.environ.get("PB_CHUNK_POINTS"):
+            ctx.set_chunk_points(int(os.environ["PB_CHUNK_POINTS"]))
         ts = []
         for i in range(2 + (args.steps if not prof else 1)):
             torch.cuda.synchronize()
