@@ -737,7 +737,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         else pb::k_degree<true, 8><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt);
         PB_CUDA(cudaEventRecord(io.ev_deg[1], st));
         mark();  // HP
-        pb::k_hp_cells<MIXED><<<div_up(n, T256), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
+        pb::k_hp_cells<MIXED><<<div_up(n, T256 * pb::kHpPer), T256, 0, st>>>(n, w.sg, w.pts4, w.fcell_of, w.fcell_key, w.deg_sorted, d_degree, w.cell_hp,
                                                                w.cell_minhp, cnt, dsem, d.min_pts, w.cell_min18, w.cell_first);
         L++;
         if (host_io && (ctx->early_d2h & 1)) {  // the degrees are final: their read-back overlaps the rest of the chunk instead of trailing it

@@ -472,61 +472,74 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
     degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y);
 }
 
-// K9  HP rule + per-cell HP statistics + degree scatter to input order
+// K9  HP rule + per-cell HP statistics + degree scatter to input order.  A thread owns kHpPer points (32 consecutive
+//     points per warp and round): the loads of all rounds are issued before the first round is processed, so the
+//     three-deep chain of dependent loads (cell -> key -> segment table) is paid once per kHpPer points.
+constexpr int kHpPer = 4;
 template <bool MIXED>
-__global__ void k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const int *__restrict__ fcell_of,
-                           const uint64_t *__restrict__ fcell_key, const int *__restrict__ deg_sorted,
-                           int *__restrict__ degree_out, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
-                           unsigned long long *__restrict__ counters, const int *__restrict__ sem,
-                           const int *__restrict__ min_pts_tab, int *__restrict__ cell_min18, int *__restrict__ cell_first) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < n;
-    unsigned act = __ballot_sync(kFull, valid);
-    if (!valid) return;
-    int c = fcell_of[i];
-    int s = (int)(fcell_key[c] >> kSegShift);
-    int d = deg_sorted[i];
-    int *w = reinterpret_cast<int *>(pts4 + i) + 3;
-    int orig = *w;
-    bool hp;  // binary_cuda_functions.cu:175-186
-    if (!MIXED) {
-        hp = d >= sg.min_pts[s];
-    } else {
-        int myc = sem[orig] - 2;
-        hp = d >= min_pts_tab[myc];
-        if (hp) atomicMin(cell_min18 + (long long)c * kCls + myc, orig);
+__global__ void __launch_bounds__(256)
+k_hp_cells(int n, SegArrays sg, float4 *__restrict__ pts4, const int *__restrict__ fcell_of,
+           const uint64_t *__restrict__ fcell_key, const int *__restrict__ deg_sorted,
+           int *__restrict__ degree_out, int *__restrict__ cell_hp, int *__restrict__ cell_minhp,
+           unsigned long long *__restrict__ counters, const int *__restrict__ sem,
+           const int *__restrict__ min_pts_tab, int *__restrict__ cell_min18, int *__restrict__ cell_first) {
+    const int lane = lane_id();
+    const int warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 * kHpPer);  // first point of the warp
+    int cc[kHpPer], dd[kHpPer], oo[kHpPer], ss[kHpPer];
+#pragma unroll
+    for (int k = 0; k < kHpPer; k++) {
+        const int i = warp0 + 32 * k + lane;
+        cc[k] = dd[k] = oo[k] = 0;
+        if (i < n) cc[k] = fcell_of[i], dd[k] = deg_sorted[i], oo[k] = reinterpret_cast<const int *>(pts4 + i)[3];
     }
-    degree_out[orig] = d;
-    if (hp) *w = orig | kHpBit;
-    unsigned grp = __match_any_sync(act, c);
-    unsigned hpm = __ballot_sync(act, hp) & grp;
-    int mn = __reduce_min_sync(grp, hp ? orig : 0x7fffffff);
-    int first = __reduce_min_sync(grp, hp ? i : 0x7fffffff);
-    if (hpm && lane_id() == __ffs(grp) - 1) {
-        // a cell whose points all sit inside this warp is written with plain stores (k_cells initialised the tables);
-        // only the runs that touch the first / last active lane may continue in a neighbouring warp and need atomics
-        const bool interior = !(grp & 1u) && !(grp & (1u << (31 - __clz(act))));
-        if (interior) {
-            cell_hp[c] = __popc(hpm);
-            cell_minhp[c] = mn;
-            cell_first[c] = first;
+#pragma unroll
+    for (int k = 0; k < kHpPer; k++) ss[k] = (warp0 + 32 * k + lane < n) ? (int)(fcell_key[cc[k]] >> kSegShift) : 0;
+    unsigned long long dsum = 0, hsum = 0;
+#pragma unroll
+    for (int k = 0; k < kHpPer; k++) {
+        const int i = warp0 + 32 * k + lane;
+        const bool valid = i < n;
+        const unsigned act = __ballot_sync(kFull, valid);
+        if (!act) break;       // uniform
+        if (!valid) continue;  // only the last warp: the survivors use `act` as their mask below
+        const int c = cc[k], d = dd[k], orig = oo[k];
+        bool hp;  // binary_cuda_functions.cu:175-186
+        if (!MIXED) {
+            hp = d >= sg.min_pts[ss[k]];
         } else {
-            atomicAdd(cell_hp + c, __popc(hpm));
-            atomicMin(cell_minhp + c, mn);
-            atomicMin(cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
+            int myc = sem[orig] - 2;
+            hp = d >= min_pts_tab[myc];
+            if (hp) atomicMin(cell_min18 + (long long)c * kCls + myc, orig);
+        }
+        degree_out[orig] = d;
+        if (hp) reinterpret_cast<int *>(pts4 + i)[3] = orig | kHpBit;
+        unsigned grp = __match_any_sync(act, c);
+        unsigned hpm = __ballot_sync(act, hp) & grp;
+        int mn = __reduce_min_sync(grp, hp ? orig : 0x7fffffff);
+        int first = __reduce_min_sync(grp, hp ? i : 0x7fffffff);
+        if (hpm && lane == __ffs(grp) - 1) {
+            // a cell whose points all sit inside this warp round is written with plain stores (the tables start at their
+            // neutral values); only the runs that touch the first / last active lane may continue in a neighbouring
+            // round and need atomics
+            const bool interior = !(grp & 1u) && !(grp & (1u << (31 - __clz(act))));
+            if (interior) {
+                cell_hp[c] = __popc(hpm);
+                cell_minhp[c] = mn;
+                cell_first[c] = first;
+            } else {
+                atomicAdd(cell_hp + c, __popc(hpm));
+                atomicMin(cell_minhp + c, mn);
+                atomicMin(cell_first + c, first);  // sorted position of the cell's first HP: its representative in k_union
+            }
+        }
+        if (counters) {  // profiling only: [1] sum of degrees, [2] HP count
+            dsum += __reduce_add_sync(act, (unsigned)d);
+            hsum += __popc(__ballot_sync(act, hp));
         }
     }
-    if (counters) {  // profiling only: [1] sum of degrees, [2] HP count
-        unsigned long long dsum = 0, hsum = 0;
-        for (unsigned m = act; m; m &= m - 1) {
-            int l = __ffs(m) - 1;
-            dsum += (unsigned)__shfl_sync(act, d, l);
-            hsum += (unsigned)__shfl_sync(act, (int)hp, l);
-        }
-        if (lane_id() == __ffs(act) - 1) {
-            atomicAdd(counters + 1, dsum);
-            atomicAdd(counters + 2, hsum);
-        }
+    if (counters && lane == 0) {
+        atomicAdd(counters + 1, dsum);
+        atomicAdd(counters + 2, hsum);
     }
 }
 
