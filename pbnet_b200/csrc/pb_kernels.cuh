@@ -379,9 +379,12 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
 }
 
 // one 128-point window; `warp` = window index, (slice, nslice) = this warp's share of the window (small problems)
+// phase: -1 = every window; 0 = only the HEAVY windows (at most two groups: the dense blobs, 128 queries against a long
+// candidate stream), 1 = only the others.  The grid runs phase 0 first, so the kernel drains on short windows.
 template <bool SYM>
 __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const Grid &g, int *__restrict__ deg_sorted,
-                                              unsigned long long *__restrict__ n_tests, int warp, int slice, int nslice) {
+                                              unsigned long long *__restrict__ n_tests, int warp, int slice, int nslice,
+                                              int phase) {
     int lane = lane_id();
     long long base = (long long)warp * kWindow;
     if (base >= n) return;
@@ -396,6 +399,7 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
         hm[k] = __ballot_sync(kFull, head);
         G += __popc(hm[k]);
     }
+    if (phase >= 0 && (G <= 2) != (phase == 0)) return;
     // small problems launch nslice warps per window (gridDim.y).  A window of many small groups is dealt out group by
     // group to teams of `cs` warps (every group's dependent metadata loads then run in parallel on different warps
     // instead of back to back on one); the warps of a team — or, for windows of few large groups, all warps — split the
@@ -468,8 +472,12 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
 
 template <bool SYM, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests) {
-    degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y);
+k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests, int phased) {
+    // phased: the grid holds every window twice, heavy pass first
+    const int nb = phased ? gridDim.x >> 1 : gridDim.x;
+    const int phase = phased ? (blockIdx.x >= nb ? 1 : 0) : -1;
+    const int bx = blockIdx.x - (phase == 1 ? nb : 0);
+    degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y, phase);
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order.  A thread owns kHpPer points (32 consecutive
