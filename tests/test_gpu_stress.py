@@ -85,3 +85,39 @@ def test_full_size_properties(ctx):
         o += n
         ko += k
     assert ko == a["n_clusters"] and len(a["center"]) == 3 * ko
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_scene,copies", [(20_000, 1), (140_000, 3), (250_000, 3)])
+def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
+    """The symmetric neighbour count (every unordered pair tested once, the candidate's side added with REDUX + RED) and the
+    one-sided kernel of round 1 (PB_DEG_SYM=0) give bit-identical outputs: window splitting (small), heavy-first (mid-size)
+    and plain grids, with the small-call kernel switched off so that every size takes the cell-grid pipeline."""
+    import os
+
+    from pbnet_b200 import scenes
+    from pbnet_b200.cluster import Context
+    sc = scenes.make_scene(101 + n_scene % 97, n_scene)
+    calls = scenes.class_calls(sc, copies)
+    xs = np.concatenate([c["xyz_shift"] for c in calls])
+    xo = np.concatenate([c["xyz_orig"] for c in calls])
+    sem = np.concatenate([c["sem"] for c in calls])
+    seg = np.concatenate([c["seg_counts"] for c in calls])
+    csc = np.array([len(c["seg_counts"]) for c in calls], np.int32)
+    res = {}
+    old = {k: os.environ.get(k) for k in ("PB_DEG_SYM", "PB_SMALL")}
+    try:
+        os.environ["PB_SMALL"] = "0"
+        for sym in ("1", "0"):
+            os.environ["PB_DEG_SYM"] = sym
+            c = Context(0)
+            res[sym] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
+            c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert H.diff_report(res["1"], res["0"]) == []
+    assert int(res["1"]["degree"].sum()) > 0
