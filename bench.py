@@ -703,6 +703,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    from pbnet_b200 import sharding
+    # NUMA: this rank's pinned buffers and copy submissions stay on the socket its GPU hangs off (undone before the CPU legs)
+    numa = None if os.environ.get("PB_NUMA_BIND", "1") == "0" else sharding.bind_to_gpu_numa_node(local_rank)
     from pbnet_b200.cluster import Context
     ctx = Context(local_rank)          # production configuration: no stage events, no counters in the timed region
     r18 = np.full(18, np.float32(scenes.RADIUS), np.float32)
@@ -711,7 +714,6 @@ def main():
     n, S, seg, csc, stream = run.n, run.S, run.seg, run.csc, run.stream
 
     # gather of proposals to rank 0 (the only collective; NCCL over NVLink) — pbnet_b200/sharding.py
-    from pbnet_b200 import sharding
     # ids restart at 0 in every call and a call has a handful of clusters: int16 on the wire; the transfer of step i
     # overlaps the kernels of step i+1, the last one is awaited (finish) before the timed region ends
     gather_ids = sharding.Rank0Gather(n, torch.int32, dev, narrow_to=torch.int16, overlap=True)
@@ -770,6 +772,8 @@ def main():
         oh = step_host()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    if numa is not None:
+        os.sched_setaffinity(0, numa[2])  # the verification / CPU-baseline legs use every host core
     clocks = sampler.stop() if rank == 0 else None  # sampled from the first warm-up step to the end of the e2e loop
     h2d = 28 * n
     d2h = 8 * n + 4 * S + 16 * int(oh["n_clusters"])
@@ -837,6 +841,7 @@ def main():
             "next_rows": nxt,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "numa": ({"node": numa[0], "cpus": numa[1]} if numa else None),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

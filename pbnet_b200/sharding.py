@@ -12,6 +12,42 @@ import torch.distributed as dist
 from .workload import shard_scenes  # noqa: F401  (re-export)
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers it allocates
+    next (first touch) and its copy submissions are local to the GPU's PCIe root: with one rank per GPU of a two-socket host,
+    half of the ranks would otherwise pull their inputs across the socket interconnect.  Returns
+    ``(node, n_cpus, previous_affinity)`` or None when the topology is not exposed (single node, container without /sys).
+    ``os.sched_setaffinity(0, previous_affinity)`` undoes it."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus or cpus == prev:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus), prev
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 class Rank0Gather:
     """Variable-length gather of a 1-D tensor to rank 0 with the size exchange and the padded buffers set up
     ONCE (per-step cost = one buffer copy + one ``dist.gather``).  Works on any backend (nccl: device

@@ -136,3 +136,13 @@ def test_local_scene_threshold_and_mask_helpers():
     lab = torch.tensor([0, -100, 1, 1, 0], dtype=torch.int32)
     m = evalpost.dense_masks(lab, 2)
     assert m.tolist() == [[1, 0, 0, 0, 1], [0, 0, 1, 1, 0]]
+
+
+def test_numa_helpers_on_a_host_without_cuda():
+    """sharding.bind_to_gpu_numa_node degrades to None where the topology is not exposed; the cpulist parser handles ranges."""
+    from pbnet_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._parse_cpulist("") == set()
+    import torch
+    if not torch.cuda.is_available():
+        assert sharding.bind_to_gpu_numa_node(0) is None
