@@ -26,7 +26,10 @@ constexpr int kCoarseBits = kCellBits - 1;     // 13
 constexpr int kCoarseMax = (1 << kCoarseBits) - 1;
 constexpr int kSegShift = 3 * kCellBits;       // 42: key = seg<<42 | cz'<<29 | cy'<<16 | cx'<<3 | fine bits
 constexpr int kRowShift = 3 + kCoarseBits;     // 16: key >> 16 identifies (seg, cz', cy') = one coarse row
-constexpr int kMortonBits = 9;                 // LP-assignment order: Morton bits per axis
+#ifndef PB_MORTON_BITS
+#define PB_MORTON_BITS 9
+#endif
+constexpr int kMortonBits = PB_MORTON_BITS;    // LP-assignment order: Morton bits per axis
 constexpr int kMortonMax = (1 << kMortonBits) - 1;
 constexpr int kKey2SegShift = 3 * kMortonBits; // key2 = seg<<27 | morton27  (mixed: seg<<32 | class<<27 | morton27)
 constexpr int kRuns = 9;                       // 3 x 3 coarse stencil rows, each up to 3 coarse cells long
