@@ -299,6 +299,7 @@ __device__ __forceinline__ int slot_sum(const int (&cnt)[2 * P]) {
 template <int P, bool SYM>
 __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
                                              int *__restrict__ deg_sorted, int slice, int nslice) {
+    static_assert(!SYM || 2 * P * 32 <= 255, "a candidate's warp-wide hit count must fit one byte of the packed register");
     const float4 *__restrict__ pts4 = g.pts4;
     const int base = g0 & ~1;
     const float qnan = __int_as_float(0x7fc00000);
