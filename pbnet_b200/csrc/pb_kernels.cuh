@@ -194,8 +194,10 @@ __global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const 
 //     it issue-bound (8 slots per test); v4 uses Blackwell's packed fp32x2 pipe (FADD2/FMUL2/FFMA2): the
 //     two ADJACENT sorted points a lane owns form one 64-bit operand, the candidate coordinate is a
 //     broadcast scalar operand -> 3 FADD2 + FMUL2 + 2 FFMA2 + 2 FSETP + 2 IADD3 per TWO tests (5 slots per
-//     test).  tools/microbench/pipes.cu: the packed pair test tops out at 0.576 warp-tests/clk/SM
-//     (FFMA2-pipe bound) vs 0.5 for the scalar form (issue bound).
+//     test).  tools/microbench/pipes.cu (profiles/microbench_pipes_r01_v2.txt, _r02.txt; slowest-warp timing, no
+//     loop-invariant operands): the one-sided packed candidate loop tops out at 0.485 warp-tests/clk/SM, the scalar
+//     form at 0.332, the symmetric loop (round 2, below) at 0.387 / 0.414 with 2 / 3 query pairs per lane.  A packed
+//     instruction occupies two issue slots, so the pair test is ISSUE bound: 6 x 2 + 4 = 16 slots per two tests.
 // ------------------------------------------------------------------------------------------------
 // cnt += (d <= r2) as FSETP.LE + predicated IADD3 (nvcc emits FSETP.GTU + 2 IADD3 for the C expression)
 __device__ __forceinline__ void count_le(int &cnt, float d, float r2) {
