@@ -65,7 +65,15 @@ struct pb_ctx {
     unsigned long long *h_counters = nullptr;
     // chunked two-stream pipelining of large batched calls
     long long chunk_points = 0;  // 0 = automatic
-    cudaStream_t aux[2] = {nullptr, nullptr}, auxp[2] = {nullptr, nullptr};
+    static constexpr int kMaxSlots = 4;  // chunk streams / private work areas in flight
+    cudaStream_t aux[kMaxSlots] = {}, auxp[kMaxSlots] = {};
+    int slots_host = 2, slots_dev = 2;   // PB_SLOTS_HOST / PB_SLOTS_DEV: work areas (and streams) the chunks of a call rotate over
+    int dev_chunks = 2;                  // PB_DEV_CHUNKS: chunks of a device-resident call of >= 6 M points
+                                         // (measured at C1 with PB_TIMELINE: the k_degree kernels of concurrent chunks run one after the
+                                         //  other — each fills every SM — and the tails of two chunks overlap 1.4x; device data: 31.3 ms
+                                         //  for 2 chunks / 2 slots and 3 / 3, 31.7 for 4 / 4, 32.1 for 4 / 2; host data: a third slot lets
+                                         //  the last chunk's H2D and k_degree start before the middle chunk's and starves the earlier
+                                         //  chunks' tails: 37.2-45.8 ms against 36.8 ms with two slots)
     int prio_mode = -1;  // -1 automatic (host data: prioritised pair), 0 never, 1 always
     bool stagger = false;  // PB_STAGGER=1: serialise k_degree of consecutive chunks (measured: 41.0 ms vs 39.9 ms in lock step at C1)
     int host_split[8] = {150, 350, 500, 0, 0, 0, 0, 0};  // PB_HOST_SPLIT: chunk sizes for host data of >= 6 M points, per mille
@@ -85,10 +93,10 @@ struct pb_ctx {
     int coop_blocks_per_sm = 0, sm_count = 0;
     int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxSlots] = {};
     cudaStream_t copy_st = nullptr;  // host outputs that are final early (the degrees) leave on their own stream
-    cudaEvent_t ev_hp[2] = {nullptr, nullptr}, ev_degdone[2] = {nullptr, nullptr};  // per work-area slot
-    cudaEvent_t ev_ids[2] = {nullptr, nullptr}, ev_idsdone[2] = {nullptr, nullptr};
+    cudaEvent_t ev_hp[kMaxSlots] = {}, ev_degdone[kMaxSlots] = {};  // per work-area slot
+    cudaEvent_t ev_ids[kMaxSlots] = {}, ev_idsdone[kMaxSlots] = {};
     bool deg_phased = true; // PB_DEG_PHASED=0: k_degree always walks the windows in order (1: heavy windows first on mid-size problems)
     int early_d2h = 3;     // PB_EARLY_D2H: bit 0 = degrees leave after k_hp_cells, bit 1 = ids leave before k_centres (host outputs)
     int *h_chunk_scalars = nullptr;
@@ -153,10 +161,14 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         // calls are 1 ms SLOWER with priorities and keep the plain pair)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking);
-        cudaStreamCreateWithPriority(&ctx->auxp[0], cudaStreamNonBlocking, hi);
-        cudaStreamCreateWithPriority(&ctx->auxp[1], cudaStreamNonBlocking, lo);
+        for (int k = 0; k < pb_ctx::kMaxSlots; k++) {
+            cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking);
+            cudaStreamCreateWithPriority(&ctx->auxp[k], cudaStreamNonBlocking, (k & 1) ? lo : hi);
+        }
+        const char *sh = getenv("PB_SLOTS_HOST"), *sd = getenv("PB_SLOTS_DEV"), *dc = getenv("PB_DEV_CHUNKS");
+        if (sh && atoi(sh) >= 1 && atoi(sh) <= pb_ctx::kMaxSlots) ctx->slots_host = atoi(sh);
+        if (sd && atoi(sd) >= 1 && atoi(sd) <= pb_ctx::kMaxSlots) ctx->slots_dev = atoi(sd);
+        if (dc && atoi(dc) >= 1 && atoi(dc) <= 8) ctx->dev_chunks = atoi(dc);
         const char *e = getenv("PB_STREAM_PRIO");  // experiments: 0 = never, 1 = always
         ctx->prio_mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         const char *sg = getenv("PB_STAGGER");
@@ -190,10 +202,9 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         if (dmb && atoi(dmb) >= 8 && atoi(dmb) <= 9) ctx->deg_minb = atoi(dmb);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming);
+    for (int k = 0; k < pb_ctx::kMaxSlots; k++) cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < pb_ctx::kMaxSlots; k++) {
         cudaEventCreateWithFlags(&ctx->ev_hp[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_degdone[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_ids[k], cudaEventDisableTiming);
@@ -220,7 +231,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if (ctx->h_chunk_scalars) cudaFreeHost(ctx->h_chunk_scalars);
     if (ctx->h_chunk_counters) cudaFreeHost(ctx->h_chunk_counters);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < pb_ctx::kMaxSlots; k++) {
         if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
         if (ctx->ev_hp[k]) cudaEventDestroy(ctx->ev_hp[k]);
         if (ctx->ev_degdone[k]) cudaEventDestroy(ctx->ev_degdone[k]);
@@ -1077,7 +1088,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         // host data: three chunks on the prioritised stream pair (the first H2D copy is the exposed head of the pipeline)
         // (round 2, measured on 3.6 M points = one rank's share of C1 at 8 GPUs: 6.36 ms unchunked, 6.18 ms at 2 chunks,
         // 7.1 / 7.4 ms at 3 / 4 chunks; from host memory 8.7 -> 7.9 ms at 2 chunks)
-        const int auto_chunks = n >= 6000000 ? (host_io ? 3 : 2) : (n >= 1500000 ? 2 : 1);
+        const int auto_chunks = n >= 6000000 ? (host_io ? 3 : ctx->dev_chunks) : (n >= 1500000 ? 2 : 1);
         long long target = ctx->chunk_points > 0 ? ctx->chunk_points
                            : (ctx->chunk_points == 0 && auto_chunks > 1 ? ((long long)n + auto_chunks - 1) / auto_chunks : (long long)n + 1);
         int c = 0;
@@ -1113,7 +1124,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     }
     const int G = (int)chunks.size();
     const bool multi = G > 1;
-    const int slots = multi ? 2 : 1;
+    const int slots = multi ? std::min(G, host_io ? ctx->slots_host : ctx->slots_dev) : 1;
     const bool small_tiles = ctx->tile_mode == 1 || (ctx->tile_mode < 0 && n < 262144);
     // per-chunk host tables: local segment starts, first segment of every segment's call, tile table
     std::vector<std::vector<int>> lstart(G), lcall(G);
@@ -1138,7 +1149,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     const bool mixed = attempt == 1;
     ctx->launches = 0;
     // ---- workspace: `slots` private work areas + call-wide cluster metadata ------------------------------
-    Work w[2];
+    Work w[pb_ctx::kMaxSlots];
     float *center_all = nullptr;
     int *clt_sem_all = nullptr;
     for (int pass = 0; pass < 2; pass++) {
@@ -1185,13 +1196,14 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     float thresh[18];
     for (int i = 0; i < 18; i++) thresh[i] = kMeanCount[i] * para_f;  // fp32 multiply, binary.cu:256
 
-    cudaStream_t cs[2] = {st, st};
+    cudaStream_t cs[pb_ctx::kMaxSlots] = {st, st, st, st};
     if (multi) {
         const bool prio = ctx->prio_mode < 0 ? host_io : ctx->prio_mode == 1;
-        cs[0] = prio ? ctx->auxp[0] : ctx->aux[0], cs[1] = prio ? ctx->auxp[1] : ctx->aux[1];
         PB_CUDA(cudaEventRecord(ctx->ev_fork, st));
-        PB_CUDA(cudaStreamWaitEvent(cs[0], ctx->ev_fork, 0));
-        PB_CUDA(cudaStreamWaitEvent(cs[1], ctx->ev_fork, 0));
+        for (int k = 0; k < slots; k++) {
+            cs[k] = prio ? ctx->auxp[k] : ctx->aux[k];
+            PB_CUDA(cudaStreamWaitEvent(cs[k], ctx->ev_fork, 0));
+        }
     }
     std::vector<ChunkIO> ios(G);
     std::vector<int> hdr_host;
@@ -1217,8 +1229,8 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
     int fronts = 0;
     auto front = [&](int gi) -> int {
         make_io(gi);
-        return small_tiles ? enqueue_front<kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host)
-                           : enqueue_front<kTileItems>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % 2], ctx->launches, hdr_host);
+        return small_tiles ? enqueue_front<kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % slots], ctx->launches, hdr_host)
+                           : enqueue_front<kTileItems>(ctx, w[gi % slots], ios[gi], host_io, mixed, radius, min_pts, thresh, cs[gi % slots], ctx->launches, hdr_host);
     };
     for (; fronts < std::min(G, slots); fronts++) {
         int rc = front(fronts);
@@ -1228,11 +1240,11 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         PB_CUDA(cudaEventSynchronize(ios[gi].ev_front));
         int rc;
         if (small_tiles)
-            rc = mixed ? enqueue_rest<true, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
-                       : enqueue_rest<false, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
+            rc = mixed ? enqueue_rest<true, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % slots], ctx->launches)
+                       : enqueue_rest<false, kTileItemsSmall>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % slots], ctx->launches);
         else
-            rc = mixed ? enqueue_rest<true, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches)
-                       : enqueue_rest<false, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % 2], ctx->launches);
+            rc = mixed ? enqueue_rest<true, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % slots], ctx->launches)
+                       : enqueue_rest<false, kTileItems>(ctx, w[gi % slots], ios[gi], host_io, assign_lp, cs[gi % slots], ctx->launches);
         if (rc) return rc;
         if (fronts < G) {  // the next chunk of this slot
             rc = front(fronts++);
@@ -1240,10 +1252,10 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         }
     }
     if (multi) {
-        PB_CUDA(cudaEventRecord(ctx->ev_join[0], cs[0]));
-        PB_CUDA(cudaEventRecord(ctx->ev_join[1], cs[1]));
-        PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
-        PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
+        for (int k = 0; k < slots; k++) {
+            PB_CUDA(cudaEventRecord(ctx->ev_join[k], cs[k]));
+            PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+        }
     }
     PB_CUDA(cudaStreamSynchronize(st));
     int errbits = 0;
@@ -1304,6 +1316,19 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         covered += cur_b - cur_a;
         ctx->stage_ms[ST_DEGREE] = covered;
         ctx->counters[6] = G;
+    }
+    if (prof && getenv("PB_TIMELINE")) {  // diagnostic: when every stage of every chunk started, on the clock of chunk 0's first event
+        cudaEvent_t t0 = ctx->chunk_ev[0];
+        for (int gi = 0; gi < G; gi++) {
+            cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
+            fprintf(stderr, "[pb timeline] chunk %d (%d points, stream %d):", gi, chunks[gi].p1 - chunks[gi].p0, gi % slots);
+            for (int i = 0; i <= ST_COUNT; i++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, t0, ev[i]);
+                fprintf(stderr, " %s %.2f", i < ST_COUNT ? kStageNames[i] : "end", ms);
+            }
+            fprintf(stderr, "\n");
+        }
     }
     if (prof) {
         const float deg_union = ctx->stage_ms[ST_DEGREE];
