@@ -451,6 +451,10 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
                 if (SYM && lane == 4) jb = gend;  // the own row: only what follows the group (its end cell is never empty)
             }
             unsigned cand = __reduce_add_sync(kFull, (unsigned)(je - jb));
+            if (SYM && cand == 0 && total == 1) {  // a lone point with an empty later stencil: its only hit would be itself
+                pos = gend;
+                continue;
+            }
             if (SYM && lane == kRuns) jb = pos, je = gend;  // range 9: the group itself, one-sided
             if (n_tests && sub == 0) {
                 tests += (unsigned long long)(cand + (SYM ? (unsigned)total : 0u)) * (unsigned)total;
