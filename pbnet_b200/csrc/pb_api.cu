@@ -86,7 +86,10 @@ struct pb_ctx {
     int label_ppw = 0;       // PB_LABEL_PPW: points per warp of k_label (0 = by problem size)
     int deg_smem = 0;        // PB_DEG_SMEM: unused dynamic shared memory requested for k_degree: caps its resident CTAs per SM so that
                              // registers stay free for the other chunk's latency-bound kernels (overlap experiment)
-    int deg_slice_mult = 48; // PB_DEG_SLICES (measured on one 224 k-point scene: k_degree 271 us at 16, 211 us at 48): warps per SM that k_degree aims for on small problems (window splitting)
+    int deg_slice_mult = 512; // PB_DEG_SLICES: warps per SM that k_degree aims for when it splits the candidate streams of a window over several
+                             // warps (measured: one 224 k-point scene 271 us at 16, 211 us at 48, no change up to 512; C4, 1 M points in dense
+                             // blobs: k_degree 1.53 ms at 48 (38 % of the SM time idle: whole windows are too coarse a unit), 0.81 at 256,
+                             // 0.72 at 512 / 1024; 3.6 M points: 5.13 ms per step at 48, 5.05 at 512; C1 chunks are beyond the range)
     int small_mode = -1;   // PB_SMALL=0: never use the small-call kernel; 1: whenever it is eligible; -1: automatic
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
     size_t h_stage_cap = 0;
