@@ -151,36 +151,64 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 
 // K7  coarse stencil rows: runs9[c*9 + (dz+1)*3 + (dy+1)] = [first coarse cell, last+1) with
 //     cx'-1 <= x' <= cx'+1 in coarse row (cy'+dy, cz'+dz) — contiguous because cells sort x-fastest
-__global__ void k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const int *__restrict__ d_Cc,
-                       int2 *__restrict__ runs9) {
-    long long total = (long long)(*d_Cc) * kRuns;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(t / kRuns), k = (int)(t % kRuns);
-        uint64_t key = cc_key[c];  // seg<<39 | z'<<26 | y'<<13 | x'
-        int s = (int)(key >> (3 * kCoarseBits));
-        int cx = (int)(key & kCoarseMax), cy = (int)((key >> kCoarseBits) & kCoarseMax),
-            cz = (int)((key >> (2 * kCoarseBits)) & kCoarseMax);
-        int ny = cy + (k % 3) - 1, nz = cz + (k / 3) - 1;
-        int2 out = make_int2(0, 0);
-        if (ny >= 0 && ny <= kCoarseMax && nz >= 0 && nz <= kCoarseMax) {
-            uint64_t base = ((uint64_t)s << (3 * kCoarseBits)) | ((uint64_t)nz << (2 * kCoarseBits)) |
-                            ((uint64_t)ny << kCoarseBits);
-            uint64_t klo = base | (uint64_t)max(cx - 1, 0);
-            uint64_t khi = base | (uint64_t)min(cx + 1, kCoarseMax);  // inclusive
-            int b = sg.cc_start[s], e = sg.cc_end[s];
-            int lo = b, hi = e;
-            while (lo < hi) {  // first cell with key >= klo
-                int mid = (lo + hi) >> 1;
-                if (__ldg(cc_key + mid) < klo) lo = mid + 1;
-                else hi = mid;
+//     Four (cell, row) searches per thread run in lock step: every probe round issues four independent loads instead of
+//     one (the kernel is a chain of ~log2(cells of the segment) dependent L2 loads per search).
+constexpr int kRunsIlp = 4;
+__global__ void __launch_bounds__(256)
+k_runs(SegArrays sg, const uint64_t *__restrict__ cc_key, const int *__restrict__ d_Cc, int2 *__restrict__ runs9) {
+    const long long total = (long long)(*d_Cc) * kRuns;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * kRunsIlp) {
+        uint64_t klo[kRunsIlp], khi[kRunsIlp];
+        int lo[kRunsIlp], hi[kRunsIlp], e[kRunsIlp];
+        bool ok[kRunsIlp];
+#pragma unroll
+        for (int u = 0; u < kRunsIlp; u++) {
+            const long long t = t0 + u * stride;
+            ok[u] = false, lo[u] = hi[u] = e[u] = 0, klo[u] = khi[u] = 0;
+            if (t >= total) continue;
+            const int c = (int)(t / kRuns), k = (int)(t % kRuns);
+            const uint64_t key = cc_key[c];  // seg<<39 | z'<<26 | y'<<13 | x'
+            const int s = (int)(key >> (3 * kCoarseBits));
+            const int cx = (int)(key & kCoarseMax), cy = (int)((key >> kCoarseBits) & kCoarseMax),
+                      cz = (int)((key >> (2 * kCoarseBits)) & kCoarseMax);
+            const int ny = cy + (k % 3) - 1, nz = cz + (k / 3) - 1;
+            if (ny >= 0 && ny <= kCoarseMax && nz >= 0 && nz <= kCoarseMax) {
+                const uint64_t base = ((uint64_t)s << (3 * kCoarseBits)) | ((uint64_t)nz << (2 * kCoarseBits)) |
+                                      ((uint64_t)ny << kCoarseBits);
+                klo[u] = base | (uint64_t)max(cx - 1, 0);
+                khi[u] = base | (uint64_t)min(cx + 1, kCoarseMax);  // inclusive
+                lo[u] = sg.cc_start[s], hi[u] = e[u] = sg.cc_end[s];
+                ok[u] = true;
             }
-            int first = lo;
-            // at most three cells (x'-1, x', x'+1) of that row follow: a short linear walk instead of a second search
-            while (lo < e && __ldg(cc_key + lo) <= khi) lo++;
-            out = make_int2(first, lo);
         }
-        runs9[t] = out;
+        bool busy = true;
+        while (busy) {  // first cell with key >= klo, all searches one probe per round
+            busy = false;
+#pragma unroll
+            for (int u = 0; u < kRunsIlp; u++) {
+                if (lo[u] < hi[u]) {
+                    const int mid = (lo[u] + hi[u]) >> 1;
+                    if (__ldg(cc_key + mid) < klo[u]) lo[u] = mid + 1;
+                    else hi[u] = mid;
+                    busy = true;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRunsIlp; u++) {
+            const long long t = t0 + u * stride;
+            if (t >= total) continue;
+            int2 out = make_int2(0, 0);
+            if (ok[u]) {
+                const int first = lo[u];
+                int p = first;
+                // at most three cells (x'-1, x', x'+1) of that row follow: a short linear walk instead of a second search
+                while (p < e[u] && __ldg(cc_key + p) <= khi[u]) p++;
+                out = make_int2(first, p);
+            }
+            runs9[t] = out;
+        }
     }
 }
 
@@ -1131,6 +1159,7 @@ __device__ __forceinline__ void ctr_chain(const CtrSmem &sm, int half, int fill,
     }
 }
 
+constexpr int kCtrBigSegment = 8192;  // points
 // whole block (8 warps = 256 threads) must call
 __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const int *__restrict__ clt_seg,
                                               const int *__restrict__ cluster_id, const float *__restrict__ x,
@@ -1142,11 +1171,15 @@ __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const 
         __syncthreads();
         if (threadIdx.x == 0) sm.cluster = atomicAdd(next_cluster, 1);
         __syncthreads();
-        const int kk = sm.cluster;
-        if (kk >= K) break;
+        // the cluster list is walked twice: clusters of LARGE segments first (their serial replay is the kernel's critical path
+        // and must not start last), the others afterwards
+        const int k2 = sm.cluster;
+        if (k2 >= 2 * K) break;
+        const int kk = k2 >= K ? k2 - K : k2;
         const int s = clt_seg[kk];
         const int local = kk - sg.id_base[s];
         const int b = sg.start[s], e = sg.start[s + 1];
+        if ((e - b >= kCtrBigSegment) != (k2 < K)) continue;  // uniform: every thread reads the same sm.cluster
         const int nchunks = (e - b + kCtrChunkPts - 1) / kCtrChunkPts;
         float M = 0.f;   // lane c < 3 of warp 0 carries coordinate c
         int cnt = 0;     // members replayed so far (warp 0) / gathered so far (warps 1..7)
