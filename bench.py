@@ -462,15 +462,21 @@ def timed_steps(run, steps, warmup, barrier, max_over_ranks, post_step=None, pos
 
 
 # ----------------------------------------------------------------------------------------------------
-def voxel_bench(d_xo, n, dev):
+def voxel_bench(d_xo, n, dev, scene_of_point=None):
     """Rows a12-a14, the HBM-bound scatter-gather of the path: preallocated outputs, >= 20 repetitions over a rotation
-    of buffer sets larger than L2 (126 MB), min / median per op."""
+    of buffer sets larger than L2 (126 MB), min / median per op.  The batch column is the point's scene, as in the
+    reference (ME.utils.batched_coordinates, network/PBNet.py:236-247: scenes never share a voxel); without it
+    (`scene_of_point=None`) all scenes fall into ONE grid and every voxel row is fetched once per scene that touches it."""
     import torch
 
     from pbnet_b200 import scenes, voxel
     nv = min(n, 8_000_000)
     coords = torch.stack([d_xo[0][:nv], d_xo[1][:nv], d_xo[2][:nv]], 1).contiguous()
-    bcol = torch.zeros(nv, dtype=torch.int32, device=dev)
+    if scene_of_point is None:
+        bcol = torch.zeros(nv, dtype=torch.int32, device=dev)
+    else:
+        sc = np.ascontiguousarray(scene_of_point[:nv]).astype(np.int32)
+        bcol = torch.from_numpy(sc - sc.min()).to(dev)
     peak_v, _ = measured_peaks()
     reps = 24
 
@@ -498,7 +504,8 @@ def voxel_bench(d_xo, n, dev):
     t_bwd = timed_each(lambda i: voxel.voxel_rows(outs[i % sets], vm, "sum", out=gouts[i % sets]), reps)
     gb_f = (nv * C * 4 + V * C * 4 + nv * 8) / 1e9
     gb_b = (nv * C * 4 + V * C * 4 + nv * 4 + V * 4) / 1e9
-    res = {"points": nv, "voxels": V, "repetitions": reps, "buffers": f"{sets} rotating input/output sets, outputs preallocated",
+    res = {"points": nv, "voxels": V, "batches": int(bcol.max().item()) + 1, "repetitions": reps,
+           "buffers": f"{sets} rotating input/output sets, outputs preallocated",
            "voxelize_points_per_s": {"best": nv / t_vox[0], "median": nv / t_vox[1]},
            "devoxelize": {"channels": C, "ms_min": t_dev[0] * 1e3, "ms_median": t_dev[1] * 1e3, "algorithmic_gb": gb_f,
                           "achieved_gbs_median": gb_f / t_dev[1], "frac_of_hbm_copy_peak_median": gb_f / t_dev[1] / peak_v,
@@ -641,6 +648,10 @@ def run_stress(args):
         sweep.append({"point": label, "points": run.n, "value": run.n / (ms_step * 1e-3), "ms_per_step": ms_step,
                       "clusters": int(out["n_clusters"]), "launches_per_step": int(launches), "roofline": roof, "roofline_alu": alu,
                       "sum_degree_per_point": counters["sum_deg"] / max(1, run.n), "hp_points": counters["n_hp"],
+                      "centre_replay": {"halves": counters.get("centre_halves", 0),
+                                        "replayed_with_div_rn": counters.get("centre_halves_replayed", 0),
+                                        "replay_cycles": counters.get("centre_replay_cycles", 0),
+                                        "gather_cycles": counters.get("centre_gather_cycles", 0)},
                       "stage_ms": {k: round(v, 3) for k, v in stage.items()}, "verify": ver, "cpu_oracle_points_per_s": cpu_rate})
         del run
         torch.cuda.empty_cache()
@@ -804,7 +815,7 @@ def main():
     dropin = vox = nxt = None
     if rank == 0 and not args.no_extras:
         dropin = dropin_bench(w, args.dropin_calls)
-        vox = voxel_bench(run.d_in[3:6], n, dev)
+        vox = voxel_bench(run.d_in[3:6], n, dev, np.repeat(w["call_scene"], w["call_points"]))
         nxt = next_rows_bench(sizes, dev)
 
     if rank == 0:

@@ -90,6 +90,9 @@ struct pb_ctx {
                              // warps (measured: one 224 k-point scene 271 us at 16, 211 us at 48, no change up to 512; C4, 1 M points in dense
                              // blobs: k_degree 1.53 ms at 48 (38 % of the SM time idle: whole windows are too coarse a unit), 0.81 at 256,
                              // 0.72 at 512 / 1024; 3.6 M points: 5.13 ms per step at 48, 5.05 at 512; C1 chunks are beyond the range)
+    int devox_u = 4;           // PB_DEVOX_U: elements per thread of k_devox
+    int small_deg_slices = 0;  // PB_SMALL_SLICES: candidate slices per query group in P1 of the small-call kernel (0: automatic)
+    int small_tree_cap = pbsm::kTreeMax;  // PB_SMALL_TREES: P3 of the small-call kernel works on the tree graph up to this many trees (0: union-find always)
     int small_mode = -1;   // PB_SMALL=0: never use the small-call kernel; 1: whenever it is eligible; -1: automatic
     char *h_stage = nullptr;  // pinned staging of the small-call path (inputs in, results out: one copy each way)
     size_t h_stage_cap = 0;
@@ -195,6 +198,12 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         if (ds && atoi(ds) > 0) ctx->deg_slice_mult = atoi(ds);
         const char *sm = getenv("PB_SMALL");
         ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
+        const char *du = getenv("PB_DEVOX_U");
+        if (du) ctx->devox_u = atoi(du);
+        const char *ssl = getenv("PB_SMALL_SLICES");
+        if (ssl) ctx->small_deg_slices = std::max(0, atoi(ssl));
+        const char *stc = getenv("PB_SMALL_TREES");
+        if (stc) ctx->small_tree_cap = std::max(0, std::min(atoi(stc), (int)pbsm::kTreeMax));
         const char *dsy = getenv("PB_DEG_SYM");
         if (dsy) ctx->deg_sym = dsy[0] != '0';
         const char *dp = getenv("PB_DEG_PHASED");
@@ -831,7 +840,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     }
     mark();  // CENTRES
     pb::k_centres<<<std::min(gPersist, 148 * 4), 256, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
-                                                            w.d_scalars + 9);
+                                                            w.d_scalars + 9, cnt ? cnt + 4 : nullptr);
     L++;
     mark();  // D2H
     PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 10, cudaMemcpyDeviceToHost, st));
@@ -860,7 +869,7 @@ constexpr int kNotSmall = -1;
 constexpr long long kSmallAdjWords = 3ll << 20;   // 12 MB of adjacency bitmap: one segment of ~10 k points (measured on a B200:
                                                   // 0.21 ms at 2.3 k points, 0.36 ms at 6 k vs 0.50 / 0.63 ms through the cell grid; the
                                                   // O(n^2) phases cross over near 12 k points)
-constexpr int kSmallCentreHead = 256;             // clusters whose centres travel with the first read-back
+constexpr int kSmallCentreHead = pbsm::kCentreHead;             // clusters whose centres travel with the first read-back
 constexpr int kSmallHead = 48;                    // ints of scalars in front of the result block (16 scalars + 11 time stamps)
 }  // namespace
 
@@ -911,12 +920,17 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
         a.rep = ar.get<int>(N), a.keep = ar.get<int>(N), a.kscan = ar.get<int>(N), a.clt_seg = ar.get<int>(N);
         a.adj = ar.get<unsigned>((size_t)std::max<long long>(adj_words, 1));
         a.root0 = ar.get<int>(N), a.best64 = ar.get<unsigned long long>(N);
+        a.tslot = ar.get<int>(N), a.troot = ar.get<int>(pbsm::kTreeMax), a.lplist = ar.get<int>(N);
+        a.tidx = ar.get<unsigned char>(N);
         // zero-initialised region, ending with the scalars; the result block [scalars | cluster_num | cluster_id | degree]
         // starts there (one read-back when the results go to the host)
         zero_begin = reinterpret_cast<char *>(ar.get<char>(0));
         a.hpmask = ar.get<unsigned>(mask_words), a.labmask = ar.get<unsigned>(mask_words);
         a.flag = ar.get<int>(N), a.raw_count = ar.get<int>(N);
-        outblk = ar.get<int>(kSmallHead + pbsm::kMaxSeg + 2 * N);
+        a.deg_acc = ar.get<int>(N);
+        a.conn = ar.get<unsigned long long>(pbsm::kTreeMax), a.tcnt = ar.get<int>(4), a.lpcnt = ar.get<int>(pbsm::kMaxSeg);
+        // [scalars | cluster_num | cluster_id | degree | centres and classes of the first kSmallCentreHead clusters]
+        outblk = ar.get<int>(kSmallHead + pbsm::kMaxSeg + 2 * N + 4 * kSmallCentreHead);
         if (pass == 0) {
             int rc = ensure_arena(ctx, dry.off, st);
             if (rc) return rc;
@@ -925,6 +939,7 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     a.scal = outblk;
     const size_t zero_bytes = reinterpret_cast<char *>(outblk + kSmallHead) - zero_begin;
     a.n = n, a.S = S, a.assign_lp = assign_lp;
+    a.tree_cap = ctx->small_tree_cap, a.deg_slices = ctx->small_deg_slices;
     for (int i = 0; i < 18; i++) a.radius[i] = radius[i], a.min_pts[i] = min_pts[i], a.thresh[i] = kMeanCount[i] * para_f;
     a.sg.start = d_start, a.call_first = d_callfirst;
     // ---- inputs
@@ -948,6 +963,7 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
         a.sem = reinterpret_cast<const int *>(din + 6 * N);
         a.cluster_num = outblk + kSmallHead, a.cluster_id = outblk + kSmallHead + pbsm::kMaxSeg, a.degree = outblk + kSmallHead + pbsm::kMaxSeg + n;
         a.center = d_center, a.clt_sem = d_cltsem;
+        a.center_head = reinterpret_cast<float *>(outblk + out_ints), a.cltsem_head = outblk + out_ints + 3 * kSmallCentreHead;
     } else {
         a.x = x, a.y = y, a.z = z, a.xo = xo, a.yo = yo, a.zo = zo, a.sem = sem;
         a.cluster_num = cluster_num, a.cluster_id = cluster_id, a.degree = degree;
@@ -965,9 +981,8 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     int scal_local[kSmallHead];
     const int head = std::min(n, kSmallCentreHead);
     if (host_io) {
-        PB_CUDA(cudaMemcpyAsync(hres, outblk, out_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(hres + out_ints, d_center, sizeof(float) * 3 * head, cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaMemcpyAsync(hres + out_ints + 3 * kSmallCentreHead, d_cltsem, sizeof(int) * head, cudaMemcpyDeviceToHost, st));
+        // one read-back: the kernel keeps the first clusters' centres and classes right behind the result block
+        PB_CUDA(cudaMemcpyAsync(hres, outblk, (out_ints + 4 * (size_t)kSmallCentreHead) * sizeof(int), cudaMemcpyDeviceToHost, st));
     } else {
         PB_CUDA(cudaMemcpyAsync(ctx->h_small, outblk, sizeof(int) * kSmallHead, cudaMemcpyDeviceToHost, st));
     }
@@ -1338,7 +1353,7 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
         for (int i = 0; i < 6; i++) ctx->counters[i] = 0;
         ctx->counters[8] = 0;
-        ctx->counters[10] = 0;
+        ctx->counters[10] = ctx->counters[11] = ctx->counters[12] = ctx->counters[13] = ctx->counters[14] = 0;
         for (int gi = 0; gi < G; gi++) {
             cudaEvent_t *ev = &ctx->chunk_ev[(size_t)gi * (ST_COUNT + 1)];
             for (int i = 0; i < ST_COUNT; i++) {
@@ -1352,6 +1367,10 @@ static int run_impl(pb_ctx *ctx, const float *x, const float *y, const float *z,
             ctx->counters[1] += (int64_t)hc[1];
             ctx->counters[2] += (int64_t)hc[2];
             ctx->counters[10] += (int64_t)hc[3];
+            ctx->counters[11] += (int64_t)hc[4];
+            ctx->counters[12] += (int64_t)hc[5];
+            ctx->counters[13] += (int64_t)hc[6];
+            ctx->counters[14] += (int64_t)hc[7];
             ctx->counters[3] += hs[4];
             ctx->counters[4] += hs[1];
             ctx->counters[5] += hs[2];
@@ -1663,14 +1682,18 @@ extern "C" int pb_devoxelize(pb_ctx *ctx, const float *vfeat, int64_t V, int C, 
     bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_v) | reinterpret_cast<uintptr_t>(d_out)) % 16 == 0);
     const long long width = vec4 ? C / 4 : C;
     const long long total = n * width;
-    const int grid = (int)std::min<long long>((total + T - 1) / T, 148LL * 64);  // grid-stride, 64 blocks per SM
-    if (total < (1LL << 32)) {
-        if (vec4) pbv::k_devox<float4, uint32_t><<<grid, T, 0, st>>>((const float4 *)d_v, (uint32_t)width, d_inv, (uint32_t)total, (float4 *)d_out);
-        else pbv::k_devox<float, uint32_t><<<grid, T, 0, st>>>(d_v, (uint32_t)width, d_inv, (uint32_t)total, d_out);
-    } else {
-        if (vec4) pbv::k_devox<float4, unsigned long long><<<grid, T, 0, st>>>((const float4 *)d_v, (unsigned long long)width, d_inv, (unsigned long long)total, (float4 *)d_out);
-        else pbv::k_devox<float, unsigned long long><<<grid, T, 0, st>>>(d_v, (unsigned long long)width, d_inv, (unsigned long long)total, d_out);
+    const int U = ctx->devox_u;  // elements per thread (PB_DEVOX_U: 2, 4 or 8)
+    const int grid = (int)std::min<long long>((total + (long long)U * T - 1) / ((long long)U * T), 148LL * 128 / U);  // grid-stride
+#define PB_DEVOX(UU)                                                                                                          \
+    if (total < (1LL << 32) - 4096) {                                                                                         \
+        if (vec4) pbv::k_devox<float4, uint32_t, UU><<<grid, T, 0, st>>>((const float4 *)d_v, (uint32_t)width, d_inv, (uint32_t)total, (float4 *)d_out); \
+        else pbv::k_devox<float, uint32_t, UU><<<grid, T, 0, st>>>(d_v, (uint32_t)width, d_inv, (uint32_t)total, d_out);      \
+    } else {                                                                                                                  \
+        if (vec4) pbv::k_devox<float4, unsigned long long, UU><<<grid, T, 0, st>>>((const float4 *)d_v, (unsigned long long)width, d_inv, (unsigned long long)total, (float4 *)d_out); \
+        else pbv::k_devox<float, unsigned long long, UU><<<grid, T, 0, st>>>(d_v, (unsigned long long)width, d_inv, (unsigned long long)total, d_out); \
     }
+    if (U == 2) { PB_DEVOX(2) } else if (U == 8) { PB_DEVOX(8) } else { PB_DEVOX(4) }
+#undef PB_DEVOX
     ctx->launches = 1;
     if (host_io) PB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * C * 4, cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaGetLastError());

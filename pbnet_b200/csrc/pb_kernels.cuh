@@ -1050,7 +1050,7 @@ __global__ void k_selftest_division(unsigned long long n_samples, unsigned long 
 constexpr int kCtrGatherWarps = 7;
 constexpr int kCtrChunkPts = kCtrGatherWarps * 160;   // points scanned per chunk (5 per gather lane)
 
-struct CtrSmem {
+struct alignas(16) CtrSmem {
     float buf[2][3][kCtrChunkPts];
     float rcp[2][kCtrChunkPts];
     int wcount[kCtrGatherWarps];
@@ -1102,7 +1102,8 @@ __device__ __forceinline__ void ctr_gather(CtrSmem &sm, int half, int ub, int e,
 }
 
 // lanes 0..2 of the calling warp replay x, y, z side by side over one half of the buffer
-__device__ __forceinline__ void ctr_chain(const CtrSmem &sm, int half, int fill, int &cnt, float &M, int coord) {
+// returns how the half was settled (2: one-correction quotient chain, 3: div.rn.f32)
+__device__ __forceinline__ int ctr_chain(const CtrSmem &sm, int half, int fill, int &cnt, float &M, int coord) {
     const float *src = sm.buf[half][coord];
     const float *myrcp = sm.rcp[half];
     bool fast = cnt + fill < (1 << 24) - 1;
@@ -1143,20 +1144,18 @@ __device__ __forceinline__ void ctr_chain(const CtrSmem &sm, int half, int fill,
         if (t < fill) step(v4.x, y4.x, fn + 1.f);
         if (t + 1 < fill) step(v4.y, y4.y, fn + 2.f);
         if (t + 2 < fill) step(v4.z, y4.z, fn + 3.f);
-        if (odd) {
-            M = M0;
-            fast = false;
-        } else {
+        if (!odd) {
             cnt += fill;
+            return 2;
         }
+        M = M0;
     }
-    if (!fast) {
-        for (int t = 0; t < fill; t++) {
-            float v = src[t];
-            cnt++;
-            M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
-        }
+    for (int t = 0; t < fill; t++) {
+        float v = src[t];
+        cnt++;
+        M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
     }
+    return 3;
 }
 
 constexpr int kCtrBigSegment = 8192;  // points
@@ -1164,7 +1163,13 @@ constexpr int kCtrBigSegment = 8192;  // points
 __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const int *__restrict__ clt_seg,
                                               const int *__restrict__ cluster_id, const float *__restrict__ x,
                                               const float *__restrict__ y, const float *__restrict__ z,
-                                              float *__restrict__ center, int *__restrict__ next_cluster, CtrSmem &sm) {
+                                              float *__restrict__ center, int *__restrict__ next_cluster, CtrSmem &sm,
+                                              float *__restrict__ center_head = nullptr, int n_head = 0,
+                                              unsigned long long *__restrict__ stats = nullptr) {
+    // center_head: optional second copy of the first n_head centres (the small-call kernel keeps it next to its result
+    // block so that one read-back carries everything)
+    // stats (profiling runs): [0] (half, coordinate) replays run, [1] of them replayed with div.rn.f32, [2] cycles warp 0
+    // spent replaying, [3] cycles warp 1 spent gathering (summed over all clusters)
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     const int coord = lane < 3 ? lane : 0;
     while (true) {
@@ -1188,23 +1193,34 @@ __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const 
         for (int c = 0; c < nchunks; c++) {
             __syncthreads();                      // half c&1 is complete
             const int fill = sm.m[c & 1];
+            const long long tc0 = stats ? clock64() : 0;
             if (wid == 0) {
-                ctr_chain(sm, c & 1, fill, cnt, M, coord);
+                const int tier = ctr_chain(sm, c & 1, fill, cnt, M, coord);
+                if (stats && lane < 3 && fill > 0) {
+                    atomicAdd(stats, 1ull);
+                    if (tier > 2) atomicAdd(stats + 1, 1ull);
+                }
+                if (stats && lane == 0) atomicAdd(stats + 2, (unsigned long long)(clock64() - tc0));
             } else {
                 gathered += fill;
                 if (c + 1 < nchunks) ctr_gather(sm, (c + 1) & 1, b + (c + 1) * kCtrChunkPts, e, local, gathered, cluster_id, x, y, z);
+                if (stats && threadIdx.x == 32) atomicAdd(stats + 3, (unsigned long long)(clock64() - tc0));
             }
         }
-        if (wid == 0 && lane < 3) center[3 * kk + lane] = M;
+        if (wid == 0 && lane < 3) {
+            center[3 * kk + lane] = M;
+            if (center_head && kk < n_head) center_head[3 * kk + lane] = M;
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
           const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
-          const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster) {
+          const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster,
+          unsigned long long *__restrict__ stats) {
     __shared__ CtrSmem sm;
-    centres_block(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, sm);
+    centres_block(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, sm, nullptr, 0, stats);
 }
 
 // ------------------------------------------------------------------------------------------------

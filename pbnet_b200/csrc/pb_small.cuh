@@ -8,8 +8,13 @@
 //                                   instruction; a ballot is one 32-bit word of the query's adjacency row
 //   P2  parent[u] = smallest-index HP neighbour (first set bit of row & HP mask): a forest that already joins almost
 //       every point of a blob
-//   P3  union-find over the HP graph at WORD granularity: 32 neighbours' parents are compared with the query's root
-//       in one coalesced load; only genuinely foreign neighbours pay a find / union
+//   P3  components of the HP graph.  The P2 forest has only a handful of trees (its roots are the local minima of the
+//       point index: about n / (HP degree + 1) of them), so with <= 64 trees the components are computed on the TREE graph:
+//       every HP point ORs the tree numbers of its HP neighbours into one 64-bit word (byte loads, no atomics on the
+//       neighbours, no pointer chasing), one 64-bit atomicOr per point builds the 64 x 64 tree adjacency, and every block
+//       closes it with Warshall's algorithm in one warp.  More than 64 trees (sparse graphs): union-find at WORD
+//       granularity — 32 neighbours' parents are compared with the query's root in one coalesced load; only genuinely
+//       foreign neighbours pay a find / union
 //   P4  flatten; roots flagged at their (minimum) point index; block-level scan -> raw ids in seed order
 //       (binary.cu:161-166)
 //   P5  labels: HP -> id of its component; border LP -> maximum id over its HP neighbours (binary.cu:206-213); sizes
@@ -31,8 +36,10 @@ namespace cg = cooperative_groups;
 using pb::kFull;
 
 constexpr int kMaxSeg = 32;       // segments per small call
-constexpr int kQB = 8;            // query points per P1 task
+constexpr int kQB = 8;            // query points per P1 task (the select tree of P1 is written for 8)
 constexpr int kThreads = 256;
+constexpr int kTreeMax = 64;     // trees the tree-graph formulation of P3 handles
+constexpr int kCentreHead = 256;  // clusters whose centres travel with the result block
 constexpr int kWPL = 16;           // bitmask words per lane: a segment has at most 32*kWPL words = 16384 points
 
 struct SmallArgs {
@@ -53,6 +60,15 @@ struct SmallArgs {
     int *root0;                   // root of every point in the P2 forest
     unsigned long long *best64;   // P8: per point, min over candidates of (distance bits << 32 | ~index)
     int *seg_of, *parent, *flag, *gid_at, *raw_label, *raw_count, *rep, *keep, *kscan, *clt_seg;
+    int deg_slices;               // P1: slices per query group (0: automatic)
+    int *deg_acc;                 // P1: partial neighbour counts of the sliced form (zero-initialised)
+    int tree_cap;                 // P3 works on the tree graph when the P2 forest has at most this many trees (<= 64; 0: never)
+    int *tslot, *troot, *tcnt;    // tree number of every forest root, root point of every tree, number of trees
+    unsigned char *tidx;          // tree number of every HP point
+    unsigned long long *conn;     // [64] tree adjacency rows (zero-initialised)
+    int *lplist, *lpcnt;          // P7/P8: unlabelled points of every segment (unordered), their number (zero-initialised)
+    float *center_head;           // centres / classes of the first kSmallCentreHead clusters, next to the result block (or null)
+    int *cltsem_head;
     int *scal;                    // [0] err [2] R [3] K [9] centre ticket [16..39] phase time stamps (globaltimer ns, 64-bit)
 };
 
@@ -112,33 +128,47 @@ k_small(SmallArgs a) {
     if (gthread < S) const_cast<int *>(a.call_first)[gthread] = 0;
     // ---------------- P1: adjacency rows + degrees + HP mask + validation -------------------------------------------
     {
+        // task = 8 query points x a slice of the segment's candidate words.  With fewer query groups than warps in the grid
+        // the candidate range of a group is cut into slices (at least four words each) so that the task list fills the grid
+        // about once: the partial counts then meet in deg_acc and a short extra phase applies the HP rule.
         int task0[kMaxSeg + 1];  // first task of every segment
+        int groups = 0;
+        for (int s = 0; s < S; s++) groups += (a.start[s + 1] - a.start[s] + kQB - 1) / kQB;
+        const int want = a.deg_slices > 0 ? a.deg_slices : max(1, nwarp / max(groups, 1));
+        bool sliced = false;
         int nt = 0;
-        for (int s = 0; s < S; s++) task0[s] = nt, nt += (a.start[s + 1] - a.start[s] + kQB - 1) / kQB;
+        for (int s = 0; s < S; s++) {
+            const int W = a.mask_off[s + 1] - a.mask_off[s], nsl = max(1, min(want, W >> 2));
+            sliced |= nsl > 1;
+            task0[s] = nt, nt += ((a.start[s + 1] - a.start[s] + kQB - 1) / kQB) * nsl;
+        }
         task0[S] = nt;
         for (int t = gwarp; t < nt; t += nwarp) {
             int s = 0;
             while (task0[s + 1] <= t) s++;
             const int b = a.start[s], e = a.start[s + 1], W = a.mask_off[s + 1] - a.mask_off[s];
-            const int q0 = b + (t - task0[s]) * kQB;
+            const int nsl = max(1, min(want, W >> 2));
+            const int qg = (t - task0[s]) / nsl, sl = (t - task0[s]) % nsl;
+            const int w0 = (int)(((long long)W * sl) / nsl), w1 = (int)(((long long)W * (sl + 1)) / nsl);
+            const int q0 = b + qg * kQB;
             int cls0 = __ldg(a.sem + b);
             const bool cls_ok = cls0 >= 2 && cls0 <= 19;
             if (!cls_ok) cls0 = 2;
             const float r = a.radius[cls0 - 2];
             const float r2 = __fmul_rn(r, r);                       // binary_cuda_functions.cu:85
             const int minp = a.min_pts[cls0 - 2];
-            if (q0 == b && lane == 0) a.sg.cls[s] = cls0, a.sg.min_pts[s] = minp, a.sg.r2[s] = r2;
-            // validation of my query points (every point is a query exactly once)
+            if (q0 == b && sl == 0 && lane == 0) a.sg.cls[s] = cls0, a.sg.min_pts[s] = minp, a.sg.r2[s] = r2;
+            // validation of my query points (every point is a query of exactly one slice-0 task)
             float qx[kQB], qy[kQB], qz[kQB];
-            int cnt[kQB];
+            int mycnt = 0;   // lane j < 8: neighbours of query j found in this slice
+            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
             int err = cls_ok ? 0 : pb::kErrSem;
 #pragma unroll
             for (int j = 0; j < kQB; j++) {
                 int u = min(q0 + j, e - 1);
                 qx[j] = __ldg(a.x + u), qy[j] = __ldg(a.y + u), qz[j] = __ldg(a.z + u);
-                cnt[j] = 0;
             }
-            if (lane < kQB && q0 + lane < e) {
+            if (sl == 0 && lane < kQB && q0 + lane < e) {
                 int u = q0 + lane, c = a.sem[u];
                 a.seg_of[u] = s;
                 if (c < 2 || c > 19) err |= pb::kErrSem;
@@ -154,11 +184,11 @@ k_small(SmallArgs a) {
             float nx[PF], ny[PF], nz[PF];
 #pragma unroll
             for (int q = 0; q < PF; q++) {
-                int v = b + q * 32 + lane;
+                int v = b + (w0 + q) * 32 + lane;
                 nx[q] = ny[q] = nz[q] = 0.f;
                 if (v < e) nx[q] = __ldg(a.x + v), ny[q] = __ldg(a.y + v), nz[q] = __ldg(a.z + v);
             }
-            for (int vb0 = 0; vb0 < W; vb0 += PF) {
+            for (int vb0 = w0; vb0 < w1; vb0 += PF) {
                 float cx[PF], cy[PF], cz[PF];
 #pragma unroll
                 for (int q = 0; q < PF; q++) {
@@ -169,28 +199,47 @@ k_small(SmallArgs a) {
 #pragma unroll
                 for (int q = 0; q < PF; q++) {
                     const int vb = vb0 + q;
-                    if (vb >= W) break;
+                    if (vb >= w1) break;
                     const bool valid = b + vb * 32 + lane < e;
-                    unsigned mine = 0u;
+                    unsigned wv[kQB];
 #pragma unroll
-                    for (int j = 0; j < kQB; j++) {
-                        bool hit = valid && pb::sqd(qx[j], qy[j], qz[j], cx[q], cy[q], cz[q]) <= r2;
-                        unsigned wv = __ballot_sync(kFull, hit);
-                        cnt[j] += __popc(wv);
-                        if (lane == j) mine = wv;
-                    }
+                    for (int j = 0; j < kQB; j++)
+                        wv[j] = __ballot_sync(kFull, valid && pb::sqd(qx[j], qy[j], qz[j], cx[q], cy[q], cz[q]) <= r2);
+                    // lane j < 8 keeps the word of query j: a 3-level select on the lane's bits (predicates set once per
+                    // task), ONE population count per word for all eight queries (POPC is a quarter-rate instruction)
+                    const unsigned s0 = b0 ? wv[1] : wv[0], s1 = b0 ? wv[3] : wv[2], s2 = b0 ? wv[5] : wv[4], s3 = b0 ? wv[7] : wv[6];
+                    const unsigned mine = b2 ? (b1 ? s3 : s2) : (b1 ? s1 : s0);
+                    mycnt += __popc(mine);
                     if (lane < kQB && q0 + lane < e) row[(long long)lane * W + vb] = mine;
                 }
             }
-            // degree (self excluded by position, binary_cuda_functions.cu:88), HP rule (:175-186)
-            int mycnt = 0;
-#pragma unroll
-            for (int j = 0; j < kQB; j++)
-                if (lane == j) mycnt = cnt[j];
             if (lane < kQB && q0 + lane < e) {
-                int u = q0 + lane, d = mycnt - 1;
-                a.degree[u] = d;
-                if (d >= minp) atomicOr(a.hpmask + a.mask_off[s] + ((u - b) >> 5), 1u << ((u - b) & 31));
+                int u = q0 + lane;
+                if (sliced) {
+                    if (mycnt) atomicAdd(a.deg_acc + u, mycnt);
+                } else {
+                    // degree (self excluded by position, binary_cuda_functions.cu:88), HP rule (:175-186)
+                    int d = mycnt - 1;
+                    a.degree[u] = d;
+                    if (d >= minp) atomicOr(a.hpmask + a.mask_off[s] + ((u - b) >> 5), 1u << ((u - b) & 31));
+                }
+            }
+        }
+        if (sliced) {   // uniform over the grid
+            grid.sync();
+            const int words = a.mask_off[S];
+            for (int wd = gwarp; wd < words; wd += nwarp) {
+                int s = 0;
+                while (a.mask_off[s + 1] <= wd) s++;
+                const int u = a.start[s] + (wd - a.mask_off[s]) * 32 + lane;
+                bool hp = false;
+                if (u < a.start[s + 1]) {
+                    const int d = __ldcg(a.deg_acc + u) - 1;
+                    a.degree[u] = d;
+                    hp = d >= a.sg.min_pts[s];
+                }
+                const unsigned m = __ballot_sync(kFull, hp);
+                if (lane == 0) a.hpmask[wd] = m;
             }
         }
     }
@@ -232,10 +281,54 @@ k_small(SmallArgs a) {
                 if (p == r) break;
                 r = p;
             }
+            if (r == u) {   // a tree root: number it (in arrival order; the canonical root of a component is a minimum over points)
+                int slot = atomicAdd(a.tcnt, 1);
+                if (slot < kTreeMax) a.troot[slot] = u;
+                a.tslot[u] = slot;
+            }
         }
         a.root0[u] = r;
     }
     grid.sync();
+    const int T = __ldcg(a.tcnt);
+    const bool tree_graph = T <= a.tree_cap;   // uniform over the grid
+    if (tree_graph) {
+        // b') tree number of every HP point
+        for (int u = gthread; u < n; u += nthread) {
+            int s = a.seg_of[u];
+            const int lu = u - a.start[s];
+            if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) a.tidx[u] = (unsigned char)a.tslot[a.root0[u]];
+        }
+        grid.sync();
+        // c') one warp per HP point: lane l walks the words l, l+32, .. of the point's row (smaller indices only: every edge
+        //     once) and ORs the tree numbers of the HP neighbours it finds into a 64-bit set
+        for (int u = gwarp; u < n; u += nwarp) {
+            int s = a.seg_of[u];
+            const int b = a.start[s], W = a.mask_off[s + 1] - a.mask_off[s], lu = u - b;
+            const unsigned *hm = a.hpmask + a.mask_off[s];
+            if (!((hm[lu >> 5] >> (lu & 31)) & 1u)) continue;
+            const unsigned *row = a.adj + a.adj_off[s] + (long long)lu * W;
+            const int nwords = (lu >> 5) + 1;
+            const unsigned char *tix = a.tidx + b;
+            unsigned long long acc = 0ull;
+            for (int vb = lane; vb < nwords; vb += 32) {
+                unsigned w = row[vb] & hm[vb];
+                if (vb == (lu >> 5)) w &= (1u << (lu & 31)) - 1u;
+                const unsigned char *tw = tix + vb * 32;
+                while (w) {   // two neighbours per trip: the byte loads are independent
+                    int k0 = __ffs(w) - 1;
+                    w &= w - 1;
+                    int k1 = w ? __ffs(w) - 1 : k0;
+                    w &= w - 1;
+                    acc |= (1ull << tw[k0]) | (1ull << tw[k1]);
+                }
+            }
+            unsigned lo = __reduce_or_sync(kFull, (unsigned)acc), hi = __reduce_or_sync(kFull, (unsigned)(acc >> 32));
+            const int mine = a.tidx[u];
+            unsigned long long set = (((unsigned long long)hi << 32) | lo) & ~(1ull << mine);
+            if (lane == 0 && set) atomicOr(a.conn + mine, set);
+        }
+    } else {
     for (int u = gthread; u < n; u += nthread) a.parent[u] = a.root0[u];
     grid.sync();
     for (int u = gwarp; u < n; u += nwarp) {       // b)
@@ -291,16 +384,56 @@ k_small(SmallArgs a) {
             }
         }
     }
+    }
     grid.sync();
     stamp(a, 3);
     // ---------------- P4a: flatten, flag the roots (root = minimum index of its component) ---------------------------
-    for (int u = gthread; u < n; u += nthread) {
-        int s = a.seg_of[u];
-        const int lu = u - a.start[s];
-        if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) {
-            int rt = pb::uf_find(a.parent, u);
-            __stcg(a.parent + u, rt);
-            if (rt == u) a.flag[u] = 1;
+    if (tree_graph) {
+        // every block closes the tree graph on its own (64 rows of 64 bits: lanes hold rows l and l + 32): symmetrise,
+        // Warshall in place, then the component's canonical root = the smallest root point among its trees
+        __shared__ int s_comp_root[kTreeMax];
+        if (threadIdx.x < 32) {
+            unsigned long long r0 = lane < T ? __ldcg(a.conn + lane) : 0ull, r1 = lane + 32 < T ? __ldcg(a.conn + lane + 32) : 0ull;
+            const int pt0 = lane < T ? __ldcg(a.troot + lane) : 0x7fffffff, pt1 = lane + 32 < T ? __ldcg(a.troot + lane + 32) : 0x7fffffff;
+            unsigned long long c0 = 1ull << lane, c1 = 1ull << (lane + 32);
+            for (int k = 0; k < T; k++) {   // column k of the transpose: bit (my row) of row k
+                unsigned long long rk = __shfl_sync(kFull, k < 32 ? r0 : r1, k & 31);
+                if ((rk >> lane) & 1ull) c0 |= 1ull << k;
+                if ((rk >> (lane + 32)) & 1ull) c1 |= 1ull << k;
+            }
+            r0 |= c0, r1 |= c1;
+            for (int k = 0; k < T; k++) {
+                unsigned long long rk = __shfl_sync(kFull, k < 32 ? r0 : r1, k & 31);
+                if ((r0 >> k) & 1ull) r0 |= rk;
+                if ((r1 >> k) & 1ull) r1 |= rk;
+            }
+            int m0 = 0x7fffffff, m1 = 0x7fffffff;
+            for (int k = 0; k < T; k++) {
+                int pk = __shfl_sync(kFull, k < 32 ? pt0 : pt1, k & 31);
+                if ((r0 >> k) & 1ull) m0 = min(m0, pk);
+                if ((r1 >> k) & 1ull) m1 = min(m1, pk);
+            }
+            s_comp_root[lane] = m0, s_comp_root[lane + 32] = m1;
+        }
+        __syncthreads();
+        for (int u = gthread; u < n; u += nthread) {
+            int s = a.seg_of[u];
+            const int lu = u - a.start[s];
+            if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) {
+                int rt = s_comp_root[a.tidx[u]];
+                __stcg(a.parent + u, rt);
+                if (rt == u) a.flag[u] = 1;
+            }
+        }
+    } else {
+        for (int u = gthread; u < n; u += nthread) {
+            int s = a.seg_of[u];
+            const int lu = u - a.start[s];
+            if ((a.hpmask[a.mask_off[s] + (lu >> 5)] >> (lu & 31)) & 1u) {
+                int rt = pb::uf_find(a.parent, u);
+                __stcg(a.parent + u, rt);
+                if (rt == u) a.flag[u] = 1;
+            }
         }
     }
     grid.sync();
@@ -369,7 +502,10 @@ k_small(SmallArgs a) {
                 if (gi >= 0 && a.keep[gi]) {
                     int kk = a.kscan[gi];
                     id = kk - a.sg.id_base[s];
-                    if (a.rep[gi] == u) a.clt_sem[kk] = a.sg.cls[s], a.clt_seg[kk] = s;
+                    if (a.rep[gi] == u) {
+                        a.clt_sem[kk] = a.sg.cls[s], a.clt_seg[kk] = s;
+                        if (a.cltsem_head && kk < kCentreHead) a.cltsem_head[kk] = a.sg.cls[s];
+                    }
                     lab = true;
                 }
                 a.cluster_id[u] = id;
@@ -377,47 +513,56 @@ k_small(SmallArgs a) {
             }
             unsigned m = __ballot_sync(kFull, lab);
             if (lane == 0) a.labmask[wd] = m;
+            // the unlabelled points of a segment that has clusters are the 1-NN queries of P8: appended to the segment's
+            // list (the order of the list does not matter: every query is answered on its own)
+            unsigned q = __ballot_sync(kFull, u < a.start[s + 1] && !lab);
+            if (q && a.assign_lp && a.sg.cluster_num[s] > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(a.lpcnt + s, __popc(q));
+                base = __shfl_sync(kFull, base, 0);
+                if ((q >> lane) & 1u) a.lplist[a.start[s] + base + __popc(q & ((1u << lane) - 1u))] = u;
+            }
         }
     }
     grid.sync();
     stamp(a, 8);
     // ---------------- P8: exact 1-NN of the unlabelled points (original coordinates) ----------------------------------
-    // task = (32 consecutive points as queries, one per lane) x (a slice of 512 candidates staged through shared memory
-    // 32 at a time); a lane walks its candidates in ascending order with '<=' (ties -> largest index, :282); slices merge
-    // through atomicMin on (distance bits << 32 | ~index): smallest distance first, then the largest index.
+    // task = (32 queries of the segment's list, one per lane) x (a slice of the segment's candidates, staged through shared
+    // memory 32 at a time); a lane walks its candidates in ascending order with '<=' (ties -> largest index, :282); slices
+    // merge through atomicMin on (distance bits << 32 | ~index): smallest distance first, then the largest index.  The
+    // slices are cut so that the task list fills the grid about once.
     if (a.assign_lp) {
-        constexpr int kSliceWords = 16;
-        float *stage = &s_ctr.buf[0][0][0] + (threadIdx.x >> 5) * 96;   // 32 candidates x 3 coordinates per warp
+        float4 *stage = reinterpret_cast<float4 *>(&s_ctr.buf[0][0][0]) + (threadIdx.x >> 5) * 32;   // 32 candidates per warp
         int t0[kMaxSeg + 1];
-        int nt = 0;
+        int nt = 0, groups = 0;
+        for (int s = 0; s < S; s++) groups += (__ldcg(a.lpcnt + s) + 31) >> 5;
+        const int want = groups > 0 ? max(1, nwarp / groups) : 1;   // slices per query group
         for (int s = 0; s < S; s++) {
             const int W = a.mask_off[s + 1] - a.mask_off[s];
             t0[s] = nt;
-            if (a.sg.cluster_num[s] > 0) nt += W * ((W + kSliceWords - 1) / kSliceWords);
+            nt += ((__ldcg(a.lpcnt + s) + 31) >> 5) * min(want, (W + 1) >> 1);
         }
         t0[S] = nt;
         for (int t = gwarp; t < nt; t += nwarp) {
             int s = 0;
             while (t0[s + 1] <= t) s++;
             const int b = a.start[s], e = a.start[s + 1], W = a.mask_off[s + 1] - a.mask_off[s];
-            const int nsl = (W + kSliceWords - 1) / kSliceWords;
-            const int qw = (t - t0[s]) / nsl, sl = (t - t0[s]) % nsl;
+            const int nsl = min(want, (W + 1) >> 1), nq = __ldcg(a.lpcnt + s);
+            const int qg = (t - t0[s]) / nsl, sl = (t - t0[s]) % nsl;
             const unsigned *lm = a.labmask + a.mask_off[s];
-            const int u = b + qw * 32 + lane;
-            const bool active = u < e && !((lm[qw] >> lane) & 1u);   // unlabelled point of a segment that has clusters
-            if (!__any_sync(kFull, active)) continue;
-            float px = 0.f, py = 0.f, pz = 0.f;
-            if (active) px = a.xo[u], py = a.yo[u], pz = a.zo[u];
+            const bool active = qg * 32 + lane < nq;
+            const int u = active ? __ldcg(a.lplist + b + qg * 32 + lane) : b;
+            const float px = a.xo[u], py = a.yo[u], pz = a.zo[u];
             float bestD = __int_as_float(0x7f800000);
             int bestI = -1;
-            const int cw1 = min(W, (sl + 1) * kSliceWords);
-            int cw = sl * kSliceWords;
+            const int cw1 = (int)(((long long)W * (sl + 1)) / nsl);
+            int cw = (int)(((long long)W * sl) / nsl);
             int vn = min(b + cw * 32 + lane, e - 1);
             float nx = a.xo[vn], ny = a.yo[vn], nz = a.zo[vn];
             for (; cw < cw1; cw++) {
                 const unsigned lw = lm[cw];
                 __syncwarp();
-                stage[lane] = nx, stage[32 + lane] = ny, stage[64 + lane] = nz;
+                stage[lane] = make_float4(nx, ny, nz, 0.f);
                 __syncwarp();
                 if (cw + 1 < cw1) {
                     vn = min(b + (cw + 1) * 32 + lane, e - 1);
@@ -426,7 +571,8 @@ k_small(SmallArgs a) {
                 if (!lw) continue;
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
-                    float D = pb::sqd(px, py, pz, stage[k], stage[32 + k], stage[64 + k]);
+                    const float4 c = stage[k];
+                    float D = pb::sqd(px, py, pz, c.x, c.y, c.z);
                     if (((lw >> k) & 1u) && D <= bestD) bestD = D, bestI = b + cw * 32 + k;
                 }
             }
@@ -442,7 +588,7 @@ k_small(SmallArgs a) {
     grid.sync();
     stamp(a, 9);
     // ---------------- P9: centres --------------------------------------------------------------------------------------
-    pb::centres_block(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_ctr);
+    pb::centres_block(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_ctr, a.center_head, kCentreHead);
     stamp(a, 10);   // end of block 0's own centres (the last phase is not followed by a barrier)
 }
 

@@ -254,3 +254,38 @@ def test_launch_count_of_a_dropin_call_stays_lean():
     H.run_cuda(ctx, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], device=True)
     assert 1 <= ctx.last_launch_count <= 30, ctx.last_launch_count
     ctx.close()
+
+
+@pytest.mark.parametrize("env", [{"PB_SMALL_TREES": "0"}, {"PB_SMALL_TREES": "3"}, {"PB_SMALL_SLICES": "1"},
+                                 {"PB_SMALL_SLICES": "5", "PB_SMALL_TREES": "64"}],
+                         ids=["union-find", "tree-cap-3", "unsliced", "five-slices"])
+def test_small_call_kernel_variants(monkeypatch, env):
+    """Every formulation inside the small-call kernel gives the same bits: P3 on the tree graph (<= 64 trees) or as the
+    word-level union-find (PB_SMALL_TREES caps the tree count that takes the tree graph), P1 with its candidate range in
+    one piece or in slices (PB_SMALL_SLICES) — golden vectors of the compiled reference and per-class calls of a scene
+    against the oracle."""
+    from oracle import pb_oracle as po
+    from pbnet_b200 import scenes
+    from pbnet_b200.cluster import Context
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c2 = Context(0)
+    try:
+        c2.set_small_calls(1)
+        took = 0
+        for path in H.golden_files():
+            d, ref = H.load_golden(path)
+            got = H.run_cuda(c2, d["xyz_shift"], d["xyz_orig"], d["sem"], d["seg_counts"], d["radius"], d["min_pts"], 0.05,
+                             bool(d["nv_flag"]))
+            took += c2.counters()["small_path"]
+            assert H.diff_report(got, ref) == [], path
+        for seed, npts, copies in ((51, 40000, 1), (52, 30000, 3)):
+            sc = scenes.make_scene(seed, npts)
+            for c in scenes.class_calls(sc, copies):
+                want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], H.R18, H.M18)
+                got = H.run_cuda(c2, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"])
+                took += c2.counters()["small_path"]
+                assert H.diff_report(got, want) == [], f"class {c['sem_id']} seed {seed}"
+        assert took > 10
+    finally:
+        c2.close()
