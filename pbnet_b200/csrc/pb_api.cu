@@ -98,6 +98,7 @@ struct pb_ctx {
     size_t h_stage_cap = 0;
     int coop_blocks_per_sm = 0, sm_count = 0;
     int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
+    bool deg_tma = false;  // PB_DEG_TMA=1: candidate stream of the symmetric k_degree staged through shared memory by cp.async.bulk (experiment)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxSlots] = {};
     cudaStream_t copy_st = nullptr;  // host outputs that are final early (the degrees) leave on their own stream
@@ -206,6 +207,8 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         if (stc) ctx->small_tree_cap = std::max(0, std::min(atoi(stc), (int)pbsm::kTreeMax));
         const char *dsy = getenv("PB_DEG_SYM");
         if (dsy) ctx->deg_sym = dsy[0] != '0';
+        const char *dtm = getenv("PB_DEG_TMA");
+        if (dtm) ctx->deg_tma = dtm[0] != '0';
         const char *dp = getenv("PB_DEG_PHASED");
         if (dp) ctx->deg_phased = dp[0] != '0';
         const char *ed = getenv("PB_EARLY_D2H");
@@ -760,6 +763,16 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         // symmetric counting: candidates' degrees are accumulated with RED, so the array starts at zero
         if (nslice > 1 || ctx->deg_sym) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
         const size_t dsm = nslice == 1 ? ctx->deg_smem : 0;
+        if (ctx->deg_sym && ctx->deg_tma && nslice == 1) {
+            static bool carveout_set = false;   // nine resident CTAs need 9 x 13.5 KB of shared memory
+            if (!carveout_set) {
+                cudaFuncSetAttribute(pb::k_degree_tma<9>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+                cudaFuncSetAttribute(pb::k_degree_tma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+                carveout_set = true;
+            }
+            if (ctx->deg_minb == 9) pb::k_degree_tma<9><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
+            else pb::k_degree_tma<8><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
+        } else
         if (!ctx->deg_sym) pb::k_degree<false, PB_DEG_MINB><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
         else if (ctx->deg_minb == 9) pb::k_degree<true, 9><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
         else pb::k_degree<true, 8><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);

@@ -412,13 +412,159 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
     }
 }
 
+// ---- round 2, experiment: the candidate stream staged through shared memory by the TMA unit --------------
+// Every warp owns a ring of kTmaStages x kTmaBatch candidates (16 B each) and one mbarrier per stage.  Lane 0 issues
+// `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` for the next batches of the group's candidate ranges
+// while the warp tests the current one out of shared memory (LDS.128 broadcast instead of an LDG that may miss L1); ranges
+// shorter than kTmaMin candidates keep the direct loads.  PB_DEG_TMA=1 selects it (large problems, symmetric counting).
+constexpr int kTmaBatch = 64, kTmaStages = 3, kTmaMin = 16;
+struct alignas(128) TmaRing {
+    float4 buf[kTmaStages][kTmaBatch];
+    unsigned long long bar[kTmaStages];
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// symmetric counting of one group, candidates through the warp's TMA ring.  `issued` / `consumed` count the batches this
+// warp has sent / tested since the kernel began (stage = count % kTmaStages, parity = (count / kTmaStages) & 1).
+template <int P>
+__device__ __forceinline__ void degree_group_tma(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
+                                                 int *__restrict__ deg_sorted, TmaRing &ring, unsigned &issued,
+                                                 unsigned &consumed) {
+    static_assert(2 * P * 32 <= 255, "a candidate's warp-wide hit count must fit one byte of the packed register");
+    const float4 *__restrict__ pts4 = g.pts4;
+    const int base = g0 & ~1;
+    const float qnan = __int_as_float(0x7fc00000);
+    unsigned long long qx[P], qy[P], qz[P];
+    int cnt[2 * P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        int i = base + 64 * p + 2 * lane;
+        const bool in0 = i >= g0 && i < g0 + total, in1 = i + 1 < g0 + total;
+        if (i >= g0 + total) i = base;
+        qx[p] = ldg_pair(g.sx + i), qy[p] = ldg_pair(g.sy + i), qz[p] = ldg_pair(g.sz + i);
+        float x0, x1;
+        unpack2(qx[p], x0, x1);
+        qx[p] = pack2(in0 ? x0 : qnan, in1 ? x1 : qnan);
+        cnt[2 * p] = cnt[2 * p + 1] = 0;
+    }
+    unsigned nprev = 0;
+    const unsigned sh = 8 * (lane & 3), lmask = lane < 4 ? 0xffu : 0u;
+    int *const dq = deg_sorted + lane;
+    // four candidates q0..q3 at sorted positions j..j+3: tests, byte-packed credit to the candidates (see degree_group)
+    auto quad = [&](float4 q0, float4 q1, float4 q2, float4 q3, int j) {
+        test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+        const unsigned t0 = (unsigned)slot_sum<P>(cnt);
+        test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+        const unsigned t1 = (unsigned)slot_sum<P>(cnt);
+        test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+        const unsigned t2 = (unsigned)slot_sum<P>(cnt);
+        test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+        const unsigned t3 = (unsigned)slot_sum<P>(cnt);
+        const unsigned packed = t0 * 0xffffff01u + t1 * 0xffff0100u + t2 * 0xff010000u + t3 * 0x01000000u + nprev;
+        nprev = 0u - t3;
+        red_add_nz(dq + j, (warp_sum(packed) >> sh) & lmask);
+    };
+    auto single = [&](float4 q, int jj) {
+        test_candidate<P>(qx, qy, qz, q, r2, cnt);
+        const unsigned t = (unsigned)slot_sum<P>(cnt);
+        const unsigned hits = warp_sum(t + nprev);
+        nprev = 0u - t;
+        red_add_nz(deg_sorted + jj, lane == 0 ? hits : 0u);
+    };
+    // ---- the later candidates (ranges 4..8): long ranges through the ring, short ones directly
+    // issue cursor (ik, ib, ie) runs ahead of the test cursor (ck, cb, ce); both skip ranges shorter than kTmaMin
+    int ik = 3, ib = 0, ie = 0;
+    auto issue = [&]() {   // uniform; sends at most one batch
+        while (ik < kRuns && ib >= ie) {
+            ik++;
+            if (ik < kRuns) {
+                ib = __shfl_sync(kFull, jb, ik), ie = __shfl_sync(kFull, je, ik);
+                if (ie - ib < kTmaMin) ib = ie;
+            }
+        }
+        if (ik >= kRuns) return;
+        const int nb = min(kTmaBatch, ie - ib);
+        const unsigned st = issued % kTmaStages;
+        if (lane == 0) tma_load_1d(&ring.buf[st][0], pts4 + ib, (unsigned)nb * 16u, &ring.bar[st]);
+        ib += nb;
+        issued++;
+    };
+#pragma unroll 1
+    for (int s = 0; s < kTmaStages - 1; s++) issue();
+#pragma unroll 1
+    for (int k = 4; k < kRuns; k++) {
+        const int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
+        if (e - b < kTmaMin) {
+            int j = b;
+            for (; j + 4 <= e; j += 4) quad(__ldg(pts4 + j), __ldg(pts4 + j + 1), __ldg(pts4 + j + 2), __ldg(pts4 + j + 3), j);
+            for (; j < e; j++) single(__ldg(pts4 + j), j);
+            continue;
+        }
+#pragma unroll 1
+        for (int j0 = b; j0 < e; j0 += kTmaBatch) {
+            const int nb = min(kTmaBatch, e - j0);
+            const unsigned st = consumed % kTmaStages;
+            issue();                                           // keeps kTmaStages - 1 batches in flight behind this one
+            mbar_wait(&ring.bar[st], (consumed / kTmaStages) & 1u);
+            const float4 *cb = ring.buf[st];
+            int i = 0;
+            for (; i + 4 <= nb; i += 4) quad(cb[i], cb[i + 1], cb[i + 2], cb[i + 3], j0 + i);
+            for (; i < nb; i++) single(cb[i], j0 + i);
+            consumed++;
+            __syncwarp();                                      // every lane has read the stage before it is sent again
+        }
+    }
+    // ---- range 9: the group itself, one-sided
+    {
+        const int b = __shfl_sync(kFull, jb, kRuns), e = __shfl_sync(kFull, je, kRuns);
+        int j = b;
+        for (; j + 4 <= e; j += 4) {
+            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+            test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+            test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+            test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+            test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+        }
+        for (; j < e; j++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + j), r2, cnt);
+    }
+#pragma unroll
+    for (int s = 0; s < 2 * P; s++) {
+        int i = base + 64 * (s >> 1) + 2 * lane + (s & 1);
+        if (i >= g0 && i < g0 + total) {
+            const int d = cnt[s] - 1;  // binary_cuda_functions.cu:88  ans - 1 (self)
+            if (d) atomicAdd(deg_sorted + i, d);
+        }
+    }
+}
+
 // one 128-point window; `warp` = window index, (slice, nslice) = this warp's share of the window (small problems)
 // phase: -1 = every window; 0 = only the HEAVY windows (at most two groups: the dense blobs, 128 queries against a long
 // candidate stream), 1 = only the others.  The grid runs phase 0 first, so the kernel drains on short windows.
-template <bool SYM>
+template <bool SYM, bool TMA = false>
 __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const Grid &g, int *__restrict__ deg_sorted,
                                               unsigned long long *__restrict__ n_tests, int warp, int slice, int nslice,
-                                              int phase) {
+                                              int phase, TmaRing *ring = nullptr) {
+    unsigned issued = 0, consumed = 0;   // TMA: batches this warp has sent / tested (one window per warp and launch)
     int lane = lane_id();
     long long base = (long long)warp * kWindow;
     if (base >= n) return;
@@ -489,6 +635,13 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
                 if (SYM) intra += (unsigned long long)total * (unsigned)total;  // the one-sided share
             }
             const int sl = sub, ns = cs;
+            if (TMA) {
+                switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
+                    case 1: degree_group_tma<1>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
+                    case 2: degree_group_tma<2>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
+                    default: degree_group_tma<3>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
+                }
+            } else
             switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
                 case 1: degree_group<1, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
                 case 2: degree_group<2, SYM>(g, pos, total, lane, r2, jb, je, deg_sorted, sl, ns); break;
@@ -516,6 +669,25 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
     const int phase = phased ? (blockIdx.x >= nb ? 1 : 0) : -1;
     const int bx = blockIdx.x - (phase == 1 ? nb : 0);
     degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y, phase);
+}
+
+// the TMA-staged variant (symmetric counting, one warp per window: large problems only)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_degree_tma(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests, int phased) {
+    static_assert(PB_DEG_WINDOW <= 192, "degree_group_tma is instantiated for up to three query pairs per lane");
+    __shared__ TmaRing rings[4];
+    TmaRing &ring = rings[threadIdx.x >> 5];
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; s++) mbar_init(&ring.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int nb = phased ? gridDim.x >> 1 : gridDim.x;
+    const int phase = phased ? (blockIdx.x >= nb ? 1 : 0) : -1;
+    const int bx = blockIdx.x - (phase == 1 ? nb : 0);
+    degree_window<true, true>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, 0, 1, phase, &ring);
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order.  A thread owns kHpPer points (32 consecutive

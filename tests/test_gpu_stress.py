@@ -105,7 +105,7 @@ def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
     seg = np.concatenate([c["seg_counts"] for c in calls])
     csc = np.array([len(c["seg_counts"]) for c in calls], np.int32)
     res = {}
-    old = {k: os.environ.get(k) for k in ("PB_DEG_SYM", "PB_SMALL")}
+    old = {k: os.environ.get(k) for k in ("PB_DEG_SYM", "PB_SMALL", "PB_DEG_TMA", "PB_DEG_SLICES")}
     try:
         os.environ["PB_SMALL"] = "0"
         for sym in ("1", "0"):
@@ -113,6 +113,11 @@ def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
             c = Context(0)
             res[sym] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
             c.close()
+        # the TMA-staged candidate stream (one warp per window: PB_DEG_SLICES=1 switches the window splitting off)
+        os.environ["PB_DEG_SYM"], os.environ["PB_DEG_TMA"], os.environ["PB_DEG_SLICES"] = "1", "1", "1"
+        c = Context(0)
+        res["tma"] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
+        c.close()
     finally:
         for k, v in old.items():
             if v is None:
@@ -120,4 +125,5 @@ def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
             else:
                 os.environ[k] = v
     assert H.diff_report(res["1"], res["0"]) == []
+    assert H.diff_report(res["tma"], res["0"]) == []
     assert int(res["1"]["degree"].sum()) > 0
