@@ -19,6 +19,9 @@
 #include "pb_kernels.cuh"
 #include "pb_fused.cuh"
 #include "pb_small.cuh"
+#ifndef PB_TMA_CARVEOUT
+#define PB_TMA_CARVEOUT 60   // per cent of the SM's 228 KB kept as shared memory for k_degree_tma (nine CTAs x 13.5 KB)
+#endif
 
 namespace {
 
@@ -98,7 +101,7 @@ struct pb_ctx {
     size_t h_stage_cap = 0;
     int coop_blocks_per_sm = 0, sm_count = 0;
     int deg_minb = 9;      // PB_DEG_MINB_SYM: resident CTAs per SM the symmetric k_degree is compiled for (8 = 64 registers, 9 = 56 with spills)
-    bool deg_tma = false;  // PB_DEG_TMA=1: candidate stream of the symmetric k_degree staged through shared memory by cp.async.bulk (experiment)
+    bool deg_tma = true;   // PB_DEG_TMA=0: the symmetric k_degree reads its candidates with direct loads instead of the TMA-staged ring (A/B runs)
     bool deg_sym = true;   // PB_DEG_SYM=0: one-sided neighbour counting (every ordered pair tested; the round-1 formulation, kept for A/B runs)
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxSlots] = {};
     cudaStream_t copy_st = nullptr;  // host outputs that are final early (the degrees) leave on their own stream
@@ -763,11 +766,11 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         // symmetric counting: candidates' degrees are accumulated with RED, so the array starts at zero
         if (nslice > 1 || ctx->deg_sym) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
         const size_t dsm = nslice == 1 ? ctx->deg_smem : 0;
-        if (ctx->deg_sym && ctx->deg_tma && nslice == 1) {
+        if (ctx->deg_sym && ctx->deg_tma && nslice <= 12) {   // measured: the ring pays from ~1 M points (27 k-point call: 88 us direct, 110 us staged)
             static bool carveout_set = false;   // nine resident CTAs need 9 x 13.5 KB of shared memory
             if (!carveout_set) {
-                cudaFuncSetAttribute(pb::k_degree_tma<9>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
-                cudaFuncSetAttribute(pb::k_degree_tma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+                cudaFuncSetAttribute(pb::k_degree_tma<9>, cudaFuncAttributePreferredSharedMemoryCarveout, PB_TMA_CARVEOUT);
+                cudaFuncSetAttribute(pb::k_degree_tma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, PB_TMA_CARVEOUT);
                 carveout_set = true;
             }
             if (ctx->deg_minb == 9) pb::k_degree_tma<9><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);

@@ -416,8 +416,17 @@ __device__ __forceinline__ void degree_group(const Grid &g, int g0, int total, i
 // Every warp owns a ring of kTmaStages x kTmaBatch candidates (16 B each) and one mbarrier per stage.  Lane 0 issues
 // `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` for the next batches of the group's candidate ranges
 // while the warp tests the current one out of shared memory (LDS.128 broadcast instead of an LDG that may miss L1); ranges
-// shorter than kTmaMin candidates keep the direct loads.  PB_DEG_TMA=1 selects it (large problems, symmetric counting).
-constexpr int kTmaBatch = 64, kTmaStages = 3, kTmaMin = 16;
+// shorter than kTmaMin candidates keep the direct loads.  The default for symmetric counting (PB_DEG_TMA=0: direct loads).
+#ifndef PB_TMA_BATCH
+#define PB_TMA_BATCH 64
+#endif
+#ifndef PB_TMA_STAGES
+#define PB_TMA_STAGES 3
+#endif
+#ifndef PB_TMA_MIN
+#define PB_TMA_MIN 16
+#endif
+constexpr int kTmaBatch = PB_TMA_BATCH, kTmaStages = PB_TMA_STAGES, kTmaMin = PB_TMA_MIN;
 struct alignas(128) TmaRing {
     float4 buf[kTmaStages][kTmaBatch];
     unsigned long long bar[kTmaStages];
@@ -449,7 +458,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 template <int P>
 __device__ __forceinline__ void degree_group_tma(const Grid &g, int g0, int total, int lane, float r2, int jb, int je,
                                                  int *__restrict__ deg_sorted, TmaRing &ring, unsigned &issued,
-                                                 unsigned &consumed) {
+                                                 unsigned &consumed, int slice, int nslice) {
+    // (slice, nslice): this warp's share of the group's candidate stream on small problems — whole batches of the long ranges
+    // and quads of the short ones are dealt round-robin to the nslice warps that share the window
     static_assert(2 * P * 32 <= 255, "a candidate's warp-wide hit count must fit one byte of the packed register");
     const float4 *__restrict__ pts4 = g.pts4;
     const int base = g0 & ~1;
@@ -499,14 +510,14 @@ __device__ __forceinline__ void degree_group_tma(const Grid &g, int g0, int tota
             ik++;
             if (ik < kRuns) {
                 ib = __shfl_sync(kFull, jb, ik), ie = __shfl_sync(kFull, je, ik);
-                if (ie - ib < kTmaMin) ib = ie;
+                ib = ie - ib < kTmaMin ? ie : ib + kTmaBatch * slice;
             }
         }
         if (ik >= kRuns) return;
         const int nb = min(kTmaBatch, ie - ib);
         const unsigned st = issued % kTmaStages;
         if (lane == 0) tma_load_1d(&ring.buf[st][0], pts4 + ib, (unsigned)nb * 16u, &ring.bar[st]);
-        ib += nb;
+        ib += kTmaBatch * nslice;
         issued++;
     };
 #pragma unroll 1
@@ -515,13 +526,15 @@ __device__ __forceinline__ void degree_group_tma(const Grid &g, int g0, int tota
     for (int k = 4; k < kRuns; k++) {
         const int b = __shfl_sync(kFull, jb, k), e = __shfl_sync(kFull, je, k);
         if (e - b < kTmaMin) {
-            int j = b;
-            for (; j + 4 <= e; j += 4) quad(__ldg(pts4 + j), __ldg(pts4 + j + 1), __ldg(pts4 + j + 2), __ldg(pts4 + j + 3), j);
-            for (; j < e; j++) single(__ldg(pts4 + j), j);
+            for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
+                if (j + 4 <= e) quad(__ldg(pts4 + j), __ldg(pts4 + j + 1), __ldg(pts4 + j + 2), __ldg(pts4 + j + 3), j);
+                else
+                    for (int jj = j; jj < e; jj++) single(__ldg(pts4 + jj), jj);
+            }
             continue;
         }
 #pragma unroll 1
-        for (int j0 = b; j0 < e; j0 += kTmaBatch) {
+        for (int j0 = b + kTmaBatch * slice; j0 < e; j0 += kTmaBatch * nslice) {
             const int nb = min(kTmaBatch, e - j0);
             const unsigned st = consumed % kTmaStages;
             issue();                                           // keeps kTmaStages - 1 batches in flight behind this one
@@ -537,21 +550,23 @@ __device__ __forceinline__ void degree_group_tma(const Grid &g, int g0, int tota
     // ---- range 9: the group itself, one-sided
     {
         const int b = __shfl_sync(kFull, jb, kRuns), e = __shfl_sync(kFull, je, kRuns);
-        int j = b;
-        for (; j + 4 <= e; j += 4) {
-            float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
-            test_candidate<P>(qx, qy, qz, q0, r2, cnt);
-            test_candidate<P>(qx, qy, qz, q1, r2, cnt);
-            test_candidate<P>(qx, qy, qz, q2, r2, cnt);
-            test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+        for (int j = b + 4 * slice; j < e; j += 4 * nslice) {
+            if (j + 4 <= e) {
+                float4 q0 = __ldg(pts4 + j), q1 = __ldg(pts4 + j + 1), q2 = __ldg(pts4 + j + 2), q3 = __ldg(pts4 + j + 3);
+                test_candidate<P>(qx, qy, qz, q0, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q1, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q2, r2, cnt);
+                test_candidate<P>(qx, qy, qz, q3, r2, cnt);
+            } else {
+                for (int jj = j; jj < e; jj++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + jj), r2, cnt);
+            }
         }
-        for (; j < e; j++) test_candidate<P>(qx, qy, qz, __ldg(pts4 + j), r2, cnt);
     }
 #pragma unroll
     for (int s = 0; s < 2 * P; s++) {
         int i = base + 64 * (s >> 1) + 2 * lane + (s & 1);
         if (i >= g0 && i < g0 + total) {
-            const int d = cnt[s] - 1;  // binary_cuda_functions.cu:88  ans - 1 (self)
+            const int d = cnt[s] - (slice == 0 ? 1 : 0);  // binary_cuda_functions.cu:88  ans - 1 (self)
             if (d) atomicAdd(deg_sorted + i, d);
         }
     }
@@ -637,9 +652,9 @@ __device__ __forceinline__ void degree_window(int n, const SegArrays &sg, const 
             const int sl = sub, ns = cs;
             if (TMA) {
                 switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
-                    case 1: degree_group_tma<1>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
-                    case 2: degree_group_tma<2>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
-                    default: degree_group_tma<3>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed); break;
+                    case 1: degree_group_tma<1>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed, sl, ns); break;
+                    case 2: degree_group_tma<2>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed, sl, ns); break;
+                    default: degree_group_tma<3>(g, pos, total, lane, r2, jb, je, deg_sorted, *ring, issued, consumed, sl, ns); break;
                 }
             } else
             switch ((total + (pos & 1) + 63) >> 6) {  // query pairs per lane
@@ -671,7 +686,7 @@ k_degree(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned lon
     degree_window<SYM>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y, phase);
 }
 
-// the TMA-staged variant (symmetric counting, one warp per window: large problems only)
+// the TMA-staged variant of the symmetric counting
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_degree_tma(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned long long *__restrict__ n_tests, int phased) {
@@ -687,7 +702,7 @@ k_degree_tma(int n, SegArrays sg, Grid g, int *__restrict__ deg_sorted, unsigned
     const int nb = phased ? gridDim.x >> 1 : gridDim.x;
     const int phase = phased ? (blockIdx.x >= nb ? 1 : 0) : -1;
     const int bx = blockIdx.x - (phase == 1 ? nb : 0);
-    degree_window<true, true>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, 0, 1, phase, &ring);
+    degree_window<true, true>(n, sg, g, deg_sorted, n_tests, (bx * blockDim.x + threadIdx.x) >> 5, blockIdx.y, gridDim.y, phase, &ring);
 }
 
 // K9  HP rule + per-cell HP statistics + degree scatter to input order.  A thread owns kHpPer points (32 consecutive

@@ -108,16 +108,21 @@ def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
     old = {k: os.environ.get(k) for k in ("PB_DEG_SYM", "PB_SMALL", "PB_DEG_TMA", "PB_DEG_SLICES")}
     try:
         os.environ["PB_SMALL"] = "0"
+        os.environ["PB_DEG_TMA"] = "0"   # candidates by direct loads
         for sym in ("1", "0"):
             os.environ["PB_DEG_SYM"] = sym
             c = Context(0)
             res[sym] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
             c.close()
-        # the TMA-staged candidate stream (one warp per window: PB_DEG_SLICES=1 switches the window splitting off)
-        os.environ["PB_DEG_SYM"], os.environ["PB_DEG_TMA"], os.environ["PB_DEG_SLICES"] = "1", "1", "1"
-        c = Context(0)
-        res["tma"] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
-        c.close()
+        # the TMA-staged candidate stream (the default), with the problem-size dependent window splitting and with one warp
+        # per window (PB_DEG_SLICES=1: the form large problems take)
+        os.environ["PB_DEG_SYM"], os.environ["PB_DEG_TMA"] = "1", "1"
+        for key, slices in (("tma", None), ("tma1", "1")):
+            if slices:
+                os.environ["PB_DEG_SLICES"] = slices
+            c = Context(0)
+            res[key] = H.run_cuda(c, xs, xo, sem, seg, call_seg_counts=csc, device=True)
+            c.close()
     finally:
         for k, v in old.items():
             if v is None:
@@ -126,4 +131,5 @@ def test_symmetric_degree_kernel_equals_one_sided(n_scene, copies):
                 os.environ[k] = v
     assert H.diff_report(res["1"], res["0"]) == []
     assert H.diff_report(res["tma"], res["0"]) == []
+    assert H.diff_report(res["tma1"], res["0"]) == []
     assert int(res["1"]["degree"].sum()) > 0
