@@ -1022,6 +1022,28 @@ k_label(int n, SegArrays sg, Grid g, const float4 *__restrict__ pts4, const int 
                     if (!__any_sync(kFull, pend)) continue;
                     int Bc = fb + l;
                     int b0 = g.fcell_start[Bc], b1 = g.fcell_start[Bc + 1];
+                    const unsigned pm = __ballot_sync(kFull, pend);
+                    if (__popc(pm) <= 4) {
+                        // few LPs wait for this cell (the usual case: border LPs are sparse): the LANES take the cell's
+                        // points, 32 per trip, and the LPs are served one after the other — a lone LP next to a full
+                        // cell costs two trips instead of a serial walk over its ~45 points
+                        for (unsigned m2 = pm; m2; m2 &= m2 - 1) {
+                            const int l2 = __ffs(m2) - 1;
+                            const float lx = __shfl_sync(kFull, p.x, l2), ly = __shfl_sync(kFull, p.y, l2), lz = __shfl_sync(kFull, p.z, l2);
+                            bool hit = false;
+                            for (int j0 = b0; j0 < b1 && !hit; j0 += 32) {
+                                const int j = j0 + lane;
+                                bool h = false;
+                                if (j < b1) {
+                                    float4 q = __ldg(pts4 + j);
+                                    h = (__float_as_int(q.w) & kHpBit) && sqd(lx, ly, lz, q.x, q.y, q.z) <= r2;
+                                }
+                                hit = __any_sync(kFull, h);
+                            }
+                            if (hit && lane == l2) best = gc, pend = false;
+                        }
+                        continue;
+                    }
                     for (int j = b0; j < b1; j++) {
                         float4 q = __ldg(pts4 + j);
                         if (!(__float_as_int(q.w) & kHpBit)) continue;
