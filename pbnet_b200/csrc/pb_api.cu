@@ -766,7 +766,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
         // symmetric counting: candidates' degrees are accumulated with RED, so the array starts at zero
         if (nslice > 1 || ctx->deg_sym) PB_CUDA(cudaMemsetAsync(w.deg_sorted, 0, sizeof(int) * (size_t)n, st));
         const size_t dsm = nslice == 1 ? ctx->deg_smem : 0;
-        if (ctx->deg_sym && ctx->deg_tma && nslice <= 12) {   // measured: the ring pays from ~1 M points (27 k-point call: 88 us direct, 110 us staged)
+        if (ctx->deg_sym && ctx->deg_tma && nslice <= 4) {   // measured: the ring pays from ~2.4 M points (3.6 M: 5.10 -> 4.87 ms; 1.26 M sparse points, 7 warps per window: 0.56 -> 0.68 ms; 27 k-point call: 88 -> 110 us)
             static bool carveout_set = false;   // nine resident CTAs need 9 x 13.5 KB of shared memory
             if (!carveout_set) {
                 cudaFuncSetAttribute(pb::k_degree_tma<9>, cudaFuncAttributePreferredSharedMemoryCarveout, PB_TMA_CARVEOUT);
