@@ -773,8 +773,8 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
                 cudaFuncSetAttribute(pb::k_degree_tma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, PB_TMA_CARVEOUT);
                 carveout_set = true;
             }
-            if (ctx->deg_minb == 9) pb::k_degree_tma<9><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
-            else pb::k_degree_tma<8><<<g, 128, 0, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
+            if (ctx->deg_minb == 9) pb::k_degree_tma<9><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
+            else pb::k_degree_tma<8><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
         } else
         if (!ctx->deg_sym) pb::k_degree<false, PB_DEG_MINB><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
         else if (ctx->deg_minb == 9) pb::k_degree<true, 9><<<g, 128, dsm, st>>>(n, w.sg, grid, w.deg_sorted, cnt, phased);
