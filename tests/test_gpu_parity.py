@@ -181,6 +181,16 @@ def _edge_cases(ctx):
     want = po.oracle_binary_cluster(xs, xo, sem, [len(xs)], H.R18, H.M18)
     got = H.run_cuda(ctx, xs, xo, sem, [len(xs)])
     assert H.diff_report(got, want) == []
+    # a coordinate shared by every member of a cluster (a perfectly flat blob: the centre replay sees exact zero differences
+    # in z from the second member on) next to an ordinary blob, large enough for several replay chunks
+    flat = rng.normal(0, 0.01, size=(3000, 3)).astype(np.float32)
+    flat[:, 2] = np.float32(1.25)
+    blob = (rng.normal(0, 0.01, size=(2500, 3)) + [1.0, 0.0, 0.0]).astype(np.float32)
+    xs = np.concatenate([flat, blob])[rng.permutation(5500)]
+    sem = np.full(len(xs), 5, np.int32)
+    want = po.oracle_binary_cluster(xs, xs, sem, [len(xs)], H.R18, H.M18)
+    got = H.run_cuda(ctx, xs, xs, sem, [len(xs)])
+    assert H.diff_report(got, want) == [] and got["n_clusters"] == 2
     # error behaviour: class out of range, NaN, mixed classes -> error codes, never exit()
     bad = np.full(10, 1, np.int32)
     with pytest.raises(PBError) as ei:
