@@ -648,8 +648,8 @@ def run_stress(args):
         sweep.append({"point": label, "points": run.n, "value": run.n / (ms_step * 1e-3), "ms_per_step": ms_step,
                       "clusters": int(out["n_clusters"]), "launches_per_step": int(launches), "roofline": roof, "roofline_alu": alu,
                       "sum_degree_per_point": counters["sum_deg"] / max(1, run.n), "hp_points": counters["n_hp"],
-                      "centre_replay": {"chunks": counters.get("centre_chunks", 0),
-                                        "chunks_in_safe_mode": counters.get("centre_chunks_safe", 0),
+                      "centre_replay": {"halves": counters.get("centre_halves", 0),
+                                        "replayed_with_div_rn": counters.get("centre_halves_replayed", 0),
                                         "replay_cycles": counters.get("centre_replay_cycles", 0),
                                         "gather_cycles": counters.get("centre_gather_cycles", 0)},
                       "stage_ms": {k: round(v, 3) for k, v in stage.items()}, "verify": ver, "cpu_oracle_points_per_s": cpu_rate})

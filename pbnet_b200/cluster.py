@@ -125,7 +125,7 @@ class Context:
 
     def counters(self) -> dict:
         names = ["pair_tests", "sum_deg", "n_hp", "lp_queries", "cells", "raw_clusters", "chunks", "mixed_mode", "coarse_cells",
-                 "small_path", "intra_tests", "centre_chunks", "centre_chunks_safe",
+                 "small_path", "intra_tests", "centre_halves", "centre_halves_replayed",
                  "centre_replay_cycles", "centre_gather_cycles"]
         return {k: int(self._lib.pb_counter(self._h, i)) for i, k in enumerate(names)}
 

@@ -93,7 +93,6 @@ struct pb_ctx {
                              // warps (measured: one 224 k-point scene 271 us at 16, 211 us at 48, no change up to 512; C4, 1 M points in dense
                              // blobs: k_degree 1.53 ms at 48 (38 % of the SM time idle: whole windows are too coarse a unit), 0.81 at 256,
                              // 0.72 at 512 / 1024; 3.6 M points: 5.13 ms per step at 48, 5.05 at 512; C1 chunks are beyond the range)
-    int ctr_force_fail = 0;    // PB_CTR_FORCE_FAIL=k: every k-th proof of the fast centre replay is declared failed (tests of the restart path)
     int devox_u = 4;           // PB_DEVOX_U: elements per thread of k_devox
     int small_deg_slices = 0;  // PB_SMALL_SLICES: candidate slices per query group in P1 of the small-call kernel (0: automatic)
     int small_tree_cap = pbsm::kTreeMax;  // PB_SMALL_TREES: P3 of the small-call kernel works on the tree graph up to this many trees (0: union-find always)
@@ -203,8 +202,6 @@ extern "C" int pb_create(int device, pb_ctx **out) {
         if (ds && atoi(ds) > 0) ctx->deg_slice_mult = atoi(ds);
         const char *sm = getenv("PB_SMALL");
         ctx->small_mode = sm ? (sm[0] == '0' ? 0 : 1) : -1;
-        const char *cff = getenv("PB_CTR_FORCE_FAIL");
-        if (cff) ctx->ctr_force_fail = std::max(0, atoi(cff));
         const char *du = getenv("PB_DEVOX_U");
         if (du) ctx->devox_u = atoi(du);
         const char *ssl = getenv("PB_SMALL_SLICES");
@@ -859,7 +856,7 @@ int enqueue_rest(pb_ctx *ctx, Work &w, const ChunkIO &io, bool host_io, int assi
     }
     mark();  // CENTRES
     pb::k_centres<<<std::min(gPersist, 148 * 4), 256, 0, st>>>(d_K, w.sg, w.clt_seg, d_cluster_id, dx, dy, dz, io.center_out,
-                                                            w.d_scalars + 9, cnt ? cnt + 4 : nullptr, ctx->ctr_force_fail);
+                                                            w.d_scalars + 9, cnt ? cnt + 4 : nullptr);
     L++;
     mark();  // D2H
     PB_CUDA(cudaMemcpyAsync(io.h_scalars, w.d_scalars, sizeof(int) * 10, cudaMemcpyDeviceToHost, st));
@@ -958,7 +955,7 @@ static int run_small(pb_ctx *ctx, const float *x, const float *y, const float *z
     a.scal = outblk;
     const size_t zero_bytes = reinterpret_cast<char *>(outblk + kSmallHead) - zero_begin;
     a.n = n, a.S = S, a.assign_lp = assign_lp;
-    a.tree_cap = ctx->small_tree_cap, a.deg_slices = ctx->small_deg_slices, a.ctr_force_fail = ctx->ctr_force_fail;
+    a.tree_cap = ctx->small_tree_cap, a.deg_slices = ctx->small_deg_slices;
     for (int i = 0; i < 18; i++) a.radius[i] = radius[i], a.min_pts[i] = min_pts[i], a.thresh[i] = kMeanCount[i] * para_f;
     a.sg.start = d_start, a.call_first = d_callfirst;
     // ---- inputs

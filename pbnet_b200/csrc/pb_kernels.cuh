@@ -1253,64 +1253,38 @@ __global__ void k_selftest_division(unsigned long long n_samples, unsigned long 
 }
 
 // Block-level formulation (round 2): a block of 8 warps draws clusters from the ticket counter.  Warps 1-7 scan the
-// cluster's segment chunk by chunk and compact the members' coordinates (ascending point order) and what the replay needs
-// of their running counts into one half of a double buffer while warp 0 replays the recurrence over the other half — the
-// chain never waits for global memory.
-//
-// What bounds the replaying warp (MEASURED with clock64, tools/microbench/centres.cu): a dependent fp32 operation costs
-// ~5.2 cycles and an instruction ~2 cycles of the warp's issue: cycles per member ~ max(5.2 x chain operations, 2 x
-// instructions).  The one-correction chain with its proof inline (5 chain operations, 16 instructions) runs at 26.5 cycles
-// per member.  The FAST replay below has a chain of THREE operations and SEVEN instructions per member:
-//   - the reciprocal is split as yh + yl (~48 bits): q = fma(a, yh, t) with t ~ a*yl is RN(a/n) except when a/n lies within
-//     ~2^-40 of a rounding boundary; t = fma(-D, yl, (x - c)*yl) is computed next to a = x - M from D ~ M - c, a second
-//     recurrence relative to an origin c near the cluster (t only needs ~17 bits; working relative to c keeps the
-//     cancellation of x*yl - M*yl out of it: shifted coordinates collapse onto the instance centres, |a| << |x|);
-//   - yh, yl and (x - c)*yl come from the gather warps;
-//   - the PROOF is not in the replaying warp's stream at all: it overwrites x with a and (x - c)*yl with q, and while it
-//     replays the next chunk the gather warps check every member of the finished one, lane-parallel, with the Markstein step
-//     q2 = fma(fma(-n, q, a), yh, q): q is faithful, so q2 is RN(a/n), and q2 == q (bitwise) with |a| inside div_by_count's
-//     range (or zero) proves the member.
-// A chunk that fails its proof (about one in 10^3) restarts the pipeline at that chunk: it is gathered again, replayed with
-// the one-correction chain / div.rn.f32 (ctr_chain, exact unconditionally), and the fast replay resumes behind it.
+// cluster's segment chunk by chunk and compact the members' coordinates (ascending point order) and the reciprocals of
+// their running counts into one half of a double buffer while warp 0 replays the recurrence over the other half — the
+// chain never waits for global memory, and the scan of a 27 k-point segment takes 25 trips instead of 215.
 constexpr int kCtrGatherWarps = 7;
-constexpr int kCtrPer = 3;                                       // points per gather lane and chunk
-constexpr int kCtrChunkPts = kCtrGatherWarps * 32 * kCtrPer;   // points scanned per chunk
+constexpr int kCtrChunkPts = kCtrGatherWarps * 160;   // points scanned per chunk (5 per gather lane)
 
 struct alignas(16) CtrSmem {
-    float2 p2[2][3][kCtrChunkPts];   // (x, RN(RN(x - c) * yl)) of every member; after a fast replay: (a = x - M, q)
-    float2 p1[2][kCtrChunkPts];      // (-1, -yl): the multiplier pair of the packed step, yl = RN(1/n - yh)
-    float rcp[2][kCtrChunkPts];      // yh = RN(1/n) of every member's running count n
-    float pad[16];                   // the fast replay prefetches up to twelve elements past the end of a half
-    float corig[2][4];               // origin c of each half
-    float Msave[2][4];               // running mean at the start of the half's last replay
-    int cntsave[2];                  // members before it
-    int proof[2];                    // the half was replayed fast and waits for its proof
+    float buf[2][3][kCtrChunkPts];
+    float rcp[2][kCtrChunkPts];
     int wcount[kCtrGatherWarps];
-    int wbad[kCtrGatherWarps];
     int m[2];       // members in each half
-    int fail;       // chunk whose proof failed (-1: none)
     int cluster;    // ticket
 };
 
 __device__ __forceinline__ void ctr_gather(CtrSmem &sm, int half, int ub, int e, int local, int cnt_before,
                                            const int *__restrict__ cluster_id, const float *__restrict__ x,
-                                           const float *__restrict__ y, const float *__restrict__ z, float cx, float cy,
-                                           float cz) {
-    // called by warps 1..7; warp gw owns points [ub + gw*32*kCtrPer, +32*kCtrPer); (cx, cy, cz) = origin of this half
+                                           const float *__restrict__ y, const float *__restrict__ z) {
+    // called by warps 1..7; warp gw owns points [ub + gw*160, +160)
     const int lane = lane_id(), gw = (threadIdx.x >> 5) - 1;
-    int id[kCtrPer];
-    float vx[kCtrPer], vy[kCtrPer], vz[kCtrPer];
-    unsigned mk[kCtrPer];
+    int id[5];
+    float vx[5], vy[5], vz[5];
+    unsigned mk[5];
     int total = 0;
 #pragma unroll
-    for (int j = 0; j < kCtrPer; j++) {
-        int u = ub + gw * 32 * kCtrPer + j * 32 + lane;
+    for (int j = 0; j < 5; j++) {
+        int u = ub + gw * 160 + j * 32 + lane;
         bool ok = u < e;
         id[j] = ok ? cluster_id[u] : -2;
         vx[j] = ok ? x[u] : 0.f, vy[j] = ok ? y[u] : 0.f, vz[j] = ok ? z[u] : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < kCtrPer; j++) {
+    for (int j = 0; j < 5; j++) {
         mk[j] = __ballot_sync(kFull, id[j] == local);
         total += __popc(mk[j]);
     }
@@ -1324,125 +1298,30 @@ __device__ __forceinline__ void ctr_gather(CtrSmem &sm, int half, int ub, int e,
         all += c;
     }
 #pragma unroll
-    for (int j = 0; j < kCtrPer; j++) {
+    for (int j = 0; j < 5; j++) {
         if (id[j] == local) {
             int o = off + __popc(mk[j] & ((1u << lane) - 1u));
-            const float fn = (float)(cnt_before + o + 1), yh = __frcp_rn(fn);
-            const float yl = __fmul_rn(__fmaf_rn(-fn, yh, 1.f), yh);   // (1 - n*yh) is exact; 1/n - yh = (1 - n*yh)/n
-            sm.p2[half][0][o] = make_float2(vx[j], __fmul_rn(__fsub_rn(vx[j], cx), yl));
-            sm.p2[half][1][o] = make_float2(vy[j], __fmul_rn(__fsub_rn(vy[j], cy), yl));
-            sm.p2[half][2][o] = make_float2(vz[j], __fmul_rn(__fsub_rn(vz[j], cz), yl));
-            sm.p1[half][o] = make_float2(-1.f, -yl);
-            sm.rcp[half][o] = yh;
+            sm.buf[half][0][o] = vx[j], sm.buf[half][1][o] = vy[j], sm.buf[half][2][o] = vz[j];
+            sm.rcp[half][o] = __frcp_rn((float)(cnt_before + o + 1));
         }
         off += __popc(mk[j]);
     }
-    if (gw == 0 && lane == 0)
-        sm.m[half] = all, sm.proof[half] = 0, sm.corig[half][0] = cx, sm.corig[half][1] = cy, sm.corig[half][2] = cz;
+    if (gw == 0 && lane == 0) sm.m[half] = all;
     asm volatile("bar.sync 1, 224;" ::: "memory");   // wcount may be rewritten by the next chunk only after everyone read it
 }
 
-// warps 1..7: proof of a half that was replayed fast (see above); uniform result over the seven warps
-__device__ __forceinline__ bool ctr_prove(CtrSmem &sm, int half) {
-    const int lane = lane_id(), gw = (threadIdx.x >> 5) - 1;
-    const int fill = sm.m[half], cnt0 = sm.cntsave[half];
-    bool bad = false;
-    for (int i = gw * 32 + lane; i < fill; i += kCtrGatherWarps * 32) {
-        const float fn = (float)(cnt0 + i + 1), yh = sm.rcp[half][i];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float2 aq = sm.p2[half][k][i];
-            const float a = aq.x, q = aq.y;
-            const float q2 = __fmaf_rn(__fmaf_rn(-fn, q, a), yh, q);
-            const float aa = fabsf(a);
-            bad |= (__float_as_uint(q2) != __float_as_uint(q)) | (!(aa > 1e-30f && aa < 1e30f) && a != 0.f);
-        }
-    }
-    const bool wb = __any_sync(kFull, bad);
-    if (lane == 0) sm.wbad[gw] = wb;
-    asm volatile("bar.sync 1, 224;" ::: "memory");
-    int anyb = 0;
-#pragma unroll
-    for (int k = 0; k < kCtrGatherWarps; k++) anyb |= sm.wbad[k];
-    asm volatile("bar.sync 1, 224;" ::: "memory");   // wbad may be rewritten only after everyone read it
-    return anyb == 0;
-}
-
-// warp 0, fast replay of one half: lane l < 3 carries coordinate l (the other lanes idle along on coordinate 0 and store
-// nothing).  (M, D) live in ONE packed fp32x2 register pair: per member
-//     FFMA2  (a, t) = (M, D) * (-1, -yl) + (x, (x - c)*yl)        a = RN(x - M) exactly (the product by -1 is exact)
-//     FFMA   q = fma(a, yh, t)
-//     FADD2  (M, D) += (q, q)
-// three instructions, a chain of three operations: 12.2 cycles per member for a lone warp (tools/microbench/fplat.cu; with M
-// and D as two scalar recurrences the second FADD trails the first by the pipe's two issue cycles: 16.5; the
-// one-correction chain: 20.2, and 26.5 with its proof inline).  Overwrites p2 with (a, q) for the proof.
-__device__ __forceinline__ void ctr_fast(CtrSmem &sm, int half, int fill, int &cnt, float &M, int coord, bool store) {
-    float2 *p2 = sm.p2[half][coord];
-    const float2 *p1 = sm.p1[half];
-    const float *yhp = sm.rcp[half];
-    unsigned long long MD = pack2(M, __fsub_rn(M, sm.corig[half][coord]));
-    auto step = [&](unsigned long long vx, unsigned long long ny, float yh) -> unsigned long long {
-        float a, t;
-        unpack2(fma2(MD, ny, vx), a, t);
-        const float q = __fmaf_rn(a, yh, t);
-        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(MD) : "l"(MD), "l"(pack2(q, q)));
-        return pack2(a, q);
-    };
-    // blocks of four members, operands prefetched two blocks ahead (ptxas sinks a shared load towards its first use)
-    // (no clamping of the prefetch addresses: every array of CtrSmem is followed by at least 96 bytes of the same struct,
-    // the up to twelve elements read past a half's end are never used, and the integer instructions of a clamp would sit
-    // between the chain's operations — a lone warp issues in order)
-    auto ldp = [&](const float2 *p, int i) { return *reinterpret_cast<const ulonglong2 *>(p + i); };
-    auto ldy = [&](int i) { return *reinterpret_cast<const float4 *>(yhp + i); };
-    int t = 0;
-    ulonglong2 va = ldp(p2, 0), vb = ldp(p2, 2), na = ldp(p1, 0), nb = ldp(p1, 2);
-    float4 y4 = ldy(0);
-    ulonglong2 va1 = ldp(p2, 4), vb1 = ldp(p2, 6), na1 = ldp(p1, 4), nb1 = ldp(p1, 6);
-    float4 y41 = ldy(4);
-    for (; t + 4 <= fill; t += 4) {
-        const ulonglong2 va2 = ldp(p2, t + 8), vb2 = ldp(p2, t + 10), na2 = ldp(p1, t + 8), nb2 = ldp(p1, t + 10);
-        const float4 y42 = ldy(t + 8);
-        // (a, q) is the register pair the step computed in — a in place, q where t was: one 8-byte store per member and no
-        // register moves (a 16-byte store of two members needs four adjacent registers, i.e. four MOVs in the chain's stream)
-        const unsigned long long o0 = step(va.x, na.x, y4.x);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t) = o0;
-        const unsigned long long o1 = step(va.y, na.y, y4.y);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t + 1) = o1;
-        const unsigned long long o2 = step(vb.x, nb.x, y4.z);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t + 2) = o2;
-        const unsigned long long o3 = step(vb.y, nb.y, y4.w);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t + 3) = o3;
-        va = va1, vb = vb1, na = na1, nb = nb1, y4 = y41;
-        va1 = va2, vb1 = vb2, na1 = na2, nb1 = nb2, y41 = y42;
-    }
-    if (t < fill) {
-        const unsigned long long o = step(va.x, na.x, y4.x);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t) = o;
-    }
-    if (t + 1 < fill) {
-        const unsigned long long o = step(va.y, na.y, y4.y);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t + 1) = o;
-    }
-    if (t + 2 < fill) {
-        const unsigned long long o = step(vb.x, nb.x, y4.z);
-        if (store) *reinterpret_cast<unsigned long long *>(p2 + t + 2) = o;
-    }
-    float Dd;
-    unpack2(MD, M, Dd);
-    cnt += fill;
-}
-
-// warp 0, SAFE replay of one half (exact unconditionally): the one-correction quotient chain with its proof inline, and
-// div.rn.f32 when that proof fails.  Returns 2 / 3.
+// lanes 0..2 of the calling warp replay x, y, z side by side over one half of the buffer
+// returns how the half was settled (2: one-correction quotient chain, 3: div.rn.f32)
 __device__ __forceinline__ int ctr_chain(const CtrSmem &sm, int half, int fill, int &cnt, float &M, int coord) {
-    const float2 *src = sm.p2[half][coord];   // .x = the coordinate (the half is freshly gathered when this runs)
+    const float *src = sm.buf[half][coord];
     const float *myrcp = sm.rcp[half];
     bool fast = cnt + fill < (1 << 24) - 1;
     if (fast) {
-        // The recurrence runs on the ONE-correction quotient q1 (FSUB, FMUL, 2 FFMA, FADD on the chain); the second
-        // Markstein correction q2 = RN(a/n) is computed next to it, off the chain, and compared: if they ever differ (rare: q1
-        // is already the correctly rounded quotient almost always), or the range guard of div_by_count trips, the half is
-        // replayed with div.rn.f32.  Results are bit-identical to M += (x - M) / n with IEEE division either way.
+        // The recurrence runs on the ONE-correction quotient q1 (FSUB, FMUL, 2 FFMA, FADD on the chain: 5 dependent
+        // operations per member instead of 7); the second Markstein correction q2 = RN(a/n) is computed next to it, off
+        // the chain, and compared: if they ever differ (rare: q1 is already the correctly rounded quotient almost always),
+        // or the range guard of div_by_count trips, the half is replayed with div.rn.f32.  Results are bit-identical to
+        // M += (x - M) / n with IEEE division either way.
         float M0 = M;
         bool odd = false;
         auto step = [&](float v, float y, float fn) {
@@ -1456,11 +1335,24 @@ __device__ __forceinline__ int ctr_chain(const CtrSmem &sm, int half, int fill, 
             float aa = fabsf(a);
             odd |= (q2 != q1) | (!(aa > 1e-30f && aa < 1e30f) && a != 0.f);
         };
+        // blocks of four members; the NEXT block's coordinates and reciprocals are fetched (two 16-byte shared loads) while
+        // this one runs, so the chain never waits for shared memory (counts stay below 2^24: float increments are exact)
         float fn = (float)cnt;
-        for (int t = 0; t < fill; t++) {
-            fn += 1.f;
-            step(src[t].x, myrcp[t], fn);
+        int t = 0;
+        float4 v4 = *reinterpret_cast<const float4 *>(src), y4 = *reinterpret_cast<const float4 *>(myrcp);
+        for (; t + 4 <= fill; t += 4) {
+            const int tn = min(t + 4, kCtrChunkPts - 4);
+            const float4 nv = *reinterpret_cast<const float4 *>(src + tn), ny = *reinterpret_cast<const float4 *>(myrcp + tn);
+            step(v4.x, y4.x, fn + 1.f);
+            step(v4.y, y4.y, fn + 2.f);
+            step(v4.z, y4.z, fn + 3.f);
+            step(v4.w, y4.w, fn + 4.f);
+            fn += 4.f;
+            v4 = nv, y4 = ny;
         }
+        if (t < fill) step(v4.x, y4.x, fn + 1.f);
+        if (t + 1 < fill) step(v4.y, y4.y, fn + 2.f);
+        if (t + 2 < fill) step(v4.z, y4.z, fn + 3.f);
         if (!odd) {
             cnt += fill;
             return 2;
@@ -1468,7 +1360,7 @@ __device__ __forceinline__ int ctr_chain(const CtrSmem &sm, int half, int fill, 
         M = M0;
     }
     for (int t = 0; t < fill; t++) {
-        float v = src[t].x;
+        float v = src[t];
         cnt++;
         M = __fadd_rn(M, __fdiv_rn(__fsub_rn(v, M), (float)cnt));
     }
@@ -1482,18 +1374,16 @@ __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const 
                                               const float *__restrict__ y, const float *__restrict__ z,
                                               float *__restrict__ center, int *__restrict__ next_cluster, CtrSmem &sm,
                                               float *__restrict__ center_head = nullptr, int n_head = 0,
-                                              unsigned long long *__restrict__ stats = nullptr, int force_fail = 0) {
+                                              unsigned long long *__restrict__ stats = nullptr) {
     // center_head: optional second copy of the first n_head centres (the small-call kernel keeps it next to its result
     // block so that one read-back carries everything)
-    // stats (profiling runs): [0] chunks replayed, [1] of them in safe mode (after a failed proof, or counts near 2^24),
-    // [2] cycles warp 0 spent replaying, [3] cycles warp 1 spent proving + gathering (summed over all clusters)
-    // force_fail (tests): every force_fail-th proof is declared failed, to exercise the restart path
+    // stats (profiling runs): [0] (half, coordinate) replays run, [1] of them replayed with div.rn.f32, [2] cycles warp 0
+    // spent replaying, [3] cycles warp 1 spent gathering (summed over all clusters)
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     const int coord = lane < 3 ? lane : 0;
-    int proofs = 0;   // proofs this block has run (uniform over the gather warps)
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) sm.cluster = atomicAdd(next_cluster, 1), sm.fail = -1;
+        if (threadIdx.x == 0) sm.cluster = atomicAdd(next_cluster, 1);
         __syncthreads();
         // the cluster list is walked twice: clusters of LARGE segments first (their serial replay is the kernel's critical path
         // and must not start last), the others afterwards
@@ -1505,76 +1395,26 @@ __device__ __forceinline__ void centres_block(int K, const SegArrays &sg, const 
         const int b = sg.start[s], e = sg.start[s + 1];
         if ((e - b >= kCtrBigSegment) != (k2 < K)) continue;  // uniform: every thread reads the same sm.cluster
         const int nchunks = (e - b + kCtrChunkPts - 1) / kCtrChunkPts;
-        const float s0x = x[b], s0y = y[b], s0z = z[b];   // origin of the first two halves: the segment's first point
         float M = 0.f;   // lane c < 3 of warp 0 carries coordinate c
         int cnt = 0;     // members replayed so far (warp 0) / gathered so far (warps 1..7)
-        int start = 0, safe_chunk = -1;
-        while (true) {   // one pass per (re)start of the pipeline; a restart follows a failed proof (rare)
-            if (wid > 0) ctr_gather(sm, start & 1, b + start * kCtrChunkPts, e, local, cnt, cluster_id, x, y, z, s0x, s0y, s0z);
-            int gathered = cnt, failed = -1;
-            for (int c = start; c <= nchunks; c++) {
-                __syncthreads();                      // half c&1 is complete; the proof of chunk c-2 is in
-                failed = sm.fail;
-                if (failed >= 0 || c == nchunks) break;
-                const int h = c & 1, fill = sm.m[h];
-                const long long tc0 = stats ? clock64() : 0;
-                if (wid == 0) {
-                    if (lane < 3) sm.Msave[h][lane] = M;
-                    if (lane == 0) sm.cntsave[h] = cnt;
-                    const bool fastable = c != safe_chunk && cnt + fill < (1 << 24) - 1;
-                    if (fastable) {
-                        ctr_fast(sm, h, fill, cnt, M, coord, lane < 3);
-                        if (lane == 0) sm.proof[h] = 1;
-                    } else {
-                        ctr_chain(sm, h, fill, cnt, M, coord);
-                    }
-                    if (stats && lane == 0) {
-                        atomicAdd(stats, 1ull);
-                        if (!fastable) atomicAdd(stats + 1, 1ull);
-                        atomicAdd(stats + 2, (unsigned long long)(clock64() - tc0));
-                    }
-                } else {
-                    gathered += fill;
-                    bool ok = true;
-                    if (c > start && sm.proof[h ^ 1]) {   // chunk c-1 was replayed fast during the previous trip
-                        ok = ctr_prove(sm, h ^ 1);
-                        proofs++;
-                        if (force_fail > 0 && proofs % force_fail == 0) ok = false;
-                        if (!ok && threadIdx.x == 32) sm.fail = c - 1;
-                    }
-                    if (ok && c + 1 < nchunks) {
-                        // origin of the new half: the running mean as it stood at the start of chunk c - 1 (published before
-                        // the barrier above), the segment's first point before that
-                        const bool seeded = c - 1 >= start;
-                        ctr_gather(sm, h ^ 1, b + (c + 1) * kCtrChunkPts, e, local, gathered, cluster_id, x, y, z,
-                                   seeded ? sm.Msave[h ^ 1][0] : s0x, seeded ? sm.Msave[h ^ 1][1] : s0y, seeded ? sm.Msave[h ^ 1][2] : s0z);
-                    }
-                    if (stats && threadIdx.x == 32) atomicAdd(stats + 3, (unsigned long long)(clock64() - tc0));
+        if (wid > 0) ctr_gather(sm, 0, b, e, local, 0, cluster_id, x, y, z);
+        int gathered = 0;
+        for (int c = 0; c < nchunks; c++) {
+            __syncthreads();                      // half c&1 is complete
+            const int fill = sm.m[c & 1];
+            const long long tc0 = stats ? clock64() : 0;
+            if (wid == 0) {
+                const int tier = ctr_chain(sm, c & 1, fill, cnt, M, coord);
+                if (stats && lane < 3 && fill > 0) {
+                    atomicAdd(stats, 1ull);
+                    if (tier > 2) atomicAdd(stats + 1, 1ull);
                 }
+                if (stats && lane == 0) atomicAdd(stats + 2, (unsigned long long)(clock64() - tc0));
+            } else {
+                gathered += fill;
+                if (c + 1 < nchunks) ctr_gather(sm, (c + 1) & 1, b + (c + 1) * kCtrChunkPts, e, local, gathered, cluster_id, x, y, z);
+                if (stats && threadIdx.x == 32) atomicAdd(stats + 3, (unsigned long long)(clock64() - tc0));
             }
-            if (failed < 0) {
-                // the last chunk still waits for its proof (the loop above proves chunk c-1 during trip c)
-                const int hl = (nchunks - 1) & 1;
-                if (nchunks > start && sm.proof[hl]) {   // uniform: written before the last barrier
-                    if (wid > 0) {
-                        bool ok = ctr_prove(sm, hl);
-                        proofs++;
-                        if (force_fail > 0 && proofs % force_fail == 0) ok = false;
-                        if (!ok && threadIdx.x == 32) sm.fail = nchunks - 1;
-                    }
-                    __syncthreads();
-                    failed = sm.fail;
-                }
-                if (failed < 0) break;
-            }
-            // restart at the failed chunk: state as it was when that chunk began, the chunk itself in safe mode
-            __syncthreads();   // everyone has read sm.fail and the saved state stays untouched until here
-            start = failed, safe_chunk = failed;
-            M = sm.Msave[failed & 1][coord];
-            cnt = sm.cntsave[failed & 1];
-            __syncthreads();
-            if (threadIdx.x == 0) sm.fail = -1;
-            __syncthreads();
         }
         if (wid == 0 && lane < 3) {
             center[3 * kk + lane] = M;
@@ -1587,9 +1427,9 @@ __global__ void __launch_bounds__(256)
 k_centres(const int *__restrict__ d_K, SegArrays sg, const int *__restrict__ clt_seg,
           const int *__restrict__ cluster_id, const float *__restrict__ x, const float *__restrict__ y,
           const float *__restrict__ z, float *__restrict__ center, int *__restrict__ next_cluster,
-          unsigned long long *__restrict__ stats, int force_fail) {
+          unsigned long long *__restrict__ stats) {
     __shared__ CtrSmem sm;
-    centres_block(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, sm, nullptr, 0, stats, force_fail);
+    centres_block(*d_K, sg, clt_seg, cluster_id, x, y, z, center, next_cluster, sm, nullptr, 0, stats);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,7 +60,6 @@ struct SmallArgs {
     int *root0;                   // root of every point in the P2 forest
     unsigned long long *best64;   // P8: per point, min over candidates of (distance bits << 32 | ~index)
     int *seg_of, *parent, *flag, *gid_at, *raw_label, *raw_count, *rep, *keep, *kscan, *clt_seg;
-    int ctr_force_fail;           // P9: test knob of the centre replay (centres_block)
     int deg_slices;               // P1: slices per query group (0: automatic)
     int *deg_acc;                 // P1: partial neighbour counts of the sliced form (zero-initialised)
     int tree_cap;                 // P3 works on the tree graph when the P2 forest has at most this many trees (<= 64; 0: never)
@@ -533,7 +532,7 @@ k_small(SmallArgs a) {
     // merge through atomicMin on (distance bits << 32 | ~index): smallest distance first, then the largest index.  The
     // slices are cut so that the task list fills the grid about once.
     if (a.assign_lp) {
-        float4 *stage = reinterpret_cast<float4 *>(&s_ctr.p2[0][0][0]) + (threadIdx.x >> 5) * 32;   // 32 candidates per warp
+        float4 *stage = reinterpret_cast<float4 *>(&s_ctr.buf[0][0][0]) + (threadIdx.x >> 5) * 32;   // 32 candidates per warp
         int t0[kMaxSeg + 1];
         int nt = 0, groups = 0;
         for (int s = 0; s < S; s++) groups += (__ldcg(a.lpcnt + s) + 31) >> 5;
@@ -589,7 +588,7 @@ k_small(SmallArgs a) {
     grid.sync();
     stamp(a, 9);
     // ---------------- P9: centres --------------------------------------------------------------------------------------
-    pb::centres_block(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_ctr, a.center_head, kCentreHead, nullptr, a.ctr_force_fail);
+    pb::centres_block(*d_K, a.sg, a.clt_seg, a.cluster_id, a.x, a.y, a.z, a.center, a.scal + 9, s_ctr, a.center_head, kCentreHead);
     stamp(a, 10);   // end of block 0's own centres (the last phase is not followed by a barrier)
 }
 

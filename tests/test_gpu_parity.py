@@ -299,26 +299,3 @@ def test_small_call_kernel_variants(monkeypatch, env):
         assert took > 10
     finally:
         c2.close()
-
-
-@pytest.mark.parametrize("every", [1, 3], ids=["every-proof-fails", "every-third-proof-fails"])
-def test_centre_replay_restart_path(monkeypatch, every):
-    """The fast centre replay is proved chunk by chunk by the gather warps; a failed proof restarts the pipeline at that
-    chunk in safe mode.  Genuine failures are rare (about one chunk in 10^3), so the test forces them
-    (PB_CTR_FORCE_FAIL): centres must stay bit-identical to the oracle on multi-chunk clusters, through the cell-grid
-    pipeline and through the small-call kernel."""
-    from oracle import pb_oracle as po
-    from pbnet_b200 import scenes
-    from pbnet_b200.cluster import Context
-    monkeypatch.setenv("PB_CTR_FORCE_FAIL", str(every))
-    c2 = Context(0)
-    try:
-        sc = scenes.make_scene(77, 60000)
-        for small in (1, 0):
-            c2.set_small_calls(small)
-            for c in scenes.class_calls(sc, 1):
-                want = po.oracle_binary_cluster(c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"], H.R18, H.M18)
-                got = H.run_cuda(c2, c["xyz_shift"], c["xyz_orig"], c["sem"], c["seg_counts"])
-                assert H.diff_report(got, want) == [], f"class {c['sem_id']} small={small}"
-    finally:
-        c2.close()

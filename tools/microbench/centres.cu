@@ -53,7 +53,7 @@ int main() {
             for (int rep = 0; rep < 5; rep++) {
                 cudaMemset(dticket, 0, 4), cudaMemset(dstats, 0, 64);
                 cudaEventRecord(e0);
-                pb::k_centres<<<4, 256>>>(dK, sg, dclt, did, dx, dy, dz, dc, dticket, rep == 4 ? dstats : nullptr, 0);
+                pb::k_centres<<<4, 256>>>(dK, sg, dclt, did, dx, dy, dz, dc, dticket, rep == 4 ? dstats : nullptr);
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);
                 float ms;
@@ -65,7 +65,7 @@ int main() {
             cudaMemcpy(hc, dc, 12, cudaMemcpyDeviceToHost);
             const int chunks = (N + pb::kCtrChunkPts - 1) / pb::kCtrChunkPts;
             printf("N %7d members %7d chunks %4d: %8.1f us = %6.2f ns/member, %6.2f us/chunk; replay cycles/member %.1f gather cycles/chunk %.0f "
-                   "chunks replayed %llu, in safe mode %llu  exact %d\n",
+                   "halves %llu replayed %llu  exact %d\n",
                    N, members, chunks, best * 1e3, best * 1e6 / members, best * 1e3 / chunks, (double)hs[2] / members,
                    (double)hs[3] / chunks, hs[0], hs[1], (int)(hc[0] == M[0] && hc[1] == M[1] && hc[2] == M[2]));
             cudaFree(dx), cudaFree(dy), cudaFree(dz), cudaFree(did), cudaFree(dc), cudaFree(dstart), cudaFree(didb), cudaFree(dclt), cudaFree(dK), cudaFree(dticket), cudaFree(dstats);

@@ -24,4 +24,4 @@ for prof in (False, True):
         torch.cuda.synchronize(); dd = (time.perf_counter() - t0) / 20 * 1e6
         st = {k: round(v * 1e3) for k, v in ctx.stage_ms().items()} if prof else {}
         print(f"n={len(sem)} prof={prof} host-arrays {dt:.0f} us  device-arrays {dd:.0f} us launches {ctx.last_launch_count} stages(us) {st} sum {sum(st.values())}"
-              + (f" centre chunks {ctx.counters()['centre_chunks']} safe {ctx.counters()['centre_chunks_safe']} replay cycles {ctx.counters()['centre_replay_cycles']} gather cycles {ctx.counters()['centre_gather_cycles']} clusters {out['n_clusters']} sizes {np.bincount(out['cluster_id'][out['cluster_id'] >= 0] if not hasattr(out['cluster_id'], 'cpu') else out['cluster_id'].cpu().numpy()[out['cluster_id'].cpu().numpy() >= 0]).tolist()}" if prof else ""))
+              + (f" centre halves {ctx.counters()['centre_halves']} replayed {ctx.counters()['centre_halves_replayed']} replay cycles {ctx.counters()['centre_replay_cycles']} gather cycles {ctx.counters()['centre_gather_cycles']} clusters {out['n_clusters']} sizes {np.bincount(out['cluster_id'][out['cluster_id'] >= 0] if not hasattr(out['cluster_id'], 'cpu') else out['cluster_id'].cpu().numpy()[out['cluster_id'].cpu().numpy() >= 0]).tolist()}" if prof else ""))
